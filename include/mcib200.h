@@ -1,0 +1,269 @@
+/*
+ * mcib200.h — C ABI of libmcib200.so: the B200 (sm_100a) sampling-and-accumulation
+ * hot path of MCIntegration.jl (VEGAS / VEGAS-MC / MCMC `montecarlo` drivers plus
+ * the adaptive maps of src/distribution).
+ *
+ * This is the drop-in boundary.  Every entry point states which reference
+ * interface it replaces (paths relative to the reference repo, v0.4.2).
+ * A Julia host binds these with `ccall((:mci_xxx, "libmcib200"), ...)`; see
+ * INTEGRATION.md and julia/MCIntegrationB200.jl.
+ *
+ * Conventions
+ *   - plain C, `extern "C"`, no C++/torch types in any signature;
+ *   - every pointer argument is HOST memory owned by the caller; the callee
+ *     copies what it needs before returning and never frees caller memory;
+ *   - return value 0 = MCI_OK, negative = error; text via mci_last_error();
+ *   - no exception ever crosses the ABI, no callback into the host: the
+ *     integrand and the `measure` rule run on the device and are selected by
+ *     id (mci_integrand_id / mci_measure_kind);
+ *   - a handle is bound to one GPU and is not thread-safe; distinct handles
+ *     are independent (one per GPU / rank);
+ *   - there is NO CPU fallback: without a CUDA device mci_create() fails with
+ *     MCI_ERR_NO_DEVICE.
+ *   - all arrays are little-endian f64 / i32 / u64, C row-major.
+ */
+#ifndef MCIB200_H
+#define MCIB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCI_ABI_VERSION 1
+
+/* ---- limits of the POD problem description ------------------------------ */
+#define MCI_MAX_TOPVAR 16    /* top-level variables (`config.var` tuple, configuration.jl:40) */
+#define MCI_MAX_LEAF 32      /* leaf maps over all top-level variables                  */
+#define MCI_MAX_INTEGRAND 8  /* Ni, without the normalisation integrand                 */
+#define MCI_MAX_SLOT 24      /* max dof of one pool variable on the device              */
+#define MCI_MAX_USERDATA 32  /* doubles                                                 */
+#define MCI_MAX_OBS 64       /* total observable length (sum of obs_len)                */
+
+/* ---- error codes ------------------------------------------------------- */
+enum {
+  MCI_OK = 0,
+  MCI_ERR_INVALID = -1,     /* bad argument / problem description (Julia @assert sites)  */
+  MCI_ERR_NO_DEVICE = -2,   /* no CUDA device or kernel image not loadable: no fallback  */
+  MCI_ERR_CUDA = -3,        /* CUDA runtime error                                        */
+  MCI_ERR_NUMERIC = -4,     /* non-finite weight / non-positive block normalisation
+                               (main.jl:269-271, variable.jl:212-213, common.jl:71,79)   */
+  MCI_ERR_UNSUPPORTED = -5, /* layout/integrand combination not built into this library  */
+  MCI_ERR_COMM = -6,        /* NCCL failure                                              */
+  MCI_ERR_MCMC_START = -7   /* no non-zero start weight found (mcmc/montecarlo.jl:109)   */
+};
+
+/* solver: `solver::Symbol` kwarg of integrate (main.jl:72, dispatch main.jl:253-264) */
+enum { MCI_SOLVER_VEGAS = 0, MCI_SOLVER_VEGASMC = 1, MCI_SOLVER_MCMC = 2 };
+
+/* leaf kinds: Continuous (variable.jl:87-153) / Discrete (variable.jl:272-325) */
+enum { MCI_LEAF_CONTINUOUS = 0, MCI_LEAF_DISCRETE = 1 };
+
+/*
+ * Built-in integrands.  A Julia closure cannot run on the device, so the
+ * integrand `f(x, c)` / `f(idx, x, c)` (main.jl:25-33) becomes a device
+ * function selected by id.  Each id fixes the variable layout it reads
+ * (validated in mci_create).  `userdata` replaces `config.userdata`.
+ */
+enum mci_integrand_id {
+  MCI_F_GAUSS_ND = 1,       /* (2pi)^(-d/2) exp(-|x|^2/2), one Continuous pool, dof=[[d]]     (BASELINE C2) */
+  MCI_F_LOG_OVER_SQRT = 2,  /* log(x)/sqrt(x), pool, dof=[[1]]        test/montecarlo.jl:129-134 (C1)      */
+  MCI_F_GENZ_CORNER_POOL = 3, /* (1+sum c_i x_i)^-(d+1), pool dof=[[d]], c_i=userdata[i]         (C3 A)   */
+  MCI_F_GENZ_CORNER_COMP = 4, /* same, d-leaf CompositeVar, dof=[[1]]                             (C3 B)   */
+  MCI_F_BUBBLE = 5,         /* example/bubble.jl:50-75, vars (R,theta,phi,T,Ext)                  (C4)     */
+  MCI_F_PRODUCT_4 = 6,      /* f_k = prod_i (1+a_k (x_i-1/2)), 4 integrands, pool dof=[[d]]x4     (C5)     */
+  MCI_F_SPHERE1 = 7,        /* x1^2+x2^2<1, pool dof=[[2]]            test/montecarlo.jl:4-9               */
+  MCI_F_SPHERE2 = 8,        /* circle + sphere, dof=[[2],[3]]         test/montecarlo.jl:19-49             */
+  MCI_F_DISCRETE_X = 9,     /* f = x[1], Discrete leaf               test/montecarlo.jl:104-111           */
+  MCI_F_DISCRETE2_CONST = 10, /* f = 1, composite of two Discrete    test/montecarlo.jl:113-120           */
+  MCI_F_LATTICE_POOL = 11,  /* 1/(1-cos x cos y cos z)/pi^3, pool dof=[[3]]   test/montecarlo.jl:136-147  */
+  MCI_F_LATTICE_COMP = 12,  /* same with CompositeVar(X,Y,Z), dof=1           test/montecarlo.jl:149-164  */
+  MCI_F_HYPERSPHERE3 = 13,  /* 3 nested unit balls, dof=[[2],[3],[4]] test/montecarlo.jl:200-216         */
+  MCI_F_POLY3 = 14,         /* (x, x^2, x^3), dof=[[1],[1],[1]]       test/thread.jl                       */
+  MCI_F_X2_PLUS_Y2 = 15     /* x1^2+x2^2, pool dof=[[2]]              main.jl:64, vegas/montecarlo.jl:69   */
+};
+
+/* `measure` kwarg (main.jl:35-37, 83).  Default = obs[i] += relw[i]. */
+enum mci_measure_kind {
+  MCI_MEASURE_DEFAULT = 0,
+  MCI_MEASURE_BIN_BY_DISCRETE = 1 /* obs[0][Ext-lower] += relw[0]; example/bubble.jl:81-84.
+                                     The binning leaf is the LAST leaf of the problem.      */
+};
+
+/* one leaf map (Continuous ctor kwargs variable.jl:137, Discrete ctor :299) */
+typedef struct mci_leaf_t {
+  int32_t kind;    /* MCI_LEAF_*                                                    */
+  int32_t nbins;   /* Continuous: number of increments = length(grid)-1 (`ninc`-1,
+                      variable.jl:147); Discrete: upper-lower+1                     */
+  int32_t adapt;   /* 0/1                                                           */
+  int32_t lower_i; /* Discrete: `lower`                                             */
+  double lower;    /* Continuous bounds                                             */
+  double upper;
+  double alpha;    /* learning rate of train! (variable.jl:206-239, :369-382)       */
+} mci_leaf_t;
+
+/*
+ * POD mirror of the Configuration fields the solver loops consume
+ * (configuration.jl:37-60) plus the integrate() kwargs that reach the hot
+ * loop (main.jl:71-90).
+ */
+typedef struct mci_problem_t {
+  int32_t solver;          /* MCI_SOLVER_*                                               */
+  int32_t integrand_id;    /* enum mci_integrand_id                                      */
+  int32_t measure_kind;    /* enum mci_measure_kind                                      */
+  int32_t n_integrand;     /* config.N (without the normalisation integrand)             */
+  int32_t n_topvar;        /* length(config.var)                                         */
+  int32_t n_leaf;          /* sum of leaves                                              */
+  const int32_t *topvar_nleaf;  /* [n_topvar] 1 for Continuous/Discrete, k for CompositeVar */
+  const int32_t *topvar_offset; /* [n_topvar] `var.offset` (informational: device slots are compact) */
+  const mci_leaf_t *leaf;  /* [n_leaf] in top-level order then leaf order                */
+  const int32_t *dof;      /* [n_integrand][n_topvar] row-major; the all-zero normalisation
+                              row (configuration.jl:153) is appended by the library      */
+  const int32_t *obs_len;  /* [n_integrand] 1 for scalar observables                     */
+  const int32_t *neighbor_ptr; /* CSR over Nd=n_integrand+1 nodes (0-based), or NULL for the
+                                  default chain (configuration.jl:201-209); mcmc only   */
+  const int32_t *neighbor_idx;
+  const double *userdata;  /* [n_userdata]                                               */
+  int32_t n_userdata;
+  int32_t n_block;         /* total blocks of one iteration over ALL ranks (main.jl:121) */
+  uint64_t neval_per_block;/* nevalperblock = neval / block (main.jl:232).  For the chain
+                              solvers = walkers_per_block * steps per walker            */
+  uint64_t seed;           /* Philox key                                                 */
+  int32_t measurefreq;     /* main.jl:84                                                 */
+  int32_t walkers_per_block; /* chain solvers: concurrent chains per block (>=1)         */
+  double thermal_ratio;    /* mcmc burn-in (mcmc/montecarlo.jl:77,133)                   */
+  int32_t device;          /* CUDA device ordinal                                        */
+  int32_t hist_policy;     /* 0 = auto; see MCI_HIST_* (performance knob, not semantics) */
+} mci_problem_t;
+
+enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3 };
+
+/*
+ * Per-iteration statistics handed back to the host: what `_block!` +
+ * `addConfig!` + MPIreduceConfig! leave in obsSum/summedConfig
+ * (main.jl:236-292, configuration.jl:252-299).  Any pointer may be NULL.
+ */
+typedef struct mci_iteration_out_t {
+  double *block_obs;   /* [n_block][sum obs_len]  config_n.observable of each block (un-normalised) */
+  double *block_norm;  /* [n_block]               config_n.normalization (incl. the 1e-10 floor)    */
+  double *hist;        /* [sum_leaf nbins]        summed leaf histograms incl. (n_block+1)*1e-10     */
+  double *visited;     /* [Nd]                    incl. floors                                       */
+  double *propose;     /* [3][Nd][max(Nd,Nv)]     row-major (Julia's array is column-major)          */
+  double *accept;      /* [3][Nd][max(Nd,Nv)]                                                        */
+  uint64_t *neval;     /* [1] integrand evaluations (config.neval)                                   */
+} mci_iteration_out_t;
+
+typedef struct mci_handle_t mci_handle_t;
+
+/* library / ABI version (MCI_ABI_VERSION) */
+int mci_abi_version(void);
+
+/*
+ * Build device state for one problem on one GPU.
+ * Replaces: Configuration(...) ctor marshalling (configuration.jl:105-194) +
+ * the per-thread deepcopy of configs (main.jl:130-137).
+ * Maps start as the reference constructors leave them: uniform grids
+ * (variable.jl:137), Discrete distribution uniform (variable.jl:305-315),
+ * reweight = 1/Nd (configuration.jl:172-175).
+ */
+int mci_create(const mci_problem_t *problem, mci_handle_t **out);
+
+/* release everything owned by the handle (NULL is a no-op) */
+void mci_destroy(mci_handle_t *h);
+
+/* message of the last error on this handle; h == NULL -> last mci_create error of this thread */
+const char *mci_last_error(const mci_handle_t *h);
+
+/* sizes the caller needs to allocate the arrays below */
+int mci_sizes(const mci_handle_t *h, int32_t *grid_len /* sum (nbins+1) over Continuous */,
+              int32_t *disc_len /* sum nbins over Discrete */, int32_t *hist_len /* sum nbins all leaves */,
+              int32_t *obs_len /* sum obs_len */, int32_t *nd /* Ni+1 */, int32_t *pa_len /* 3*Nd*max(Nd,Nv) */);
+
+/*
+ * Upload maps (warm restart `config=result.config`, main.jl:95-97; and the
+ * host-side train! path).  grids: concatenated Continuous grids (nbins+1
+ * each); disc_dist: concatenated Discrete `distribution`; disc_accum:
+ * concatenated `accumulation` (nbins+1 each, variable.jl:314-315);
+ * reweight[Nd].  NULL = leave unchanged.
+ */
+int mci_set_maps(mci_handle_t *h, const double *grids, const double *disc_dist, const double *disc_accum,
+                 const double *reweight);
+int mci_get_maps(mci_handle_t *h, double *grids, double *disc_dist, double *disc_accum, double *reweight);
+
+/*
+ * One iteration's blocks: the `for _ in 1:block/nprocs  _block!(...)` loop
+ * plus MPIreduce of the statistics (main.jl:144-180) collapsed into one call.
+ * Runs this rank's blocks {b : b mod world == rank} on the device (fill
+ * kernel), reduces per-CTA partials in a fixed order, all-reduces over ranks
+ * when a communicator is attached, and copies the statistics to `out`.
+ * `iter` is the 0-based iteration number: it enters the Philox key so every
+ * iteration draws fresh samples.
+ * Replaces: Vegas.montecarlo (vegas/montecarlo.jl:72-191), VegasMC.montecarlo
+ * (vegas_mc/montecarlo.jl:112-241), MCMC.montecarlo (mcmc/montecarlo.jl:72-184).
+ */
+int mci_run_iteration(mci_handle_t *h, uint64_t iter, mci_iteration_out_t *out);
+
+/*
+ * Asynchronous halves of mci_run_iteration for drivers that keep the loop on
+ * the device: launch only (no host sync) / fetch the statistics of the last
+ * launched iteration.
+ */
+int mci_launch_iteration(mci_handle_t *h, uint64_t iter);
+int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out);
+
+/*
+ * Device-side grid refinement on the (all-reduced) histogram of the last
+ * iteration: Dist.train! for every leaf with adapt=true, then histogram
+ * reset.  Replaces variable.jl:206-239 (Continuous: smooth -> rescale ->
+ * regrid), variable.jl:369-382 (Discrete) and common.jl:43-83.
+ */
+int mci_refine(mci_handle_t *h);
+
+/*
+ * doReweight! (main.jl:322-346) on the visited counts of the last iteration.
+ * goal == NULL -> no reweight_goal.  Updates the device copy of reweight.
+ */
+int mci_reweight(mci_handle_t *h, double gamma, const double *goal);
+
+/*
+ * Multi-GPU: one process per GPU.  Rank 0 calls mci_comm_unique_id and the
+ * host distributes the 128 bytes (MPI.bcast in Julia, torch.distributed in
+ * the Python harness); every rank then calls mci_comm_init.  Afterwards
+ * mci_run_iteration ends with ONE ncclAllReduce(sum, f64) of the packed
+ * statistics buffer, replacing MPIreduce + MPIreduceConfig! + MPIbcastConfig!
+ * + doReweightMPI!'s Bcast (main.jl:177-188, configuration.jl:264-321,
+ * main.jl:348-356).  Blocks are partitioned b mod world == rank
+ * (main.jl:122,152-166).
+ */
+int mci_comm_unique_id(void *id128);
+int mci_comm_init(mci_handle_t *h, const void *id128, int32_t rank, int32_t world);
+/* partition blocks without a communicator (the caller reduces, e.g. torch.distributed) */
+int mci_set_partition(mci_handle_t *h, int32_t rank, int32_t world);
+/* device pointer + length (doubles) of the packed statistics buffer, for external collectives */
+int mci_stats_device_ptr(mci_handle_t *h, void **dptr, int64_t *n_doubles);
+
+/*
+ * Parity probe (L0): regenerate samples [first, first+count) of block `block`
+ * of iteration `iter` with the current maps, VEGAS sampler only.  Layout:
+ * x[count][n_draw], bins[count][n_draw] (0-based grid bin / discrete index),
+ * jac[count], weights[count][Ni].  n_draw = draws per sample in the
+ * reference's draw order (vegas/montecarlo.jl:122-131, sampler.jl:431-440).
+ */
+int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t first, int32_t count, double *x,
+                      int32_t *bins, double *jac, double *weights);
+
+/* measurement helpers ---------------------------------------------------- */
+/* number of kernel launches issued by this handle so far */
+int mci_launch_count(const mci_handle_t *h, uint64_t *n);
+/* CUDA-event time (ms) of the fill kernel / of the whole device part of the last iteration */
+int mci_last_timing(mci_handle_t *h, float *fill_ms, float *iteration_ms);
+/* FP64 DFMA peak micro-benchmark on `device` (TFLOP/s, FMA = 2 flop) */
+int mci_fp64_peak(int32_t device, double *tflops);
+/* name of the fill kernel variant chosen for this handle (static string) */
+const char *mci_kernel_name(const mci_handle_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCIB200_H */

@@ -1,0 +1,129 @@
+"""Built-in device integrands.
+
+A Julia closure `f(x, c)` (main.jl:25-33) cannot run on the GPU without CUDA.jl codegen, which the
+north star excludes, so an integrand is a device function compiled into libmcib200.so and selected
+by id.  Each entry fixes the number of integrands it returns and the variable layout it reads.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Sequence
+
+from . import _abi
+
+
+@dataclass(frozen=True)
+class Integrand:
+    name: str
+    id: int
+    n_integrand: int
+    userdata: tuple = ()
+    doc: str = ""
+
+    def with_userdata(self, data: Sequence[float]) -> "Integrand":
+        return Integrand(self.name, self.id, self.n_integrand, tuple(float(x) for x in data), self.doc)
+
+
+gauss_nd = Integrand("gauss_nd", _abi.F_GAUSS_ND, 1, doc="(2π)^(-d/2) exp(-|x|²/2); one Continuous pool, dof=[[d]]")
+log_over_sqrt = Integrand("log_over_sqrt", _abi.F_LOG_OVER_SQRT, 1, doc="log(x)/√x (test/montecarlo.jl:129-134)")
+sphere1 = Integrand("sphere1", _abi.F_SPHERE1, 1, doc="x₁²+x₂²<1 (test/montecarlo.jl:4-9)")
+sphere2 = Integrand("sphere2", _abi.F_SPHERE2, 2, doc="circle and sphere indicators, dof=[[2],[3]] (test/montecarlo.jl:19-49)")
+discrete_x = Integrand("discrete_x", _abi.F_DISCRETE_X, 1, doc="f = x[1] on a Discrete pool (test/montecarlo.jl:104-111)")
+discrete2_const = Integrand("discrete2_const", _abi.F_DISCRETE2_CONST, 1, doc="f = 1 on Discrete([(1,3),(1,4)]) (test/montecarlo.jl:113-120)")
+lattice_pool = Integrand("lattice_pool", _abi.F_LATTICE_POOL, 1, doc="1/(1-cos x cos y cos z)/π³, pool dof=[[3]] (test/montecarlo.jl:136-147)")
+lattice_comp = Integrand("lattice_comp", _abi.F_LATTICE_COMP, 1, doc="same on CompositeVar(X,Y,Z), dof=1 (test/montecarlo.jl:149-180)")
+hypersphere3 = Integrand("hypersphere3", _abi.F_HYPERSPHERE3, 3, doc="nested unit balls d=2,3,4 (test/montecarlo.jl:200-216, N=3)")
+poly3 = Integrand("poly3", _abi.F_POLY3, 3, doc="(x, x², x³) (test/thread.jl)")
+x2_plus_y2 = Integrand("x2_plus_y2", _abi.F_X2_PLUS_Y2, 1, doc="x₁²+x₂² (main.jl:64)")
+
+
+def genz_corner_peak(d: int, layout: str = "pool", csum: float = 1.85) -> Integrand:
+    """(1+Σ cᵢxᵢ)^-(d+1) with cᵢ = csum·i/Σi (d=16 → cᵢ = 1.85·i/136)."""
+    tot = d * (d + 1) // 2
+    c = tuple(csum * i / tot for i in range(1, d + 1))
+    fid = _abi.F_GENZ_CORNER_POOL if layout == "pool" else _abi.F_GENZ_CORNER_COMP
+    return Integrand(f"genz_corner_{layout}{d}", fid, 1, c)
+
+
+def genz_corner_peak_exact(c: Sequence[float]) -> float:
+    """Closed form by inclusion–exclusion: ∫(1+c·x)^-(d+1) = Σ_S (-1)^|S| / (1+Σ_{i∈S}c_i) / (d! Πc)."""
+    from fractions import Fraction
+    import itertools
+
+    d = len(c)
+    cf = [Fraction(x).limit_denominator(10**15) for x in c]
+    tot = Fraction(0)
+    for r in range(d + 1):
+        for S in itertools.combinations(range(d), r):
+            tot += Fraction((-1) ** r) / (1 + sum(cf[i] for i in S))
+    prod = Fraction(1)
+    for x in cf:
+        prod *= x
+    return float(tot / (math.factorial(d) * prod))
+
+
+def product4(a=(0.25, 0.5, 0.75, 1.0)) -> Integrand:
+    """f_k = Π_i (1 + a_k (x_i − ½)), four integrands, each integrates to 1."""
+    return Integrand("product4", _abi.F_PRODUCT_4, 4, tuple(float(x) for x in a))
+
+
+@dataclass
+class BubblePara:
+    """example/bubble.jl:10-22 (Base.@kwdef struct Para)."""
+    rs: float = 1.0
+    beta: float = 25.0
+    spin: int = 2
+    Qsize: int = 4
+    dim: int = 3
+    me: float = 0.5
+    kF: float = field(init=False)
+    extQ: list = field(init=False)
+    β: float = field(init=False)
+
+    def __post_init__(self):
+        self.kF = (9 * math.pi / (2 * self.spin)) ** (1 / 3) / self.rs if self.dim == 3 else math.sqrt(4 / self.spin) / self.rs
+        n = self.Qsize
+        # LinRange(0.0*kF, 1.5*kF, Qsize)
+        self.extQ = [((1 - i / (n - 1)) * 0.0 * self.kF + (i / (n - 1)) * 1.5 * self.kF) for i in range(n)]
+        self.β = self.beta / (self.kF ** 2 / 2 / self.me)
+
+    def lindhard(self, q: float) -> float:
+        """example/bubble.jl:24-38 (T=0 free-electron polarisation)."""
+        me, kF, spin = self.me, self.kF, self.spin
+        density = me * kF / (2 * math.pi ** 2)
+        if q < 1e-6:
+            q = 1e-6
+        x = q / 2 / kF
+        if abs(q - 2 * kF) > 1e-6:
+            Pi = 1 + (1 - x ** 2) * math.log1p(4 * x / ((1 - x) ** 2)) / 4 / x
+        else:
+            Pi = 1.0
+        return -Pi * density * spin / 2
+
+
+def bubble(para: BubblePara | None = None) -> Integrand:
+    """example/bubble.jl:50-75; variables (R, θ, φ, T, Ext); userdata = [kF, β, me, spin, dim, Qsize, extQx…]."""
+    para = para or BubblePara()
+    ud = (para.kF, para.β, para.me, float(para.spin), float(para.dim), float(para.Qsize), *para.extQ)
+    return Integrand("bubble", _abi.F_BUBBLE, 1, tuple(ud))
+
+
+REGISTRY = {
+    f.name: f
+    for f in (gauss_nd, log_over_sqrt, sphere1, sphere2, discrete_x, discrete2_const, lattice_pool, lattice_comp,
+              hypersphere3, poly3, x2_plus_y2)
+}
+
+
+def resolve(f) -> Integrand:
+    if isinstance(f, Integrand):
+        return f
+    if isinstance(f, str) and f in REGISTRY:
+        return REGISTRY[f]
+    if callable(f):
+        raise TypeError(
+            "mcintegration.jl_b200 runs the integrand on the GPU: pass a built-in integrand "
+            "(mcintegration_jl_b200.integrands.*) instead of a Python callable; see INTEGRATION.md"
+        )
+    raise KeyError(f"unknown integrand {f!r}; known: {sorted(REGISTRY)}")

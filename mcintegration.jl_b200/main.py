@@ -1,0 +1,117 @@
+"""integrate(f; var, dof, solver, neval, ...) — the reference's driver (src/main.jl:71-218) with the
+block loop + statistics reduction of one iteration replaced by ONE call into the C ABI
+(mci_run_iteration) and train!/doReweight! replaced by mci_refine / mci_reweight on the device."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from .configuration import Configuration, maps_from_config, maps_to_config, problem_from_config
+from .integrands import resolve
+from .statistics import Result, mean_std, report
+
+_SOLVERS = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC, "mcmc": _abi.SOLVER_MCMC}
+_MEASURES = {None: _abi.MEASURE_DEFAULT, "default": _abi.MEASURE_DEFAULT,
+             "bin_by_discrete": _abi.MEASURE_BIN_BY_DISCRETE}
+
+# concurrent chains per block for the chain solvers when the caller does not say (SURVEY §7 hard part 3)
+DEFAULT_WALKERS = 4096
+
+
+def _standardize_block(neval, nblock, nworker=1):
+    """main.jl:220-234"""
+    assert neval > nblock, f"neval={neval} should be larger than nblock = {nblock}"
+    if nblock > nworker:
+        nblock = (nblock // nworker) * nworker
+    else:
+        nblock = nworker
+    return int(neval // nblock), int(nblock)
+
+
+def split_observables(config, flat):
+    """flat [obs_total] -> list per integrand (scalar or vector), like config.observable."""
+    out, o = [], 0
+    for n, proto in zip(config.obs_len(), config.observable):
+        out.append(np.array(flat[o:o + n]) if isinstance(proto, np.ndarray) else float(flat[o]))
+        o += n
+    return out
+
+
+def block_statistics(stats, config, block):
+    """main.jl:275-287 + _mean_std: per-block normalised means, their sum and squared sum."""
+    m = stats.block_obs / stats.block_norm[:, None]
+    mean, std = mean_std(m.sum(axis=0), (m * m).sum(axis=0), block)
+    return split_observables(config, mean), split_observables(config, std)
+
+
+def drive(engine, config, *, solver, niter, block, gamma=1.0, adapt=True, reweight_goal=None, ignore=None,
+          print_level=-1, run_iteration=None, first_iter=0):
+    """The `for iter in 1:niter` loop of main.jl:142-207 on top of an engine.  Engine-agnostic so the
+    tests can run the CPU oracle through the same host logic."""
+    if ignore is None:
+        ignore = 1 if adapt else 0
+    run = run_iteration or engine.run_iteration
+    history = []
+    neval_total = 0
+    for it in range(niter):
+        stats = run(first_iter + it)
+        neval_total += stats.neval
+        config.neval = stats.neval
+        config.visited = stats.visited
+        config.propose, config.accept = stats.propose, stats.accept
+        config.normalization = float(stats.block_norm.sum())
+        if solver in ("mcmc", "vegasmc"):
+            engine.reweight(gamma, reweight_goal)  # main.jl:183
+        if adapt:
+            engine.refine()  # main.jl:193-198
+        mean, std = block_statistics(stats, config, block)
+        history.append((mean, std, {"neval": stats.neval, "hist": stats.hist}))
+    maps_to_config(config, *engine.get_maps())  # `configs[1]` keeps the trained grid (main.jl:204)
+    result = Result.from_history(history, ignore, config, neval_total)
+    if print_level >= 0:
+        report(result)
+    return result
+
+
+def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, block=16, verbose=-1, gamma=1.0,
+              adapt=True, debug=False, reweight_goal=None, ignore=None, measure=None, measurefreq=1,
+              thermal_ratio=0.1, inplace=False, parallel="nothread", print=-1, walkers=None, device=0,
+              hist_policy=0, comm=None, **kwargs):
+    """Drop-in for MCIntegration.integrate (main.jl:71-90) on one B200.
+
+    `integrand` is a built-in device integrand (mcintegration_jl_b200.integrands) instead of a closure;
+    `measure` is None or "bin_by_discrete".  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
+    `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU).
+    Everything else keeps the reference's meaning; `neval` is per iteration.
+    """
+    from .engine import CudaEngine
+
+    solver = str(solver).lstrip(":")
+    if solver not in _SOLVERS:
+        raise ValueError(f"Solver {solver} is not supported!")  # main.jl:263
+    print_level = max(print, verbose)
+    f = resolve(integrand)
+    if config is None:
+        config = Configuration(**kwargs)
+    for i, m in enumerate(config.maxdof):
+        assert m + 2 <= config.var[i].poolsize(), "maxdof should be less than the length of var"  # main.jl:99-101
+    world = comm[1] if comm else 1
+    nevalperblock, block = _standardize_block(int(neval), int(block), world)
+    assert block % world == 0  # main.jl:122
+    if solver == "vegas":
+        W = 1
+    else:
+        W = int(walkers) if walkers else min(DEFAULT_WALKERS, max(1, nevalperblock // 64))
+        nevalperblock = (nevalperblock // W) * W
+    spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
+                               neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
+                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy)
+    engine = CudaEngine(spec)
+    try:
+        engine.set_maps(*maps_from_config(config))  # warm restart: config=result.config (main.jl:95-97)
+        if comm:
+            engine.comm_init(comm[2], comm[0], comm[1])
+        return drive(engine, config, solver=solver, niter=niter, block=block, gamma=gamma, adapt=adapt,
+                     reweight_goal=reweight_goal, ignore=ignore, print_level=print_level)
+    finally:
+        engine.close()

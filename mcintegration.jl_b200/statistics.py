@@ -1,0 +1,107 @@
+"""Host post-processing mirrors: _mean_std (main.jl:296-320), average/Result (statistics.jl:16-63,186-220),
+report (statistics.jl:137-172).  Tiny, runs once per iteration on block means the device produced."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def mean_std(obs_sum, obs_sq_sum, block):
+    """_mean_std: mean = Σm/B, std = sqrt(max(0,(Σm²/B − mean²)/(B−1)))."""
+    obs_sum = np.asarray(obs_sum, dtype=np.float64)
+    obs_sq_sum = np.asarray(obs_sq_sum, dtype=np.float64)
+    mean = obs_sum / block
+    if block > 1:
+        v = (obs_sq_sum / block - mean ** 2) / (block - 1)
+        std = np.sqrt(np.where(v < 0.0, 0.0, v))
+    else:
+        std = np.zeros_like(obs_sq_sum)
+    return mean, std
+
+
+def average(means, stds, init=1, max_=None):
+    """statistics.jl:186-220 for one (possibly vector) observable.  init is 1-based."""
+    if max_ is None:
+        max_ = len(means)
+    if max_ <= init:
+        return means[0], stds[0], np.zeros_like(means[0])
+    data = [np.asarray(means[i]) for i in range(init - 1, max_)]
+    weight = [1.0 / (np.asarray(stds[i]) + 1.0e-10) ** 2 for i in range(init - 1, max_)]
+    wsum = sum(weight)
+    mea = sum(d * w / wsum for d, w in zip(data, weight))
+    err = 1.0 / np.sqrt(wsum)
+    chi2 = sum(w * (d - mea) ** 2 for d, w in zip(data, weight))
+    return mea, err, chi2 / ((max_ - init + 1) - 1)
+
+
+@dataclass
+class Result:
+    """statistics.jl:16-63."""
+    mean: list
+    stdev: list
+    chi2: list
+    neval: int
+    ignore: int
+    config: object
+    iterations: list = field(default_factory=list)  # [(mean[], std[], snapshot), ...]
+
+    @classmethod
+    def from_history(cls, history, ignore, config, neval):
+        init = ignore + 1
+        assert len(history) > 0
+        N = len(history[-1][0])
+        res = [average([h[0][o] for h in history], [h[1][o] for h in history], init=init, max_=len(history))
+               for o in range(N)]
+        return cls([r[0] for r in res], [r[1] for r in res], [r[2] for r in res], neval, ignore, config, history)
+
+    def __getitem__(self, i):
+        return self.mean[i], self.stdev[i], self.chi2[i]
+
+    def dof(self):
+        return (len(self.iterations) - (self.ignore + 1) + 1) - 1
+
+
+def report(result: Result, pick=None, name=None, verbose=0, io=None):
+    """statistics.jl:137-172: per-iteration table + final estimate."""
+    import sys
+
+    io = io or sys.stdout
+    N = len(result.mean)
+    for o in range(N):
+        label = f"Integral {o + 1}" if name is None else str(name[o])
+        bar = "=" * 36 + f"  {label:^16}  " + "=" * 36
+        print(bar, file=io)
+        print(f"{'iter':>6}  {'integral':>28}  {'wgt average':>28}  {'chi2/dof':>10}", file=io)
+        print("-" * len(bar), file=io)
+        for i in range(len(result.iterations)):
+            m, s = result.iterations[i][0][o], result.iterations[i][1][o]
+            if i < result.ignore:
+                am, ae, c2 = m, s, 0.0
+                tag = "ignore"
+            else:
+                am, ae, c2 = average([h[0][o] for h in result.iterations], [h[1][o] for h in result.iterations],
+                                     init=result.ignore + 1, max_=i + 1)
+                tag = f"{i + 1:6d}"
+            pm = (lambda x: np.asarray(x).ravel()[0 if pick is None else pick])
+            print(f"{tag:>6}  {pm(m):16.8g} ± {pm(s):<10.4g}  {pm(am):16.8g} ± {pm(ae):<10.4g}  {pm(c2):10.4f}", file=io)
+        print("-" * len(bar), file=io)
+        m, s, c2 = result.mean[o], result.stdev[o], result.chi2[o]
+        print(f"{label} = {np.asarray(m).ravel()} ± {np.asarray(s).ravel()}   (reduced chi2 = {np.asarray(c2).ravel()})", file=io)
+    return None
+
+
+def do_reweight(reweight, visited, gamma, goal=None):
+    """doReweight! (main.jl:322-346) — host copy for tests; the engine runs the device/oracle version."""
+    reweight = np.array(reweight, dtype=np.float64)
+    avgstep = float(np.sum(visited))
+    for i, v in enumerate(visited):
+        if v <= 1:
+            reweight[i] *= avgstep ** gamma
+        else:
+            reweight[i] *= (avgstep / v) ** gamma
+    if goal is not None:
+        goal = np.asarray(goal, dtype=np.float64)
+        reweight *= goal / goal.sum()
+    return reweight / reweight.sum()
