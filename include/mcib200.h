@@ -219,6 +219,9 @@ int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out);
  * regrid), variable.jl:369-382 (Discrete) and common.jl:43-83.
  */
 int mci_refine(mci_handle_t *h);
+/* on != 0: mci_refine / mci_reweight only enqueue (no host synchronisation); a failed train! assert
+ * then surfaces at the next mci_fetch_iteration.  For drivers that keep the whole loop on the device. */
+int mci_set_async(mci_handle_t *h, int32_t on);
 
 /*
  * doReweight! (main.jl:322-346) on the visited counts of the last iteration.
@@ -242,6 +245,8 @@ int mci_comm_init(mci_handle_t *h, const void *id128, int32_t rank, int32_t worl
 int mci_set_partition(mci_handle_t *h, int32_t rank, int32_t world);
 /* device pointer + length (doubles) of the packed statistics buffer, for external collectives */
 int mci_stats_device_ptr(mci_handle_t *h, void **dptr, int64_t *n_doubles);
+/* after an external collective on that buffer: refresh the host copy mci_fetch_iteration reads */
+int mci_stats_sync_host(mci_handle_t *h);
 
 /*
  * Parity probe (L0): regenerate samples [first, first+count) of block `block`
@@ -258,8 +263,16 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
 int mci_launch_count(const mci_handle_t *h, uint64_t *n);
 /* CUDA-event time (ms) of the fill kernel / of the whole device part of the last iteration */
 int mci_last_timing(mci_handle_t *h, float *fill_ms, float *iteration_ms);
+/* CUDA-event stopwatch on the handle's stream (all kernels of a handle run on its own stream, which
+ * torch.cuda.Event cannot see): start records an event, stop records another, waits for it and returns ms */
+int mci_timer_start(mci_handle_t *h);
+int mci_timer_stop(mci_handle_t *h, float *ms);
 /* FP64 DFMA peak micro-benchmark on `device` (TFLOP/s, FMA = 2 flop) */
 int mci_fp64_peak(int32_t device, double *tflops);
+/* launch shape of the fill kernel: CTAs, threads per CTA, dynamic shared memory, MCI_HIST_* actually used,
+ * tiles per block and samples per thread (VEGAS; 0 for the chain solvers) */
+int mci_launch_info(const mci_handle_t *h, int32_t *grid, int32_t *threads, int64_t *smem_bytes, int32_t *hist_mode,
+                    int32_t *tiles_per_block, int32_t *samples_per_thread);
 /* name of the fill kernel variant chosen for this handle (static string) */
 const char *mci_kernel_name(const mci_handle_t *h);
 

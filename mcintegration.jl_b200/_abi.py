@@ -124,6 +124,11 @@ EXPORTS = [
     "mci_last_timing",
     "mci_fp64_peak",
     "mci_kernel_name",
+    "mci_set_async",
+    "mci_stats_sync_host",
+    "mci_launch_info",
+    "mci_timer_start",
+    "mci_timer_stop",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -173,6 +178,11 @@ def declare(lib, prefix="mci_"):
         f("last_timing", C.c_int, [H, C.POINTER(C.c_float), C.POINTER(C.c_float)])
         f("fp64_peak", C.c_int, [C.c_int32, dp])
         f("kernel_name", C.c_char_p, [H])
+        f("set_async", C.c_int, [H, C.c_int32])
+        f("timer_start", C.c_int, [H])
+        f("timer_stop", C.c_int, [H, C.POINTER(C.c_float)])
+        f("stats_sync_host", C.c_int, [H])
+        f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
     return lib
 
 

@@ -1,0 +1,13 @@
+/* mcmc kernels for every built-in integrand */
+#include "mci_kernels.h"
+#include "mci_chain.cuh"
+namespace mci {
+const void *lookup_mcmc(int fid, const char **name) {
+  switch (fid) {
+#define M(FID) case FID: if (name) *name = "mcmc_kernel<" #FID ">"; return (const void *)mcmc_kernel<FID, CHAIN_THREADS>;
+    MCI_FOR_EACH_FID(M)
+#undef M
+  }
+  return nullptr;
+}
+}  // namespace mci

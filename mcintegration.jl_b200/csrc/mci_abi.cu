@@ -1,0 +1,823 @@
+/*
+ * mci_abi.cu — the C ABI of libmcib200.so (include/mcib200.h): handle management, launch
+ * planning, the per-iteration launch sequence and the NCCL all-reduce of the packed statistics.
+ *
+ * Host roles replaced (reference paths): the per-iteration block loop + statistics reduction of
+ * integrate (src/main.jl:144-199), Configuration marshalling (src/configuration.jl:105-194),
+ * MPIreduceConfig!/MPIbcastConfig! (src/configuration.jl:264-321).
+ *
+ * There is no CPU fallback anywhere in this file: without a CUDA device mci_create fails.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mci_aux.cuh"
+#include "mci_chain.cuh"
+#include "mci_kernels.h"
+#include "mci_vegas.cuh"
+
+using namespace mci;
+
+/* ------------------------------------------------------------------------------------------ */
+/* NCCL, bound at run time (dlopen) so the library loads on hosts without libnccl              */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void *nccl_comm_t;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+
+bool nccl_load() {
+  if (g_nccl.ok) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return false;
+  g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+  return g_nccl.ok;
+}
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+
+thread_local char g_err[256];
+}  // namespace
+
+struct mci_handle_t {
+  mci_problem_t p;
+  DevProblem dp;
+  PackedLayout Y;
+  int nd, nv, ni, nleaf, pa_len, obs_total, hist_len, grid_len, disc_len, accum_len;
+  std::vector<int> leaf_grid_off, leaf_dist_off, leaf_acc_off;
+  std::vector<double> alpha;
+  int rank = 0, world = 1;
+  int device = 0, n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_iter0 = nullptr, ev_fill0 = nullptr, ev_fill1 = nullptr, ev_iter1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  /* device state */
+  double *d_grids = nullptr, *d_dist = nullptr, *d_accum = nullptr, *d_reweight = nullptr, *d_goal = nullptr;
+  double *d_alpha = nullptr, *d_gmaps = nullptr;
+  int *d_leaf_grid_off = nullptr, *d_leaf_dist_off = nullptr, *d_leaf_acc_off = nullptr;
+  double *d_tile_obs = nullptr, *d_tile_cnt = nullptr, *d_cta_hist = nullptr, *d_cta_stats = nullptr, *d_packed = nullptr;
+  unsigned long long *d_flags = nullptr;
+  int *d_err = nullptr;
+  /* pinned host mirrors */
+  double *h_packed = nullptr;
+  unsigned long long *h_flags = nullptr;
+  int *h_err = nullptr;
+  /* launch plan */
+  const void *kernel = nullptr;
+  const char *kernel_name = "";
+  bool is_pool = false;
+  int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
+  size_t smem = 0;
+  int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0;
+  uint64_t steps = 0;
+  bool maps_dirty = true, have_iteration = false, async_mode = false;
+  nccl_comm_t comm = nullptr;
+  uint64_t launches = 0;
+  float fill_ms = 0.f, iter_ms = 0.f;
+  char err[256];
+};
+
+namespace {
+
+int fail(mci_handle_t *h, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(h ? h->err : g_err, 256, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(h, call)                                                                                              \
+  do {                                                                                                           \
+    cudaError_t e_ = (call);                                                                                     \
+    if (e_ != cudaSuccess) return fail(h, MCI_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+/* integrands per id: number of values and the (leaf, slots) they read; -1 slots = dof[0] of the pool */
+struct FidInfo { int ni; int nleaf_min; int slots0; };
+bool fid_info(int fid, FidInfo &I) {
+  switch (fid) {
+    case MCI_F_GAUSS_ND: I = {1, 1, -1}; return true;
+    case MCI_F_LOG_OVER_SQRT: I = {1, 1, 1}; return true;
+    case MCI_F_GENZ_CORNER_POOL: I = {1, 1, -1}; return true;
+    case MCI_F_GENZ_CORNER_COMP: I = {1, 1, 1}; return true;
+    case MCI_F_BUBBLE: I = {1, 5, 1}; return true;
+    case MCI_F_PRODUCT_4: I = {4, 1, -1}; return true;
+    case MCI_F_SPHERE1: I = {1, 1, 2}; return true;
+    case MCI_F_SPHERE2: I = {2, 1, 3}; return true;
+    case MCI_F_DISCRETE_X: I = {1, 1, 1}; return true;
+    case MCI_F_DISCRETE2_CONST: I = {1, 1, 1}; return true;
+    case MCI_F_LATTICE_POOL: I = {1, 1, 3}; return true;
+    case MCI_F_LATTICE_COMP: I = {1, 3, 1}; return true;
+    case MCI_F_HYPERSPHERE3: I = {3, 1, 4}; return true;
+    case MCI_F_POLY3: I = {3, 1, 1}; return true;
+    case MCI_F_X2_PLUS_Y2: I = {1, 1, 2}; return true;
+  }
+  return false;
+}
+
+double volume_inverse(int d) { /* test/montecarlo.jl:201-204 */
+  const double euler = 2.71828182845904523536028747135266249775724709369995957496696763;
+  const double pi = 3.14159265358979323846;
+  return pow(d / (2 * pi * euler), d / 2.0) * sqrt((double)d) * sqrt(pi);
+}
+
+template <class T>
+int dev_alloc(mci_handle_t *h, T **p, size_t n) {
+  CU(h, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CU(h, cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return MCI_OK;
+}
+
+/* choose kernel, histogram policy, shared memory and grid for the current partition */
+int plan(mci_handle_t *h) {
+  const mci_problem_t &p = h->p;
+  DevProblem &P = h->dp;
+  const int n_local = p.n_block / h->world;
+  const size_t map_bytes = (size_t)P.map_doubles * 8;
+  const size_t hist_bytes = (size_t)P.hist_len * 8;
+  const size_t SMEM_MAX = 227 * 1024;
+  int policy = p.hist_policy;
+  if (!P.any_adapt) policy = -1;
+
+  auto pick_hist = [&](int nwarp, size_t extra, bool allow_private) {
+    /* returns mode and sets maps_in_smem */
+    h->maps_in_smem = map_bytes + extra <= SMEM_MAX ? 1 : 0;
+    size_t base = (h->maps_in_smem ? map_bytes : 0) + extra;
+    if (policy == -1) return (int)HIST_NONE;
+    if (policy == MCI_HIST_WARP_PRIVATE && allow_private && base + nwarp * hist_bytes <= SMEM_MAX) return (int)HIST_WARP_PRIVATE;
+    if (policy == MCI_HIST_SMEM_ATOMIC && base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
+    if (policy == MCI_HIST_GLOBAL_RED) return (int)HIST_GLOBAL_RED;
+    /* auto: private copies when two CTAs per SM still fit, else one shared copy, else L2 */
+    if (allow_private && base + nwarp * hist_bytes <= 110 * 1024) return (int)HIST_WARP_PRIVATE;
+    if (base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
+    return (int)HIST_GLOBAL_RED;
+  };
+  auto hist_smem = [&](int mode, int nwarp) -> size_t {
+    return mode == HIST_WARP_PRIVATE ? nwarp * hist_bytes : (mode == HIST_SMEM_ATOMIC ? hist_bytes : 0);
+  };
+
+  if (p.solver == MCI_SOLVER_VEGAS) {
+    bool pool_layout = P.nv == 1 && P.nleaf == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS &&
+                       p.measure_kind == MCI_MEASURE_DEFAULT && P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT;
+    h->is_pool = false;
+    if (pool_layout) {
+      const int nwarp = POOL_THREADS / 32;
+      const size_t red = (size_t)nwarp * (P.ni + 1) * 8;
+      int mode = pick_hist(nwarp, red, true);
+      if (h->maps_in_smem) {
+        const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], mode, &h->kernel_name);
+        if (k) {
+          h->kernel = k; h->is_pool = true; h->threads = POOL_THREADS; h->hist_mode = mode;
+          h->smem = map_bytes + hist_smem(mode, nwarp) + red;
+        }
+      }
+    }
+    if (!h->is_pool) {
+      const int nwarp = GENERIC_THREADS / 32;
+      const size_t red = (size_t)nwarp * (P.obs_total + 1) * 8;
+      int mode = pick_hist(nwarp, red, true);
+      h->kernel = lookup_vegas_generic(P.fid, &h->kernel_name);
+      if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no vegas kernel", P.fid);
+      h->threads = GENERIC_THREADS; h->hist_mode = mode;
+      h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
+    }
+  } else {
+    const int nwarp = CHAIN_THREADS / 32;
+    const size_t red = (size_t)nwarp * 8 + (p.solver == MCI_SOLVER_MCMC ? 2 * (size_t)h->pa_len * 4 : 0) + 8;
+    int mode = pick_hist(nwarp, red, true);
+    h->kernel = p.solver == MCI_SOLVER_VEGASMC ? lookup_vegasmc(P.fid, &h->kernel_name) : lookup_mcmc(P.fid, &h->kernel_name);
+    if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no chain kernel", P.fid);
+    h->threads = CHAIN_THREADS; h->hist_mode = mode;
+    h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
+  }
+  CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  int occ = 0;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->threads, h->smem));
+  if (occ < 1) return fail(h, MCI_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", h->kernel_name, h->smem);
+
+  if (p.solver == MCI_SOLVER_VEGAS) {
+    const int resident = h->n_sm * occ;
+    const uint64_t npb = p.neval_per_block;
+    const uint64_t want_tiles_pb = std::max<uint64_t>(1, ((uint64_t)8 * resident + n_local - 1) / n_local);
+    uint64_t spt = (npb + (uint64_t)h->threads * want_tiles_pb - 1) / ((uint64_t)h->threads * want_tiles_pb);
+    spt = std::min<uint64_t>(std::max<uint64_t>(spt, 1), 64);
+    h->spt = (int)spt;
+    const uint64_t tile = (uint64_t)h->threads * spt;
+    const uint64_t tpb = (npb + tile - 1) / tile;
+    if (tpb * n_local > (uint64_t)1 << 30) return fail(h, MCI_ERR_INVALID, "neval_per_block too large for one launch");
+    h->tiles_per_block = (int)tpb;
+    h->grid = (int)std::min<uint64_t>((uint64_t)resident, tpb * n_local);
+    h->ctas_per_block = 0;
+  } else {
+    const int W = std::max(1, p.walkers_per_block);
+    h->steps = p.neval_per_block / W;
+    h->ctas_per_block = (W + h->threads - 1) / h->threads;
+    h->grid = h->ctas_per_block * n_local;
+    h->tiles_per_block = 0;
+  }
+  h->n_hist_copies = (h->hist_mode == HIST_GLOBAL_RED) ? std::min(h->grid, 2 * h->n_sm) : h->grid;
+  if (h->n_hist_copies < 1) h->n_hist_copies = 1;
+
+  /* (re)allocate per-launch partial buffers */
+  cudaFree(h->d_tile_obs); cudaFree(h->d_tile_cnt); cudaFree(h->d_cta_hist); cudaFree(h->d_cta_stats);
+  h->d_tile_obs = h->d_tile_cnt = h->d_cta_hist = h->d_cta_stats = nullptr;
+  int rc;
+  if (p.solver == MCI_SOLVER_VEGAS) {
+    const size_t nt = (size_t)h->tiles_per_block * n_local;
+    if ((rc = dev_alloc(h, &h->d_tile_obs, nt * P.obs_total))) return rc;
+    if ((rc = dev_alloc(h, &h->d_tile_cnt, nt))) return rc;
+  } else {
+    const size_t stat_len = P.obs_total + 1 + P.nd + 2 * (size_t)h->pa_len + 1;
+    if ((rc = dev_alloc(h, &h->d_cta_stats, (size_t)h->grid * stat_len))) return rc;
+  }
+  if ((rc = dev_alloc(h, &h->d_cta_hist, (size_t)h->n_hist_copies * std::max(1, P.hist_len)))) return rc;
+  return MCI_OK;
+}
+
+int enqueue_build_maps(mci_handle_t *h) {
+  build_maps_kernel<<<h->nleaf, 128, 0, h->stream>>>(h->dp, h->d_grids, h->d_dist, h->d_accum, h->d_leaf_grid_off,
+                                                     h->d_leaf_dist_off, h->d_leaf_acc_off, h->d_gmaps);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  h->maps_dirty = false;
+  return MCI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mci_abi_version(void) { return MCI_ABI_VERSION; }
+
+const char *mci_last_error(const mci_handle_t *h) { return h ? h->err : g_err; }
+
+void mci_destroy(mci_handle_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_grids); cudaFree(h->d_dist); cudaFree(h->d_accum); cudaFree(h->d_reweight); cudaFree(h->d_goal);
+  cudaFree(h->d_alpha); cudaFree(h->d_gmaps); cudaFree(h->d_leaf_grid_off); cudaFree(h->d_leaf_dist_off);
+  cudaFree(h->d_leaf_acc_off); cudaFree(h->d_tile_obs); cudaFree(h->d_tile_cnt); cudaFree(h->d_cta_hist);
+  cudaFree(h->d_cta_stats); cudaFree(h->d_packed); cudaFree(h->d_flags); cudaFree(h->d_err);
+  if (h->h_packed) cudaFreeHost(h->h_packed);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  if (h->h_err) cudaFreeHost(h->h_err);
+  if (h->ev_iter0) cudaEventDestroy(h->ev_iter0);
+  if (h->ev_fill0) cudaEventDestroy(h->ev_fill0);
+  if (h->ev_fill1) cudaEventDestroy(h->ev_fill1);
+  if (h->ev_iter1) cudaEventDestroy(h->ev_iter1);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mci_create(const mci_problem_t *p, mci_handle_t **out) {
+  if (!p || !out) return fail(nullptr, MCI_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (p->n_topvar < 1 || p->n_topvar > MCI_MAX_TOPVAR || p->n_leaf < 1 || p->n_leaf > MCI_MAX_LEAF ||
+      p->n_integrand < 1 || p->n_integrand > MCI_MAX_INTEGRAND || p->n_block < 1 || p->measurefreq < 1 ||
+      p->neval_per_block < 1)
+    return fail(nullptr, MCI_ERR_INVALID, "problem dimensions out of range");
+  if (p->solver < MCI_SOLVER_VEGAS || p->solver > MCI_SOLVER_MCMC) return fail(nullptr, MCI_ERR_INVALID, "Solver %d is not supported!", p->solver);
+  FidInfo FI;
+  if (!fid_info(p->integrand_id, FI)) return fail(nullptr, MCI_ERR_UNSUPPORTED, "unknown integrand id %d", p->integrand_id);
+  if (FI.ni != p->n_integrand)
+    return fail(nullptr, MCI_ERR_INVALID, "integrand %d returns %d values but n_integrand = %d", p->integrand_id, FI.ni, p->n_integrand);
+  if (p->n_leaf < FI.nleaf_min) return fail(nullptr, MCI_ERR_INVALID, "integrand %d needs %d leaf variables", p->integrand_id, FI.nleaf_min);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || p->device < 0 || p->device >= ndev)
+    return fail(nullptr, MCI_ERR_NO_DEVICE, "no CUDA device %d (found %d): libmcib200 has no CPU fallback", p->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, MCI_ERR_NO_DEVICE, "device %d is not a Blackwell (sm_100a) GPU", p->device);
+
+  mci_handle_t *h = new mci_handle_t();
+  h->err[0] = 0;
+  h->p = *p;
+  h->device = p->device;
+  h->n_sm = prop.multiProcessorCount;
+  DevProblem &P = h->dp;
+  memset(&P, 0, sizeof P);
+  const int ni = p->n_integrand, nd = ni + 1, nv = p->n_topvar, nleaf = p->n_leaf;
+  h->ni = ni; h->nd = nd; h->nv = nv; h->nleaf = nleaf;
+  P.solver = p->solver; P.fid = p->integrand_id; P.measure_kind = p->measure_kind;
+  P.ni = ni; P.nd = nd; P.nv = nv; P.nleaf = nleaf; P.measurefreq = p->measurefreq;
+  P.thermal_ratio = p->thermal_ratio; P.seed = p->seed;
+  int first = 0;
+  for (int v = 0; v < nv; ++v) { P.top_nleaf[v] = p->topvar_nleaf[v]; P.top_first[v] = first; first += p->topvar_nleaf[v]; }
+#define BAIL(code, ...) do { int rc_ = fail(nullptr, code, __VA_ARGS__); delete h; return rc_; } while (0)
+  if (first != nleaf) BAIL(MCI_ERR_INVALID, "sum(topvar_nleaf) != n_leaf");
+  for (int i = 0; i < ni; ++i)
+    for (int v = 0; v < nv; ++v) {
+      P.dof[i * nv + v] = p->dof[i * nv + v];
+      if (p->dof[i * nv + v] < 0) BAIL(MCI_ERR_INVALID, "negative dof");
+    }
+  for (int v = 0; v < nv; ++v) P.dof[ni * nv + v] = 0; /* configuration.jl:153 */
+  for (int v = 0; v < nv; ++v) { int m = 0; for (int i = 0; i < nd; ++i) m = std::max(m, P.dof[i * nv + v]); P.maxdof[v] = m; }
+  int base = 0, tslot = 0;
+  for (int v = 0; v < nv; ++v) {
+    P.top_base[v] = base; P.top_tslot[v] = tslot;
+    base += P.maxdof[v] * P.top_nleaf[v]; tslot += P.maxdof[v];
+  }
+  P.n_draw = base; P.n_tslot = tslot;
+  if (P.n_draw > MAX_DRAW) BAIL(MCI_ERR_UNSUPPORTED, "sum(maxdof * leaves) = %d exceeds %d", P.n_draw, MAX_DRAW);
+  P.need_pad = 0;
+  for (int i = 0; i < ni; ++i) {
+    int same = 1;
+    for (int v = 0; v < nv; ++v) if (P.dof[i * nv + v] != P.maxdof[v]) same = 0;
+    P.same_dof[i] = same;
+    if (!same) P.need_pad = 1;
+  }
+  int ot = 0;
+  for (int i = 0; i < ni; ++i) { P.obs_len[i] = p->obs_len ? p->obs_len[i] : 1; P.obs_off[i] = ot; ot += P.obs_len[i]; }
+  if (ot > MCI_MAX_OBS) BAIL(MCI_ERR_UNSUPPORTED, "total observable length %d exceeds %d", ot, MCI_MAX_OBS);
+  P.obs_total = ot; h->obs_total = ot;
+  /* leaves */
+  h->leaf_grid_off.assign(nleaf, 0); h->leaf_dist_off.assign(nleaf, 0); h->leaf_acc_off.assign(nleaf, 0);
+  h->alpha.assign(nleaf, 2.0);
+  int go = 0, dd = 0, da = 0, ho = 0, mo = 0;
+  for (int v = 0; v < nv; ++v)
+    for (int k = 0; k < P.top_nleaf[v]; ++k) {
+      const int l = P.top_first[v] + k;
+      const mci_leaf_t &S = p->leaf[l];
+      DevLeaf &L = P.leaf[l];
+      if (S.nbins < 1) BAIL(MCI_ERR_INVALID, "leaf %d has no bins", l);
+      L.kind = S.kind; L.nbins = S.nbins; L.adapt = S.adapt ? 1 : 0; L.lower_i = S.lower_i; L.nbins_d = (double)S.nbins;
+      L.top = v; L.base = P.top_base[v] + k; L.stride = P.top_nleaf[v];
+      L.hist_off = ho; ho += S.nbins;
+      L.smem_off = mo;
+      h->alpha[l] = S.alpha;
+      if (S.kind == MCI_LEAF_CONTINUOUS) {
+        if (!(S.upper > S.lower)) BAIL(MCI_ERR_INVALID, "leaf %d: upper <= lower", l);
+        h->leaf_grid_off[l] = go; go += S.nbins + 1; mo += 2 * S.nbins;
+      } else if (S.kind == MCI_LEAF_DISCRETE) {
+        h->leaf_dist_off[l] = dd; dd += S.nbins; h->leaf_acc_off[l] = da; da += S.nbins + 1;
+        mo += 2 * S.nbins + 1; mo += mo & 1;
+      } else BAIL(MCI_ERR_INVALID, "leaf %d: unknown kind %d", l, S.kind);
+      if (L.adapt) P.any_adapt = 1;
+    }
+  P.map_doubles = mo; P.hist_len = ho;
+  h->grid_len = go; h->disc_len = dd; h->accum_len = da; h->hist_len = ho;
+  for (int v = 0; v < nv; ++v)
+    P.top_skip[v] = (P.top_nleaf[v] == 1 && P.leaf[P.top_first[v]].kind == MCI_LEAF_DISCRETE && P.leaf[P.top_first[v]].nbins == 1);
+  /* the slots the integrand reads must exist */
+  {
+    int need0 = FI.slots0 < 0 ? P.dof[0] : FI.slots0;
+    if (P.maxdof[0] < need0 && FI.nleaf_min == 1) BAIL(MCI_ERR_INVALID, "integrand %d reads %d slots of variable 1 but maxdof = %d", P.fid, need0, P.maxdof[0]);
+    if (FI.nleaf_min > 1)
+      for (int l = 0; l < FI.nleaf_min; ++l) if (P.maxdof[P.leaf[l].top] < 1) BAIL(MCI_ERR_INVALID, "integrand %d needs one slot of every variable", P.fid);
+    if (p->measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
+      const DevLeaf &E = P.leaf[nleaf - 1];
+      if (E.kind != MCI_LEAF_DISCRETE || P.obs_len[0] < E.nbins || P.maxdof[E.top] < 1)
+        BAIL(MCI_ERR_INVALID, "bin-by-discrete measure needs a Discrete last leaf and obs_len[0] >= its size");
+    } else if (p->measure_kind != MCI_MEASURE_DEFAULT) BAIL(MCI_ERR_INVALID, "unknown measure kind %d", p->measure_kind);
+  }
+  /* neighbor graph: configuration.jl:201-209 default, or the caller's CSR */
+  if (p->neighbor_ptr) {
+    if (p->neighbor_ptr[nd] > MAX_ND * MAX_ND) BAIL(MCI_ERR_INVALID, "neighbor graph too large");
+    for (int d = 0; d <= nd; ++d) P.nb_ptr[d] = p->neighbor_ptr[d];
+    for (int k = 0; k < P.nb_ptr[nd]; ++k) {
+      P.nb_idx[k] = p->neighbor_idx[k];
+      if (P.nb_idx[k] < 0 || P.nb_idx[k] >= nd) BAIL(MCI_ERR_INVALID, "neighbor index out of range");
+    }
+    for (int d = 0; d < nd; ++d) if (P.nb_ptr[d + 1] <= P.nb_ptr[d]) BAIL(MCI_ERR_INVALID, "integrand %d has no neighbor", d + 1);
+  } else {
+    int k = 0;
+    for (int d = 1; d <= nd; ++d) {
+      P.nb_ptr[d - 1] = k;
+      if (d == nd) P.nb_idx[k++] = 0;
+      else if (d == 1) { if (nd == 2) P.nb_idx[k++] = 1; else { P.nb_idx[k++] = nd - 1; P.nb_idx[k++] = 1; } }
+      else if (d == nd - 1) P.nb_idx[k++] = nd - 3;
+      else { P.nb_idx[k++] = d - 2; P.nb_idx[k++] = d; }
+    }
+    P.nb_ptr[nd] = k;
+  }
+  for (int i = 0; i < p->n_userdata && i < MCI_MAX_USERDATA; ++i) P.userdata[i] = p->userdata[i];
+  {
+    const double pi = 3.14159265358979323846;
+    if (P.fid == MCI_F_GAUSS_ND) P.fconst[0] = pow(2 * pi, -0.5 * P.dof[0]);
+    if (P.fid == MCI_F_BUBBLE) P.fconst[0] = 1.0 / pow(2 * pi, P.userdata[4]);
+    if (P.fid == MCI_F_HYPERSPHERE3) for (int i = 1; i <= 3; ++i) P.fconst[i - 1] = volume_inverse(i + 1);
+  }
+  P.pa_dim = std::max(nd, nv);
+  h->pa_len = 3 * nd * P.pa_dim;
+  PackedLayout &Y = h->Y;
+  Y.n_block = p->n_block; Y.obs_total = ot; Y.hist_len = ho; Y.nd = nd; Y.pa_len = h->pa_len;
+  Y.off_hist = 0; Y.off_obs = ho; Y.off_cnt = Y.off_obs + p->n_block * ot; Y.off_visited = Y.off_cnt + p->n_block;
+  Y.off_propose = Y.off_visited + nd; Y.off_accept = Y.off_propose + h->pa_len; Y.off_neval = Y.off_accept + h->pa_len;
+  Y.len = Y.off_neval + 1;
+  /* own the pointers of the problem copy */
+  h->p.topvar_nleaf = nullptr; h->p.topvar_offset = nullptr; h->p.leaf = nullptr; h->p.dof = nullptr; h->p.obs_len = nullptr;
+  h->p.neighbor_ptr = nullptr; h->p.neighbor_idx = nullptr; h->p.userdata = nullptr;
+#undef BAIL
+
+  /* ---- device resources ---- */
+  *out = h; /* so that failures below can be cleaned up by the caller through mci_destroy */
+#define TRY(x) do { int rc_ = (x); if (rc_) { snprintf(g_err, 256, "%s", h->err); mci_destroy(h); *out = nullptr; return rc_; } } while (0)
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, MCI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); mci_destroy(h); *out = nullptr; return MCI_ERR_CUDA; } } while (0)
+  CUT(cudaSetDevice(h->device));
+  CUT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUT(cudaEventCreate(&h->ev_iter0)); CUT(cudaEventCreate(&h->ev_fill0));
+  CUT(cudaEventCreate(&h->ev_fill1)); CUT(cudaEventCreate(&h->ev_iter1));
+  TRY(dev_alloc(h, &h->d_grids, go + 1)); TRY(dev_alloc(h, &h->d_dist, dd + 1)); TRY(dev_alloc(h, &h->d_accum, da + 1));
+  TRY(dev_alloc(h, &h->d_reweight, nd)); TRY(dev_alloc(h, &h->d_goal, nd)); TRY(dev_alloc(h, &h->d_alpha, nleaf));
+  TRY(dev_alloc(h, &h->d_gmaps, mo + 2));
+  TRY(dev_alloc(h, &h->d_leaf_grid_off, nleaf)); TRY(dev_alloc(h, &h->d_leaf_dist_off, nleaf)); TRY(dev_alloc(h, &h->d_leaf_acc_off, nleaf));
+  TRY(dev_alloc(h, &h->d_packed, Y.len)); TRY(dev_alloc(h, &h->d_flags, 2)); TRY(dev_alloc(h, &h->d_err, 1));
+  CUT(cudaMallocHost((void **)&h->h_packed, Y.len * sizeof(double)));
+  CUT(cudaMallocHost((void **)&h->h_flags, 2 * sizeof(unsigned long long)));
+  CUT(cudaMallocHost((void **)&h->h_err, sizeof(int)));
+  memset(h->h_packed, 0, Y.len * sizeof(double));
+  h->h_flags[0] = h->h_flags[1] = 0; *h->h_err = 0;
+  CUT(cudaMemcpy(h->d_alpha, h->alpha.data(), nleaf * sizeof(double), cudaMemcpyHostToDevice));
+  CUT(cudaMemcpy(h->d_leaf_grid_off, h->leaf_grid_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
+  CUT(cudaMemcpy(h->d_leaf_dist_off, h->leaf_dist_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
+  CUT(cudaMemcpy(h->d_leaf_acc_off, h->leaf_acc_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
+  /* initial maps as the reference constructors leave them (variable.jl:137, 305-315; configuration.jl:172-175) */
+  {
+    std::vector<double> g(go + 1), di(dd + 1), ac(da + 1), rw(nd);
+    for (int l = 0; l < nleaf; ++l) {
+      const mci_leaf_t &S = p->leaf[l];
+      if (S.kind == MCI_LEAF_CONTINUOUS) {
+        const int npts = S.nbins + 1;
+        double *q = g.data() + h->leaf_grid_off[l];
+        for (int i = 0; i < npts; ++i) { double t = (double)i / (npts - 1); q[i] = (1 - t) * S.lower + t * S.upper; }
+        q[0] = S.lower; q[npts - 1] = S.upper;
+      } else {
+        const int n = S.nbins;
+        double *d = di.data() + h->leaf_dist_off[l], *a = ac.data() + h->leaf_acc_off[l];
+        for (int i = 0; i < n; ++i) d[i] = 1.0 / n;
+        a[0] = 0.0;
+        for (int i = 1; i <= n; ++i) { double s = 0.0; for (int k = 0; k < i; ++k) s += d[k]; a[i] = s; }
+      }
+    }
+    for (int d = 0; d < nd; ++d) rw[d] = 1.0 / nd;
+    CUT(cudaMemcpy(h->d_grids, g.data(), (go + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    CUT(cudaMemcpy(h->d_dist, di.data(), (dd + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    CUT(cudaMemcpy(h->d_accum, ac.data(), (da + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    CUT(cudaMemcpy(h->d_reweight, rw.data(), nd * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  TRY(plan(h));
+#undef TRY
+#undef CUT
+  return MCI_OK;
+}
+
+int mci_sizes(const mci_handle_t *h, int32_t *grid_len, int32_t *disc_len, int32_t *hist_len, int32_t *obs_len,
+              int32_t *nd, int32_t *pa_len) {
+  if (!h) return MCI_ERR_INVALID;
+  if (grid_len) *grid_len = h->grid_len;
+  if (disc_len) *disc_len = h->disc_len;
+  if (hist_len) *hist_len = h->hist_len;
+  if (obs_len) *obs_len = h->obs_total;
+  if (nd) *nd = h->nd;
+  if (pa_len) *pa_len = h->pa_len;
+  return MCI_OK;
+}
+
+int mci_set_maps(mci_handle_t *h, const double *grids, const double *dist, const double *accum, const double *rw) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  if (grids && h->grid_len) CU(h, cudaMemcpyAsync(h->d_grids, grids, h->grid_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (dist && h->disc_len) CU(h, cudaMemcpyAsync(h->d_dist, dist, h->disc_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (accum && h->accum_len) CU(h, cudaMemcpyAsync(h->d_accum, accum, h->accum_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (rw) CU(h, cudaMemcpyAsync(h->d_reweight, rw, h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream)); /* the caller may reuse its buffers */
+  h->maps_dirty = true;
+  return MCI_OK;
+}
+
+int mci_get_maps(mci_handle_t *h, double *grids, double *dist, double *accum, double *rw) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  if (grids && h->grid_len) CU(h, cudaMemcpyAsync(grids, h->d_grids, h->grid_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (dist && h->disc_len) CU(h, cudaMemcpyAsync(dist, h->d_dist, h->disc_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (accum && h->accum_len) CU(h, cudaMemcpyAsync(accum, h->d_accum, h->accum_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (rw) CU(h, cudaMemcpyAsync(rw, h->d_reweight, h->nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return MCI_OK;
+}
+
+int mci_set_partition(mci_handle_t *h, int32_t rank, int32_t world) {
+  if (!h) return MCI_ERR_INVALID;
+  if (world < 1 || rank < 0 || rank >= world || h->p.n_block % world != 0) /* main.jl:122 */
+    return fail(h, MCI_ERR_INVALID, "invalid partition rank=%d world=%d n_block=%d", rank, world, h->p.n_block);
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->rank = rank; h->world = world;
+  return plan(h);
+}
+
+int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  const mci_problem_t &p = h->p;
+  const int n_local = p.n_block / h->world;
+  CU(h, cudaEventRecord(h->ev_iter0, h->stream));
+  if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
+  CU(h, cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned long long), h->stream));
+  if (h->hist_mode == HIST_GLOBAL_RED)
+    CU(h, cudaMemsetAsync(h->d_cta_hist, 0, (size_t)h->n_hist_copies * h->hist_len * sizeof(double), h->stream));
+  void *args[2];
+  FillArgs FA;
+  ChainArgs CA;
+  if (p.solver == MCI_SOLVER_VEGAS) {
+    FA.gmaps = h->d_gmaps; FA.tile_obs = h->d_tile_obs; FA.tile_cnt = h->d_tile_cnt; FA.cta_hist = h->d_cta_hist;
+    FA.flags = h->d_flags; FA.iter = iter; FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
+    FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
+    FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
+    args[0] = &h->dp; args[1] = &FA;
+  } else {
+    CA.gmaps = h->d_gmaps; CA.reweight = h->d_reweight; CA.cta_stats = h->d_cta_stats; CA.cta_hist = h->d_cta_hist;
+    CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, p.walkers_per_block);
+    CA.ctas_per_block = h->ctas_per_block; CA.n_local_blocks = n_local; CA.rank = h->rank; CA.world = h->world;
+    CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;
+    args[0] = &h->dp; args[1] = &CA;
+  }
+  CU(h, cudaEventRecord(h->ev_fill0, h->stream));
+  CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
+  CU(h, cudaEventRecord(h->ev_fill1, h->stream));
+  h->launches++;
+  const int fin_threads = 256;
+  const int total_el = h->Y.len;
+  const int fin_grid = std::max(1, std::min(4 * h->n_sm, (total_el * 32 + fin_threads - 1) / fin_threads));
+  if (p.solver == MCI_SOLVER_VEGAS) {
+    finalize_vegas_kernel<<<fin_grid, fin_threads, 0, h->stream>>>(h->Y, h->d_tile_obs, h->d_tile_cnt, h->d_cta_hist,
+                                                                  h->hist_mode == HIST_NONE ? 0 : h->n_hist_copies, n_local,
+                                                                  h->tiles_per_block, h->rank, h->world, p.neval_per_block,
+                                                                  h->d_packed);
+  } else {
+    finalize_chain_kernel<<<fin_grid, fin_threads, 0, h->stream>>>(h->Y, h->d_cta_stats, h->d_cta_hist,
+                                                                  h->hist_mode == HIST_NONE ? 0 : h->n_hist_copies, n_local,
+                                                                  h->ctas_per_block, h->rank, h->world, h->d_packed);
+  }
+  CU(h, cudaGetLastError());
+  h->launches++;
+  if (h->comm) {
+    int rc = g_nccl.AllReduce(h->d_packed, h->d_packed, (size_t)h->Y.len, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream);
+    if (rc != 0) return fail(h, MCI_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  }
+  CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaEventRecord(h->ev_iter1, h->stream));
+  h->have_iteration = true;
+  return MCI_OK;
+}
+
+int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out) {
+  if (!h || !out) return MCI_ERR_INVALID;
+  if (!h->have_iteration) return fail(h, MCI_ERR_INVALID, "no iteration has been launched");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->fill_ms, h->ev_fill0, h->ev_fill1);
+  cudaEventElapsedTime(&h->iter_ms, h->ev_iter0, h->ev_iter1);
+  const PackedLayout &Y = h->Y;
+  const double *pk = h->h_packed;
+  const int nb = Y.n_block;
+  const double B1 = (double)(nb + 1);
+  /* floors of clearStatistics! (configuration.jl:238-250, variable.jl:565): one per block config + the summed config */
+  if (out->block_obs) memcpy(out->block_obs, pk + Y.off_obs, sizeof(double) * nb * Y.obs_total);
+  if (out->block_norm) for (int b = 0; b < nb; ++b) out->block_norm[b] = 1.0e-10 + pk[Y.off_cnt + b];
+  if (out->hist) for (int i = 0; i < Y.hist_len; ++i) out->hist[i] = B1 * 1.0e-10 + pk[Y.off_hist + i];
+  if (out->visited) for (int i = 0; i < Y.nd; ++i) out->visited[i] = B1 * 1.0e-8 + pk[Y.off_visited + i];
+  if (out->propose) for (int i = 0; i < Y.pa_len; ++i) out->propose[i] = B1 * 1.0e-8 + pk[Y.off_propose + i];
+  if (out->accept) for (int i = 0; i < Y.pa_len; ++i) out->accept[i] = B1 * 1.0e-10 + pk[Y.off_accept + i];
+  if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
+  if (h->h_flags[1]) return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #1 integrand nonzero!"); /* mcmc/montecarlo.jl:109-113 */
+  if (*h->h_err) {
+    *h->h_err = 0;
+    cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+    return fail(h, MCI_ERR_NUMERIC, "train!: histogram should be all finite and positive"); /* variable.jl:212-213 */
+  }
+  for (int b = 0; b < nb; ++b)
+    if (!(1.0e-10 + pk[Y.off_cnt + b] > 0.0)) /* main.jl:269-271 */
+      return fail(h, MCI_ERR_NUMERIC, "Block normalization = %g is not positively defined!", pk[Y.off_cnt + b]);
+  return MCI_OK;
+}
+
+int mci_run_iteration(mci_handle_t *h, uint64_t iter, mci_iteration_out_t *out) {
+  int rc = mci_launch_iteration(h, iter);
+  if (rc) return rc;
+  mci_iteration_out_t none;
+  memset(&none, 0, sizeof none);
+  return mci_fetch_iteration(h, out ? out : &none);
+}
+
+int mci_refine(mci_handle_t *h) {
+  if (!h) return MCI_ERR_INVALID;
+  if (!h->have_iteration) return fail(h, MCI_ERR_INVALID, "mci_refine before any iteration");
+  CU(h, cudaSetDevice(h->device));
+  if (!h->dp.any_adapt) return MCI_OK;
+  int nmax = 1;
+  for (int l = 0; l < h->nleaf; ++l) nmax = std::max(nmax, h->dp.leaf[l].nbins);
+  const size_t sm = (size_t)(3 * nmax + 2) * sizeof(double);
+  if (sm > 48 * 1024) CU(h, cudaFuncSetAttribute((const void *)refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  refine_kernel<<<h->nleaf, 256, sm, h->stream>>>(h->dp, h->Y, h->d_packed, h->d_alpha, h->d_leaf_grid_off, h->d_leaf_dist_off,
+                                                  h->d_leaf_acc_off, h->d_grids, h->d_dist, h->d_accum, h->d_err);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  int rc = enqueue_build_maps(h);
+  if (rc) return rc;
+  if (!h->async_mode) {
+    CU(h, cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (*h->h_err) {
+      *h->h_err = 0;
+      cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+      return fail(h, MCI_ERR_NUMERIC, "train!: histogram should be all finite and positive");
+    }
+  }
+  return MCI_OK;
+}
+
+int mci_reweight(mci_handle_t *h, double gamma, const double *goal) {
+  if (!h) return MCI_ERR_INVALID;
+  if (!h->have_iteration) return fail(h, MCI_ERR_INVALID, "mci_reweight before any iteration");
+  CU(h, cudaSetDevice(h->device));
+  if (goal) CU(h, cudaMemcpyAsync(h->d_goal, goal, h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  reweight_kernel<<<1, 32, 0, h->stream>>>(h->Y, h->d_packed, gamma, goal ? h->d_goal : nullptr, h->d_reweight);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  if (goal) CU(h, cudaStreamSynchronize(h->stream));
+  return MCI_OK;
+}
+
+int mci_set_async(mci_handle_t *h, int32_t on) {
+  if (!h) return MCI_ERR_INVALID;
+  h->async_mode = on != 0;
+  return MCI_OK;
+}
+
+int mci_comm_unique_id(void *id128) {
+  if (!id128) return MCI_ERR_INVALID;
+  if (!nccl_load()) return fail(nullptr, MCI_ERR_COMM, "libnccl.so.2 not loadable: %s", dlerror());
+  nccl_uid_t id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, MCI_ERR_COMM, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(id128, &id, 128);
+  return MCI_OK;
+}
+
+int mci_comm_init(mci_handle_t *h, const void *id128, int32_t rank, int32_t world) {
+  if (!h || !id128) return MCI_ERR_INVALID;
+  if (!nccl_load()) return fail(h, MCI_ERR_COMM, "libnccl.so.2 not loadable");
+  int rc = mci_set_partition(h, rank, world);
+  if (rc) return rc;
+  nccl_uid_t id;
+  memcpy(&id, id128, 128);
+  CU(h, cudaSetDevice(h->device));
+  if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+  if (rc != 0) { h->comm = nullptr; return fail(h, MCI_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
+  return MCI_OK;
+}
+
+int mci_stats_device_ptr(mci_handle_t *h, void **dptr, int64_t *n_doubles) {
+  if (!h) return MCI_ERR_INVALID;
+  if (dptr) *dptr = h->d_packed;
+  if (n_doubles) *n_doubles = h->Y.len;
+  return MCI_OK;
+}
+
+/* re-read the packed statistics from the device (after an external collective on mci_stats_device_ptr) */
+int mci_stats_sync_host(mci_handle_t *h) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return MCI_OK;
+}
+
+int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t first, int32_t count, double *x,
+                      int32_t *bins, double *jac, double *weights) {
+  if (!h || count < 0) return MCI_ERR_INVALID;
+  if (h->p.solver != MCI_SOLVER_VEGAS) return fail(h, MCI_ERR_UNSUPPORTED, "mci_trace_samples: VEGAS sampler only");
+  if (count == 0) return MCI_OK;
+  CU(h, cudaSetDevice(h->device));
+  const void *k = lookup_vegas_trace(h->dp.fid);
+  if (!k) return fail(h, MCI_ERR_UNSUPPORTED, "no trace kernel for integrand %d", h->dp.fid);
+  if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
+  const int nd = h->dp.n_draw, ni = h->ni;
+  double *dx = nullptr, *dj = nullptr, *dw = nullptr;
+  int *db = nullptr;
+  CU(h, cudaMalloc((void **)&dx, sizeof(double) * (size_t)count * nd));
+  CU(h, cudaMalloc((void **)&db, sizeof(int) * (size_t)count * nd));
+  CU(h, cudaMalloc((void **)&dj, sizeof(double) * (size_t)count));
+  CU(h, cudaMalloc((void **)&dw, sizeof(double) * (size_t)count * ni));
+  const double *gm = h->d_gmaps;
+  uint32_t blk = (uint32_t)block;
+  void *args[] = {&h->dp, &gm, &iter, &blk, &first, &count, &dx, &db, &dj, &dw};
+  cudaError_t e = cudaLaunchKernel(k, dim3((count + 127) / 128), dim3(128), args, 0, h->stream);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && x) e = cudaMemcpy(x, dx, sizeof(double) * (size_t)count * nd, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && bins) e = cudaMemcpy(bins, db, sizeof(int) * (size_t)count * nd, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && jac) e = cudaMemcpy(jac, dj, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && weights) e = cudaMemcpy(weights, dw, sizeof(double) * (size_t)count * ni, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(db); cudaFree(dj); cudaFree(dw);
+  if (e != cudaSuccess) return fail(h, MCI_ERR_CUDA, "mci_trace_samples: %s", cudaGetErrorString(e));
+  return MCI_OK;
+}
+
+int mci_launch_count(const mci_handle_t *h, uint64_t *n) {
+  if (!h || !n) return MCI_ERR_INVALID;
+  *n = h->launches;
+  return MCI_OK;
+}
+
+int mci_last_timing(mci_handle_t *h, float *fill_ms, float *iteration_ms) {
+  if (!h) return MCI_ERR_INVALID;
+  if (fill_ms) *fill_ms = h->fill_ms;
+  if (iteration_ms) *iteration_ms = h->iter_ms;
+  return MCI_OK;
+}
+
+int mci_launch_info(const mci_handle_t *h, int32_t *grid, int32_t *threads, int64_t *smem_bytes, int32_t *hist_mode,
+                    int32_t *tiles_per_block, int32_t *samples_per_thread) {
+  if (!h) return MCI_ERR_INVALID;
+  if (grid) *grid = h->grid;
+  if (threads) *threads = h->threads;
+  if (smem_bytes) *smem_bytes = (int64_t)h->smem;
+  if (hist_mode) *hist_mode = h->hist_mode;
+  if (tiles_per_block) *tiles_per_block = h->tiles_per_block;
+  if (samples_per_thread) *samples_per_thread = h->spt;
+  return MCI_OK;
+}
+
+const char *mci_kernel_name(const mci_handle_t *h) { return h ? h->kernel_name : ""; }
+
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of the handle is launched on) */
+int mci_timer_start(mci_handle_t *h) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  if (!h->ev_t0) { CU(h, cudaEventCreate(&h->ev_t0)); CU(h, cudaEventCreate(&h->ev_t1)); }
+  CU(h, cudaEventRecord(h->ev_t0, h->stream));
+  return MCI_OK;
+}
+int mci_timer_stop(mci_handle_t *h, float *ms) {
+  if (!h || !ms || !h->ev_t0) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaEventRecord(h->ev_t1, h->stream));
+  CU(h, cudaEventSynchronize(h->ev_t1));
+  CU(h, cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return MCI_OK;
+}
+
+int mci_fp64_peak(int32_t device, double *tflops) {
+  if (!tflops) return MCI_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, MCI_ERR_NO_DEVICE, "no CUDA device %d", device);
+  CU(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  double *d = nullptr;
+  CU(nullptr, cudaMalloc((void **)&d, 8));
+  cudaEvent_t e0, e1;
+  CU(nullptr, cudaEventCreate(&e0)); CU(nullptr, cudaEventCreate(&e1));
+  const int iters = 1 << 14, threads = 256, grid = prop.multiProcessorCount * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<grid, threads>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(d); return fail(nullptr, MCI_ERR_CUDA, "fp64 probe: %s", cudaGetErrorString(e)); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double fl = 2.0 * 8.0 * iters * (double)threads * grid;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return MCI_OK;
+}
+
+}  // extern "C"

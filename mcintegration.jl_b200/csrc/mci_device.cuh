@@ -1,0 +1,229 @@
+/*
+ * mci_device.cuh — device-side core of libmcib200 (sm_100a): problem description as a
+ * kernel parameter, Philox4x32-10 counter RNG, the adaptive-map draws (Continuous /
+ * Discrete), the histogram scatter policies and the warp/CTA reductions.
+ *
+ * Reference arithmetic restated here (paths relative to numericalEFT/MCIntegration.jl v0.4.2):
+ *   Continuous create!/shift! map   src/distribution/sampler.jl:293-305, 336-386
+ *   Discrete   create!/shift!       src/distribution/sampler.jl:13-22, 57-71
+ *   locate (bisection)              src/distribution/common.jl:8-36
+ *   accumulate!                     src/distribution/variable.jl:196-200, 362-367, 474-478
+ *
+ * The map arithmetic uses explicit round-to-nearest intrinsics (never contracted into
+ * FMA) so that `x` and the bin index are bit-identical to a plain IEEE evaluation of the
+ * reference's expressions; see DESIGN.md "Numerics".
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcib200.h"
+
+namespace mci {
+
+constexpr int MAX_DRAW = 64;     /* sum over top-level vars of maxdof * n_leaf                     */
+constexpr int MAX_ND = MCI_MAX_INTEGRAND + 1;
+constexpr int WARP = 32;
+
+/* histogram scatter policies (MCI_HIST_*) */
+constexpr int HIST_NONE = 0;         /* no adaptive leaf                                            */
+constexpr int HIST_SMEM_ATOMIC = 1;  /* one CTA-shared fp64 histogram, shared-memory CAS atomics    */
+constexpr int HIST_GLOBAL_RED = 2;   /* RED.ADD.F64 into replicated global copies (L2)              */
+constexpr int HIST_WARP_PRIVATE = 3; /* one private histogram per warp, conflict-ranked plain RMW   */
+
+struct DevLeaf {
+  int kind, nbins, adapt, lower_i;
+  int map_off;  /* Continuous: offset (in bins) into the pair table; Discrete: offset into dist     */
+  int acc_off;  /* Discrete: offset into accumulation                                               */
+  int hist_off; /* offset into the concatenated histogram                                           */
+  int top;      /* owning top-level variable                                                        */
+  int base;     /* flat index of (this leaf, slot 1) in the per-sample x[] / bin[] arrays           */
+  int stride;   /* flat-index stride between consecutive slots (= n_leaf of the owning variable)    */
+  int smem_off; /* offset (in doubles) of this leaf's map inside the CTA's shared-memory map area   */
+  int pad_;
+  double nbins_d;
+};
+
+/* Passed by value as a __grid_constant__ kernel parameter (constant bank, uniform loads). */
+struct DevProblem {
+  int solver, fid, measure_kind, ni, nd, nv, nleaf, n_draw;
+  int obs_total, hist_len, pa_dim, measurefreq;
+  int need_pad;   /* some dof[i] != maxdof  (vegas/montecarlo.jl:82)                                */
+  int any_adapt;
+  int map_doubles; /* doubles of shared memory holding all maps                                     */
+  int n_tslot;     /* sum of maxdof over top-level variables                                        */
+  int top_nleaf[MCI_MAX_TOPVAR], top_first[MCI_MAX_TOPVAR], top_base[MCI_MAX_TOPVAR], maxdof[MCI_MAX_TOPVAR];
+  int top_tslot[MCI_MAX_TOPVAR]; /* first top-level slot index of the variable                      */
+  int top_skip[MCI_MAX_TOPVAR];  /* single Discrete leaf with one value: updates skip it            */
+  int dof[MAX_ND * MCI_MAX_TOPVAR];
+  int same_dof[MCI_MAX_INTEGRAND]; /* dof[i] == maxdof                                               */
+  int obs_off[MCI_MAX_INTEGRAND], obs_len[MCI_MAX_INTEGRAND];
+  int nb_ptr[MAX_ND + 1], nb_idx[MAX_ND * MAX_ND];
+  DevLeaf leaf[MCI_MAX_LEAF];
+  double userdata[MCI_MAX_USERDATA];
+  double fconst[4]; /* integrand constants evaluated on the host with the C library              */
+  double thermal_ratio;
+  uint64_t seed;
+  __host__ __device__ int pa_len_() const { return 3 * nd * pa_dim; }
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon et al. 2011).  Stream layout (DESIGN.md "RNG"):                     */
+/*   key = (seed_lo, seed_hi ^ iter*0x9E3779B1), counter = (idx_lo, idx_hi, pair, block)     */
+/* ---------------------------------------------------------------------------------------- */
+struct PhiloxKey {
+  uint32_t k[10][2];
+};
+
+__host__ __device__ inline void philox_expand_key(uint64_t seed, uint64_t iter, PhiloxKey &K) {
+  uint32_t k0 = (uint32_t)seed;
+  uint32_t k1 = (uint32_t)(seed >> 32) ^ ((uint32_t)iter * 0x9E3779B1u);
+  for (int r = 0; r < 10; ++r) {
+    K.k[r][0] = k0;
+    K.k[r][1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &K,
+                                               uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[r][0];
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[r][1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+/* k * 2^-52 with k the top 52 bits of (hi:lo): exponent trick, exact (no int->fp conversion) */
+__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
+  uint32_t h = (hi >> 12) | 0x3FF00000u;
+  uint32_t l = __funnelshift_r(lo, hi, 12);
+  return __dsub_rn(__hiloint2double((int)h, (int)l), 1.0);
+}
+
+/* sequential stream for the Markov-chain solvers: rand(config.rng) */
+struct Rng {
+  uint32_t c0, c1, c2, c3;
+  uint32_t b2, b3;
+  int have;
+  __device__ __forceinline__ void init(uint64_t idx, uint32_t block) {
+    c0 = (uint32_t)idx; c1 = (uint32_t)(idx >> 32); c2 = 0; c3 = block; have = 0;
+  }
+  __device__ __forceinline__ double rand(const PhiloxKey &K) {
+    if (have) { have = 0; return u52(b2, b3); }
+    uint32_t o0, o1;
+    philox4x32_10(c0, c1, c2, c3, K, o0, o1, b2, b3);
+    c2 += 1;
+    have = 1;
+    return u52(o0, o1);
+  }
+  /* rand(rng, 1:n) -> 1 + floor(u*n) */
+  __device__ __forceinline__ int randint(const PhiloxKey &K, int n) {
+    int k = (int)floor(__dmul_rn(rand(K), (double)n)) + 1;
+    return k > n ? n : k;
+  }
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* maps                                                                                      */
+/* ---------------------------------------------------------------------------------------- */
+
+/* One draw on a Continuous map (sampler.jl:295-303): pair[i] = (grid[i], grid[i+1]-grid[i]).
+ * Returns x; iy = 0-based increment; dx = width of the increment. */
+__device__ __forceinline__ double map_continuous(const double2 *__restrict__ pair, int nbins, double nbins_d, double u,
+                                                 int &iy, double &dx) {
+  const double MAGIC = 4503599627370496.0; /* 2^52: (t + 2^52) rounded down holds floor(t) in its low bits */
+  double t = __dmul_rn(u, nbins_d);
+  double f = __dadd_rd(t, MAGIC);
+  int i = __double2loint(f);
+  double fl = __dsub_rn(f, MAGIC);
+  double dy = __dsub_rn(t, fl);
+  i = min(i, nbins - 1);
+  double2 g = pair[i];
+  iy = i;
+  dx = g.y;
+  return __dadd_rn(g.x, __dmul_rn(dy, g.y));
+}
+
+/* locate (common.jl:8-36) clamped into the table instead of throwing; returns 0-based index g
+ * with acc[g] <= u < acc[g+1]; acc has n+1 entries. */
+__device__ __forceinline__ int locate_clamped(const double *__restrict__ acc, int n, double u) {
+  if (u < acc[0]) return 0;
+  int jl = 1, ju = n + 1;
+  while (ju - jl > 1) {
+    int jm = (jl + ju) >> 1;
+    if (u < acc[jm - 1]) ju = jm; else jl = jm;
+  }
+  return jl - 1;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* warp helpers                                                                              */
+/* ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ unsigned lane_id() {
+  unsigned l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* histogram scatter: hist[bin] += v for the 32 lanes of a converged warp                    */
+/* ---------------------------------------------------------------------------------------- */
+
+/* HIST_WARP_PRIVATE: `wh` is this warp's private copy.  Lanes hitting the same bin are ranked
+ * with MATCH.ANY and applied in lane order, one plain LDS/DADD/STS round per rank, so the
+ * result is deterministic.  All 32 lanes must call; inactive lanes pass active=false. */
+__device__ __forceinline__ void hist_add_private(double *wh, int bin, double v, bool active) {
+  const unsigned lane = lane_id();
+  int key = active ? bin : (int)(0x80000000u | lane);
+  unsigned peers = __match_any_sync(0xffffffffu, key);
+  int rank = __popc(peers & ((1u << lane) - 1u));
+  if (__all_sync(0xffffffffu, rank == 0)) {
+    if (active) wh[bin] += v;
+  } else {
+    int maxrank = __reduce_max_sync(0xffffffffu, rank);
+    for (int r = 0; r <= maxrank; ++r) {
+      if (active && rank == r) wh[bin] += v;
+      __syncwarp();
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void hist_add(double *h, int bin, double v, bool active) {
+  if (MODE == HIST_WARP_PRIVATE) {
+    hist_add_private(h, bin, v, active);
+  } else if (MODE == HIST_SMEM_ATOMIC || MODE == HIST_GLOBAL_RED) {
+    if (active) atomicAdd(h + bin, v); /* shared: CAS loop; global: RED.E.ADD.F64 */
+  }
+}
+
+__device__ __forceinline__ void hist_add_rt(int mode, double *h, int bin, double v, bool active) {
+  if (mode == HIST_WARP_PRIVATE) hist_add_private(h, bin, v, active);
+  else if (mode != HIST_NONE) { if (active) atomicAdd(h + bin, v); }
+}
+
+/* stage all maps into shared memory with 16-byte loads: Continuous leaves as (grid, width)
+ * pairs, Discrete leaves as [dist(n) | accumulation(n+1)] */
+__device__ __forceinline__ void stage_maps(const DevProblem &P, double *smaps, const double *__restrict__ gmaps) {
+  const int n2 = P.map_doubles >> 1; /* map area is padded to an even number of doubles */
+  const double2 *src = reinterpret_cast<const double2 *>(gmaps);
+  double2 *dst = reinterpret_cast<double2 *>(smaps);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+}  // namespace mci

@@ -1,0 +1,259 @@
+/*
+ * mci_integrands.cuh — built-in device integrands (enum mci_integrand_id, include/mcib200.h).
+ *
+ * A Julia closure f(x, c) (src/main.jl:25-33) cannot run on the device, so each integrand of the
+ * reference's tests / examples and of the BASELINE configs is a device function selected by id.
+ * `X(leaf, pos)` is the value of pool slot `pos` (1-based, like the reference's x[pos]) of leaf
+ * variable `leaf` (0-based, in top-level order then leaf order).
+ *
+ * MAXD > 0: the variable is one Continuous pool and the loops are fully unrolled over MAXD slots
+ * (predicated on the run-time dof) so that x[] stays in registers; MAXD == 0: run-time loops.
+ */
+#pragma once
+#include "mci_device.cuh"
+
+namespace mci {
+
+#define MCI_PI 3.14159265358979323846
+
+/* value accessors */
+template <int MAXD>
+struct PoolX {
+  double v[MAXD];
+  __device__ __forceinline__ double operator()(int /*leaf*/, int pos) const { return v[pos - 1]; }
+};
+struct FlatX {
+  const double *v;
+  const DevProblem *P;
+  __device__ __forceinline__ double operator()(int leaf, int pos) const {
+    return v[P->leaf[leaf].base + (pos - 1) * P->leaf[leaf].stride];
+  }
+};
+
+#define MCI_FOR_D(i, d, MAXD) _Pragma("unroll") for (int i = 0; i < ((MAXD) ? (MAXD) : (d)); ++i) if (i < (d))
+
+/* s^n for a small positive integer n by repeated squaring */
+__device__ __forceinline__ double ipow(double s, int n) {
+  double r = 1.0;
+  while (n) {
+    if (n & 1) r *= s;
+    s *= s;
+    n >>= 1;
+  }
+  return r;
+}
+
+/* example/bubble.jl:40-50 */
+__device__ __forceinline__ double green(double tau, double w, double beta) {
+  if (tau >= 0.0)
+    return w > 0.0 ? exp(-w * tau) / (1 + exp(-w * beta)) : exp(w * (beta - tau)) / (1 + exp(w * beta));
+  else
+    return w > 0.0 ? -exp(-w * (tau + beta)) / (1 + exp(-w * beta)) : -exp(-w * tau) / (1 + exp(w * beta));
+}
+
+template <int FID>
+struct Integrand;
+
+/* BASELINE C2: (2pi)^(-d/2) exp(-|x|^2/2); fconst[0] = (2pi)^(-d/2) */
+template <>
+struct Integrand<MCI_F_GAUSS_ND> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    const int d = P.dof[0];
+    double s = 0.0;
+    MCI_FOR_D(i, d, MAXD) { double x = X(0, i + 1); s += x * x; }
+    w[0] = P.fconst[0] * exp(-0.5 * s);
+  }
+};
+
+/* test/montecarlo.jl:129-134 */
+template <>
+struct Integrand<MCI_F_LOG_OVER_SQRT> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double x = X(0, 1);
+    w[0] = log(x) / sqrt(x);
+  }
+};
+
+/* Genz corner peak (1 + sum c_i x_i)^-(d+1), pool layout, c = userdata */
+template <>
+struct Integrand<MCI_F_GENZ_CORNER_POOL> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    const int d = P.dof[0];
+    double s = 1.0;
+    MCI_FOR_D(i, d, MAXD) s += P.userdata[i] * X(0, i + 1);
+    w[0] = 1.0 / ipow(s, d + 1);
+  }
+};
+
+/* same on a d-leaf CompositeVar, one slot per leaf */
+template <>
+struct Integrand<MCI_F_GENZ_CORNER_COMP> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    const int d = P.nleaf;
+    double s = 1.0;
+    for (int i = 0; i < d; ++i) s += P.userdata[i] * X(i, 1);
+    w[0] = 1.0 / ipow(s, d + 1);
+  }
+};
+
+/* example/bubble.jl:50-75; userdata = [kF, beta, me, spin, dim, Qsize, extQ_x...]; fconst[0] = (2pi)^-dim */
+template <>
+struct Integrand<MCI_F_BUBBLE> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    const double *ud = P.userdata;
+    double kF = ud[0], beta = ud[1], me = ud[2], spin = ud[3];
+    double R = X(0, 1), th = X(1, 1), ph = X(2, 1), T = X(3, 1);
+    int ext = (int)X(4, 1);
+    double r = R / (1 - R);
+    double sth, cth, sph, cph;
+    sincos(th, &sth, &cth);
+    sincos(ph, &sph, &cph);
+    double k0 = r * sth * cph, k1 = r * sth * sph, k2 = r * cth;
+    double factor = P.fconst[0];
+    factor *= r * r / ((1 - R) * (1 - R)) * sth;
+    double q0 = ud[6 + ext - 1];
+    double kq0 = k0 + q0, kq1 = k1, kq2 = k2;
+    double tau = T;
+    double w1 = ((k0 * k0 + k1 * k1 + k2 * k2) - kF * kF) / (2 * me);
+    double g1 = green(tau, w1, beta);
+    double w2 = ((kq0 * kq0 + kq1 * kq1 + kq2 * kq2) - kF * kF) / (2 * me);
+    double g2 = green(-tau, w2, beta);
+    w[0] = g1 * g2 * spin * factor; /* * cos(2 pi 0 tau / beta) == 1 */
+  }
+};
+
+/* f_k = prod_i (1 + a_k (x_i - 1/2)), a = userdata[0..3] */
+template <>
+struct Integrand<MCI_F_PRODUCT_4> {
+  static constexpr int NI = 4;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    const int d = P.dof[0];
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+    MCI_FOR_D(i, d, MAXD) {
+      double xc = X(0, i + 1) - 0.5;
+      p0 *= (1 + P.userdata[0] * xc);
+      p1 *= (1 + P.userdata[1] * xc);
+      p2 *= (1 + P.userdata[2] * xc);
+      p3 *= (1 + P.userdata[3] * xc);
+    }
+    w[0] = p0; w[1] = p1; w[2] = p2; w[3] = p3;
+  }
+};
+
+/* test/montecarlo.jl:4-9 */
+template <>
+struct Integrand<MCI_F_SPHERE1> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double a = X(0, 1), b = X(0, 2);
+    w[0] = (__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)) < 1.0) ? 1.0 : 0.0;
+  }
+};
+
+/* test/montecarlo.jl:19-24 */
+template <>
+struct Integrand<MCI_F_SPHERE2> {
+  static constexpr int NI = 2;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double a = X(0, 1), b = X(0, 2), z = X(0, 3);
+    double r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+    w[0] = (r2 < 1.0) ? 1.0 : 0.0;
+    w[1] = (__dadd_rn(r2, __dmul_rn(z, z)) < 1.0) ? 1.0 : 0.0;
+  }
+};
+
+/* test/montecarlo.jl:104-111 */
+template <>
+struct Integrand<MCI_F_DISCRETE_X> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = X(0, 1); }
+};
+
+/* test/montecarlo.jl:113-120 */
+template <>
+struct Integrand<MCI_F_DISCRETE2_CONST> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = 1.0; }
+};
+
+/* test/montecarlo.jl:136-147 */
+template <>
+struct Integrand<MCI_F_LATTICE_POOL> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(0, 2)) * cos(X(0, 3))) / (MCI_PI * MCI_PI * MCI_PI);
+  }
+};
+
+/* test/montecarlo.jl:149-164 */
+template <>
+struct Integrand<MCI_F_LATTICE_COMP> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(1, 1)) * cos(X(2, 1))) / (MCI_PI * MCI_PI * MCI_PI);
+  }
+};
+
+/* test/montecarlo.jl:200-216 with N=3; fconst[i-1] = volume_inverse(i+1) */
+template <>
+struct Integrand<MCI_F_HYPERSPHERE3> {
+  static constexpr int NI = 3;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double x1 = X(0, 1);
+    double s = __dmul_rn(x1, x1);
+#pragma unroll
+    for (int i = 1; i <= 3; ++i) {
+      double xi = X(0, i + 1);
+      s = __dadd_rn(s, __dmul_rn(xi, xi));
+      w[i - 1] = s < 1.0 ? P.fconst[i - 1] : 0.0;
+    }
+  }
+};
+
+/* test/thread.jl: (x, x^2, x^3) */
+template <>
+struct Integrand<MCI_F_POLY3> {
+  static constexpr int NI = 3;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double x = X(0, 1);
+    w[0] = x; w[1] = x * x; w[2] = x * x * x;
+  }
+};
+
+/* vegas/montecarlo.jl:69 */
+template <>
+struct Integrand<MCI_F_X2_PLUS_Y2> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA>
+  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+    double a = X(0, 1), b = X(0, 2);
+    w[0] = a * a + b * b;
+  }
+};
+
+/* run-time dispatch for the generic (non-unrolled) kernels */
+#define MCI_FOR_EACH_FID(M)                                                                                         \
+  M(MCI_F_GAUSS_ND) M(MCI_F_LOG_OVER_SQRT) M(MCI_F_GENZ_CORNER_POOL) M(MCI_F_GENZ_CORNER_COMP) M(MCI_F_BUBBLE)      \
+  M(MCI_F_PRODUCT_4) M(MCI_F_SPHERE1) M(MCI_F_SPHERE2) M(MCI_F_DISCRETE_X) M(MCI_F_DISCRETE2_CONST)                 \
+  M(MCI_F_LATTICE_POOL) M(MCI_F_LATTICE_COMP) M(MCI_F_HYPERSPHERE3) M(MCI_F_POLY3) M(MCI_F_X2_PLUS_Y2)
+
+}  // namespace mci

@@ -1,0 +1,366 @@
+/*
+ * mci_vegas.cuh — the VEGAS fill kernels: Philox -> adaptive-map draw of every variable ->
+ * integrand -> Jacobian-weighted observable + per-bin variance histogram, fused in one
+ * persistent kernel.
+ *
+ * Replaces the hot loop of Vegas.montecarlo (src/vegas/montecarlo.jl:117-187):
+ *   :122-131  redraw every pool slot <= maxdof of every variable, jac = prod 1/prob
+ *   :133-137  padding probabilities when dof differs between integrands
+ *   :140-144  weights = integrand(x, config)
+ *   :148-165  observable[i] += w_i * pad_i * jac ; normalization += 1   (every measurefreq-th sample)
+ *   :170-185  histogram += (abs(w_i) * jac)^2 for every (variable, integrand, slot <= dof)
+ *
+ * Work decomposition: one iteration = n_block logical blocks (src/main.jl:121, the unit of the
+ * error estimate) x neval_per_block samples.  A block is cut into tiles of THREADS x spt samples;
+ * persistent CTAs walk the (block, tile) list round-robin.  Sample s of block b draws from the
+ * Philox stream (seed, iter, b, s), so the set of samples does not depend on the launch shape
+ * or on the number of GPUs.  Per-tile observable sums go to tile_obs[] (summed per block, in
+ * tile order, by the finalize kernel -> deterministic); histograms are kept in shared memory
+ * for the CTA's whole life and flushed once to the CTA's global partial.
+ */
+#pragma once
+#include "mci_integrands.cuh"
+
+namespace mci {
+
+struct FillArgs {
+  const double *gmaps;   /* staged map image (see stage_maps)                                      */
+  double *tile_obs;      /* [n_tiles_total][obs_total]                                             */
+  double *tile_cnt;      /* [n_tiles_total] measured samples of the tile                            */
+  double *cta_hist;      /* [n_hist_copies][hist_len] partial histograms (zeroed before launch)     */
+  unsigned long long *flags; /* [0] = number of non-finite weights seen                            */
+  uint64_t iter;
+  uint64_t neval_per_block;
+  int n_local_blocks, rank, world; /* this rank runs blocks b = rank + k*world                      */
+  int tiles_per_block, spt;
+  int hist_mode, n_hist_copies;
+  int maps_in_smem;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* pool kernel: ONE top-level variable that is a single Continuous leaf (the reference's         */
+/* idiomatic `var = Continuous(a, b), dof = [[d1], [d2], ...]`).  Everything about a sample      */
+/* lives in registers.                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+template <int FID, int MAXD, int HMODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+  using F = Integrand<FID>;
+  constexpr int NI = F::NI;
+  constexpr int NWARP = THREADS / 32;
+  constexpr bool CAN_PAD = NI > 1; /* one integrand: dof == maxdof by construction */
+  extern __shared__ __align__(16) double smem[];
+  double *smaps = smem;                                 /* P.map_doubles                          */
+  double *shist = smem + P.map_doubles;                 /* per-warp or per-CTA histogram          */
+  double *sred = shist + (HMODE == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (HMODE == HIST_SMEM_ATOMIC ? P.hist_len : 0));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbins = P.leaf[0].nbins;
+  const double nbins_d = P.leaf[0].nbins_d;
+  const int d = P.maxdof[0];
+  const bool adapt = P.leaf[0].adapt != 0;
+
+  stage_maps(P, smaps, A.gmaps);
+  if (HMODE == HIST_WARP_PRIVATE) {
+    for (int i = tid; i < NWARP * P.hist_len; i += THREADS) shist[i] = 0.0;
+  } else if (HMODE == HIST_SMEM_ATOMIC) {
+    for (int i = tid; i < P.hist_len; i += THREADS) shist[i] = 0.0;
+  }
+  __syncthreads();
+  const double2 *pair = reinterpret_cast<const double2 *>(smaps);
+  double *myhist = HMODE == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
+                   : HMODE == HIST_SMEM_ATOMIC ? shist
+                                               : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
+
+  PhiloxKey K;
+  philox_expand_key(P.seed, A.iter, K);
+  unsigned long long bad = 0;
+
+  const int n_tiles = A.n_local_blocks * A.tiles_per_block;
+  const uint64_t tile_samples = (uint64_t)THREADS * A.spt;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int lb = tile / A.tiles_per_block;
+    const int tb = tile - lb * A.tiles_per_block;
+    const uint32_t block = (uint32_t)(A.rank + lb * A.world);
+    const uint64_t s0 = (uint64_t)tb * tile_samples;
+    double acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = 0.0;
+    int cnt = 0;
+    /* whole warps iterate together (hist_add is a warp-collective); lanes past the end are inactive */
+    for (int k = 0; k < A.spt; ++k) {
+      const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
+      const bool active = s < A.neval_per_block;
+      if (!__any_sync(0xffffffffu, active)) break;
+      PoolX<MAXD> X;
+      int bin[MAXD];
+      double prob[MAXD]; /* only live when P.need_pad */
+      double jac = 1.0;
+#pragma unroll
+      for (int j = 0; j < (MAXD + 1) / 2; ++j) {
+        if (2 * j < d) {
+          uint32_t o0, o1, o2, o3;
+          philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
+          double dx;
+          X.v[2 * j] = map_continuous(pair, nbins, nbins_d, u52(o0, o1), bin[2 * j], dx);
+          double ndx = __dmul_rn(nbins_d, dx);
+          jac *= ndx;
+          if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / ndx;
+          if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
+            X.v[2 * j + 1] = map_continuous(pair, nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dx);
+            ndx = __dmul_rn(nbins_d, dx);
+            jac *= ndx;
+            if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / ndx;
+          }
+        }
+      }
+      double w[NI];
+      F::template eval<MAXD>(X, P, w);
+      double pad[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        pad[i] = 1.0;
+        if (CAN_PAD && P.need_pad && !P.same_dof[i]) {
+          const int di = P.dof[i * P.nv];
+#pragma unroll
+          for (int p = 0; p < MAXD; ++p)
+            if (p >= di && p < d) pad[i] *= prob[p];
+        }
+      }
+      bool finite = true;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
+      if (active && !finite) bad++;
+      const bool meas = active && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
+      if (meas) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[i] += w[i] * pad[i] * jac;
+        cnt++;
+      }
+      if (HMODE != HIST_NONE && adapt) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const double a = fabs(w[i]) * jac;
+          const double w2 = a * a;
+          const int di = P.dof[i * P.nv];
+#pragma unroll
+          for (int p = 0; p < MAXD; ++p)
+            if (p < di) hist_add<HMODE>(myhist, bin[p], w2, active);
+        }
+      }
+    }
+    /* tile flush: warp shuffle -> shared -> one thread sums the warps in order */
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = warp_sum(acc[i]);
+    int wc = __reduce_add_sync(0xffffffffu, cnt);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) sred[warp * (NI + 1) + i] = acc[i];
+      sred[warp * (NI + 1) + NI] = (double)wc;
+    }
+    __syncthreads();
+    if (tid <= NI) {
+      double t = 0.0;
+      for (int wv = 0; wv < NWARP; ++wv) t += sred[wv * (NI + 1) + tid];
+      const size_t gt = (size_t)lb * A.tiles_per_block + tb;
+      if (tid < NI) {
+        /* default measure: observable i is obs_off[i] (obs_len == 1 on this path) */
+        A.tile_obs[gt * P.obs_total + P.obs_off[tid]] = t;
+      } else {
+        A.tile_cnt[gt] = t;
+      }
+    }
+  }
+  if (bad) atomicAdd(A.flags, bad);
+  /* histogram flush: fixed warp order inside the CTA -> one global partial per CTA */
+  if (HMODE == HIST_WARP_PRIVATE || HMODE == HIST_SMEM_ATOMIC) {
+    __syncthreads();
+    double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
+    for (int i = tid; i < P.hist_len; i += THREADS) {
+      double t = 0.0;
+      if (HMODE == HIST_WARP_PRIVATE) {
+        for (int wv = 0; wv < NWARP; ++wv) t += shist[wv * P.hist_len + i];
+      } else {
+        t = shist[i];
+      }
+      out[i] = t;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* one sample on an arbitrary layout (several variables, CompositeVar, Discrete leaves).         */
+/* Shared by the generic fill kernel and by the trace kernel (mci_trace_samples).                */
+/* Draw order = top-level variable, pool slot, leaf (vegas/montecarlo.jl:122-131,                */
+/* sampler.jl:431-440).  tprob[] = probability of each (variable, slot), only when need_pad.     */
+/* ------------------------------------------------------------------------------------------ */
+template <int FID>
+__device__ __forceinline__ void vegas_sample_generic(const DevProblem &P, const double *maps, const PhiloxKey &K,
+                                                     uint64_t s, uint32_t block, double *x, int *bin, double *tprob,
+                                                     double &jac, double *w, double *pad) {
+  using F = Integrand<FID>;
+  jac = 1.0;
+  int k = 0;
+  uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  for (int v = 0; v < P.nv; ++v) {
+    for (int p = 0; p < P.maxdof[v]; ++p) {
+      double tp = 1.0;
+      for (int l = 0; l < P.top_nleaf[v]; ++l, ++k) {
+        const DevLeaf &L = P.leaf[P.top_first[v] + l];
+        double u;
+        if ((k & 1) == 0) {
+          philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(k >> 1), block, K, o0, o1, o2, o3);
+          u = u52(o0, o1);
+        } else {
+          u = u52(o2, o3);
+        }
+        if (L.kind == MCI_LEAF_CONTINUOUS) {
+          double dx;
+          x[k] = map_continuous(reinterpret_cast<const double2 *>(maps + L.smem_off), L.nbins, L.nbins_d, u, bin[k], dx);
+          double ndx = __dmul_rn(L.nbins_d, dx);
+          jac *= ndx;
+          if (P.need_pad) tp *= 1.0 / ndx;
+        } else {
+          const double *dist = maps + L.smem_off;
+          const double *acc = dist + L.nbins;
+          int g = locate_clamped(acc, L.nbins, u);
+          x[k] = (double)(L.lower_i + g);
+          bin[k] = g;
+          double pr = dist[g];
+          jac /= pr;
+          if (P.need_pad) tp *= pr;
+        }
+      }
+      if (P.need_pad) tprob[P.top_tslot[v] + p] = tp;
+    }
+  }
+  FlatX X{x, &P};
+  F::template eval<0>(X, P, w);
+  for (int i = 0; i < P.ni; ++i) {
+    double pd = 1.0;
+    if (P.need_pad && !P.same_dof[i])
+      for (int v = 0; v < P.nv; ++v)
+        for (int p = P.dof[i * P.nv + v]; p < P.maxdof[v]; ++p) pd *= tprob[P.top_tslot[v] + p];
+    pad[i] = pd;
+  }
+}
+
+template <int FID, int THREADS>
+__global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+  using F = Integrand<FID>;
+  constexpr int NI = F::NI;
+  constexpr int NWARP = THREADS / 32;
+  extern __shared__ __align__(16) double smem[];
+  double *smaps = smem;
+  const int map_smem = A.maps_in_smem ? P.map_doubles : 0;
+  double *shist = smem + map_smem;
+  const int hmode = A.hist_mode;
+  double *sred = shist + (hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (hmode == HIST_SMEM_ATOMIC ? P.hist_len : 0));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (A.maps_in_smem) stage_maps(P, smaps, A.gmaps);
+  const int nsh = hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (hmode == HIST_SMEM_ATOMIC ? P.hist_len : 0);
+  for (int i = tid; i < nsh; i += THREADS) shist[i] = 0.0;
+  __syncthreads();
+  const double *maps = A.maps_in_smem ? smaps : A.gmaps;
+  double *myhist = hmode == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
+                   : hmode == HIST_SMEM_ATOMIC ? shist
+                                               : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
+  PhiloxKey K;
+  philox_expand_key(P.seed, A.iter, K);
+  unsigned long long bad = 0;
+  const int OT = P.obs_total;
+
+  const int n_tiles = A.n_local_blocks * A.tiles_per_block;
+  const uint64_t tile_samples = (uint64_t)THREADS * A.spt;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int lb = tile / A.tiles_per_block;
+    const int tb = tile - lb * A.tiles_per_block;
+    const uint32_t block = (uint32_t)(A.rank + lb * A.world);
+    const uint64_t s0 = (uint64_t)tb * tile_samples;
+    double acc[MCI_MAX_OBS];
+    for (int o = 0; o < OT; ++o) acc[o] = 0.0;
+    int cnt = 0;
+    for (int k = 0; k < A.spt; ++k) {
+      const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
+      const bool active = s < A.neval_per_block;
+      if (!__any_sync(0xffffffffu, active)) break;
+      double x[MAX_DRAW], tprob[MAX_DRAW], w[NI], pad[NI], jac;
+      int bin[MAX_DRAW];
+      vegas_sample_generic<FID>(P, maps, K, s, block, x, bin, tprob, jac, w, pad);
+      bool finite = true;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
+      if (active && !finite) bad++;
+      const bool meas = active && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
+      if (meas) {
+        if (P.measure_kind == MCI_MEASURE_DEFAULT) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) acc[P.obs_off[i]] += w[i] * pad[i] * jac;
+        } else { /* obs[0][Ext - lower] += relw[0]; the binning leaf is the last leaf, slot 1 (example/bubble.jl:81-84) */
+          acc[P.obs_off[0] + bin[P.leaf[P.nleaf - 1].base]] += w[0] * pad[0] * jac;
+        }
+        cnt++;
+      }
+      if (hmode != HIST_NONE) {
+        for (int v = 0; v < P.nv; ++v)
+          for (int i = 0; i < NI; ++i) {
+            const double a = fabs(w[i]) * jac;
+            const double w2 = a * a;
+            for (int p = 0; p < P.dof[i * P.nv + v]; ++p)
+              for (int l = 0; l < P.top_nleaf[v]; ++l) {
+                const DevLeaf &L = P.leaf[P.top_first[v] + l];
+                if (L.adapt) hist_add_rt(hmode, myhist + L.hist_off, bin[L.base + p * L.stride], w2, active);
+              }
+          }
+      }
+    }
+    int wc = __reduce_add_sync(0xffffffffu, cnt);
+    __syncthreads();
+    for (int o = 0; o < OT; ++o) {
+      double t = warp_sum(acc[o]);
+      if (lane == 0) sred[warp * (OT + 1) + o] = t;
+    }
+    if (lane == 0) sred[warp * (OT + 1) + OT] = (double)wc;
+    __syncthreads();
+    const size_t gt = (size_t)lb * A.tiles_per_block + tb;
+    for (int o = tid; o <= OT; o += THREADS) {
+      double t = 0.0;
+      for (int wv = 0; wv < NWARP; ++wv) t += sred[wv * (OT + 1) + o];
+      if (o < OT) A.tile_obs[gt * OT + o] = t;
+      else A.tile_cnt[gt] = t;
+    }
+  }
+  if (bad) atomicAdd(A.flags, bad);
+  if (hmode == HIST_WARP_PRIVATE || hmode == HIST_SMEM_ATOMIC) {
+    __syncthreads();
+    double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
+    for (int i = tid; i < P.hist_len; i += THREADS) {
+      double t = 0.0;
+      if (hmode == HIST_WARP_PRIVATE) {
+        for (int wv = 0; wv < NWARP; ++wv) t += shist[wv * P.hist_len + i];
+      } else {
+        t = shist[i];
+      }
+      out[i] = t;
+    }
+  }
+}
+
+/* L0 parity probe (mci_trace_samples): regenerate `count` samples with the generic sampler */
+template <int FID>
+__global__ void vegas_trace_kernel(const __grid_constant__ DevProblem P, const double *gmaps, uint64_t iter, uint32_t block,
+                                   uint64_t first, int count, double *xo, int *bo, double *jo, double *wo) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  PhiloxKey K;
+  philox_expand_key(P.seed, iter, K);
+  double x[MAX_DRAW], tprob[MAX_DRAW], w[Integrand<FID>::NI], pad[Integrand<FID>::NI], jac;
+  int bin[MAX_DRAW];
+  vegas_sample_generic<FID>(P, gmaps, K, first + t, block, x, bin, tprob, jac, w, pad);
+  for (int k = 0; k < P.n_draw; ++k) { xo[(size_t)t * P.n_draw + k] = x[k]; bo[(size_t)t * P.n_draw + k] = bin[k]; }
+  jo[t] = jac;
+  for (int i = 0; i < P.ni; ++i) wo[(size_t)t * P.ni + i] = w[i];
+}
+
+}  // namespace mci

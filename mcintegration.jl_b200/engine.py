@@ -182,6 +182,28 @@ class CudaEngine(HandleEngine):
     def kernel_name(self) -> str:
         return (self.lib.mci_kernel_name(self.h) or b"").decode()
 
+    def set_async(self, on: bool):
+        self._check(self.lib.mci_set_async(self.h, 1 if on else 0))
+
+    def timer_start(self):
+        self._check(self.lib.mci_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.mci_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def stats_sync_host(self):
+        self._check(self.lib.mci_stats_sync_host(self.h))
+
+    def launch_info(self) -> dict:
+        g, t, hm, tpb, spt = (C.c_int32() for _ in range(5))
+        sm = C.c_int64()
+        self._check(self.lib.mci_launch_info(self.h, C.byref(g), C.byref(t), C.byref(sm), C.byref(hm), C.byref(tpb),
+                                             C.byref(spt)))
+        return dict(grid=g.value, threads=t.value, smem_bytes=sm.value, hist_mode=hm.value,
+                    tiles_per_block=tpb.value, samples_per_thread=spt.value, kernel=self.kernel_name())
+
 
 def fp64_peak_tflops(device=0) -> float:
     lib = _abi.load_library()
