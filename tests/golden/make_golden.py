@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Generates tests/golden/golden.json — golden vectors for the deterministic pieces of the hot path.
+
+The reference is Julia and cannot run in this image (no julia binary), so these vectors are NOT outputs of
+the reference; they come from this independent pure-Python restatement of the cited reference lines
+(IEEE doubles, one rounding per operation, no FMA, strictly left-to-right sums).  They pin the C oracle
+(oracle/mci_oracle.c) and, through it, the CUDA path against a second, independently written statement of
+the same arithmetic.  The Philox vectors are the published Random123 known-answer vectors
+(Random123 kat_vectors, philox4x32 10 rounds).  The first cases of every group are the hand cases listed in
+SURVEY.md 8(c).
+
+Run:  python tests/golden/make_golden.py      (rewrites golden.json next to this file)
+Paths cited are relative to numericalEFT/MCIntegration.jl v0.4.2.
+"""
+import json
+import math
+import os
+import random
+
+M32 = 0xFFFFFFFF
+
+
+# ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) ----
+def philox4x32_10(ctr, key):
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M32, p1 & M32, ((p0 >> 32) ^ c3 ^ k1) & M32, p0 & M32
+        k0 = (k0 + 0x9E3779B9) & M32
+        k1 = (k1 + 0xBB67AE85) & M32
+    return [c0, c1, c2, c3]
+
+
+def u52(hi, lo):
+    """top 52 bits of (hi:lo) times 2^-52, in [0, 1)"""
+    return float(((hi << 32) | lo) >> 12) * 2.0 ** -52
+
+
+def uniforms(seed, it, block, idx, n):
+    """the stream layout of DESIGN.md "RNG": key = (seed_lo, seed_hi ^ (iter * 0x9E3779B1 mod 2^32)),
+    counter = (idx_lo, idx_hi, pair, block); each call yields two uniforms (words 0:1, then 2:3)."""
+    key = [seed & M32, ((seed >> 32) ^ ((it * 0x9E3779B1) & M32)) & M32]
+    out = []
+    pair = 0
+    while len(out) < n:
+        o = philox4x32_10([idx & M32, (idx >> 32) & M32, pair, block], key)
+        out.append(u52(o[0], o[1]))
+        out.append(u52(o[2], o[3]))
+        pair += 1
+    return out[:n]
+
+
+# ---- src/distribution/common.jl ----
+def locate(acc, p):
+    """common.jl:8-36; 1-based; None where the reference raises"""
+    n = len(acc)
+    if acc[0] > p or acc[-1] <= p:
+        return None
+    jl, ju = 1, n + 1
+    while ju - jl > 1:
+        jm = (jl + ju) // 2
+        if p < acc[jm - 1]:
+            ju = jm
+        else:
+            jl = jm
+    return jl
+
+
+def smooth(d, factor=6.0):
+    """common.jl:43-54"""
+    if len(d) <= 1:
+        return list(d)
+    new = list(d)
+    new[0] = (d[0] * (factor + 1) + d[1]) / (factor + 2)
+    new[-1] = (d[-1] * (factor + 1) + d[-2]) / (factor + 2)
+    for i in range(1, len(d) - 1):
+        new[i] = (d[i - 1] + d[i] * factor + d[i + 1]) / (factor + 2)
+    return new
+
+
+def seqsum(v):
+    s = 0.0
+    for x in v:
+        s += x
+    return s
+
+
+def rescale(d, alpha):
+    """common.jl:67-83 (output NOT renormalised)"""
+    if len(d) == 1:
+        return list(d)
+    assert all(x > 0 for x in d)
+    s = seqsum(d)
+    out = [x / s for x in d]
+    for i, x in enumerate(out):
+        if 0 < x <= 0.99999999:
+            out[i] = (-(1 - x) / math.log(x)) ** alpha
+    return out
+
+
+# ---- src/distribution/sampler.jl:293-305 (Continuous create!) ----
+def map_continuous(grid, y):
+    N = len(grid) - 1
+    t = y * N
+    iy = int(math.floor(t)) + 1
+    dy = t - (iy - 1)
+    x = grid[iy - 1] + dy * (grid[iy] - grid[iy - 1])
+    prob = 1.0 / (N * (grid[iy] - grid[iy - 1]))
+    return iy, x, prob
+
+
+# ---- src/distribution/variable.jl:206-239 (train! Continuous), :369-382 (Discrete) ----
+def train_continuous(grid, hist, alpha):
+    avg = rescale(smooth(hist, 6.0), alpha)
+    n = len(grid)
+    new = [0.0] * n
+    new[0], new[-1] = grid[0], grid[-1]
+    j, acc = 0, 0.0
+    f_ninc = seqsum(avg) / (n - 1)
+    for i in range(2, n):
+        while acc < f_ninc:
+            j += 1
+            acc += avg[j - 1]
+        acc -= f_ninc
+        new[i - 1] = grid[j] - (acc / avg[j - 1]) * (grid[j] - grid[j - 1])
+    return avg, new
+
+
+def train_discrete(hist, alpha):
+    d = rescale(list(hist), alpha)
+    s = seqsum(d)
+    d = [x / s for x in d]
+    acc = [0.0] + [seqsum(d[: i + 1]) for i in range(len(d))]
+    return d, acc
+
+
+# ---- src/main.jl:296-320, :322-346; src/statistics.jl:186-220 ----
+def mean_std(s, s2, block):
+    mean = s / block
+    if block > 1:
+        v = (s2 / block - mean * mean) / (block - 1)
+        return mean, math.sqrt(v) if v > 0 else 0.0
+    return mean, 0.0
+
+
+def do_reweight(rw, visited, gamma, goal=None):
+    avg = seqsum(visited)
+    rw = list(rw)
+    for i, v in enumerate(visited):
+        rw[i] *= (avg ** gamma) if v <= 1 else ((avg / v) ** gamma)
+    if goal is not None:
+        gs = seqsum(goal)
+        rw = [r * (g / gs) for r, g in zip(rw, goal)]
+    s = seqsum(rw)
+    return [r / s for r in rw]
+
+
+def average(means, stds, init):
+    """statistics.jl:186-220, scalar observable; init 1-based"""
+    mx = len(means)
+    if mx <= init:
+        return means[0], stds[0], 0.0
+    w = [1.0 / (s + 1.0e-10) ** 2 for s in stds[init - 1:]]
+    d = means[init - 1:]
+    ws = sum(w)
+    mea = sum(di * wi / ws for di, wi in zip(d, w))
+    err = 1.0 / math.sqrt(ws)
+    chi2 = sum(wi * (di - mea) ** 2 for di, wi in zip(d, w))
+    return mea, err, chi2 / ((mx - init + 1) - 1)
+
+
+def main():
+    rnd = random.Random(20261017)
+    G = {}
+    G["philox_kat"] = [
+        dict(ctr=[0, 0, 0, 0], key=[0, 0], out=[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        dict(ctr=[M32] * 4, key=[M32] * 2, out=[0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        dict(ctr=[0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], key=[0xA4093822, 0x299F31D0],
+             out=[0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for k in G["philox_kat"]:  # the restatement above must reproduce the published vectors
+        assert philox4x32_10(k["ctr"], k["key"]) == k["out"], k
+    G["uniforms"] = [dict(seed=s, iter=it, block=b, idx=i, u=uniforms(s, it, b, i, 7))
+                     for s, it, b, i in [(1234, 0, 0, 0), (1234, 3, 15, (1 << 33) + 7), (0xDEADBEEFCAFEF00D, 9, 2, 12345)]]
+
+    # locate: test/utility.jl:1-10 plus clamping edges
+    grid = [0.0, 0.1, 0.3, 0.5]
+    eps = 2.0 ** -52
+    pts = [eps, 0.5 - eps, grid[0], 0.05, 0.2, 0.31, 0.1, 0.3, 0.5, -0.1]
+    G["locate"] = dict(acc=grid, p=pts, idx=[locate(grid, p) for p in pts])
+    assert G["locate"]["idx"][:6] == [1, 3, 1, 1, 2, 3]
+
+    # map: SURVEY 8(c) hand cases + random grids
+    maps = []
+    g3 = [0.0, 0.1, 0.4, 1.0]
+    for y in (0.0, 0.5, 0.75, 1 - 2.0 ** -53, 1.0 / 3, 2.0 / 3):
+        iy, x, p = map_continuous(g3, y)
+        maps.append(dict(grid=g3, y=y, iy=iy, x=x, prob=p))
+    for _ in range(6):
+        n = rnd.choice([5, 17, 1000])
+        cuts = sorted(rnd.uniform(-5, 5) for _ in range(n - 2))
+        g = [-5.0] + cuts + [5.0]
+        for _ in range(4):
+            y = rnd.random()
+            iy, x, p = map_continuous(g, y)
+            maps.append(dict(grid=g, y=y, iy=iy, x=x, prob=p))
+    G["map_continuous"] = maps
+
+    # smooth / rescale / train!
+    tc = []
+    hand = [([0.0, 0.1, 0.4, 1.0], [4.0, 1.0, 0.25], 2.0), ([0.0, 0.25, 0.5, 0.75, 1.0], [1.0, 2.0, 3.0, 10.0], 2.0)]
+    for grid_, hist, alpha in hand:
+        avg, new = train_continuous(grid_, hist, alpha)
+        tc.append(dict(grid=grid_, hist=hist, alpha=alpha, smooth=smooth(hist), rescaled=avg, newgrid=new))
+    for n, alpha in [(8, 2.0), (64, 1.5), (1000, 2.0), (1000, 3.0)]:
+        lo, hi = rnd.uniform(-3, 0), rnd.uniform(1, 7)
+        g = [lo + (hi - lo) * i / (n - 1) for i in range(n)]
+        g[-1] = hi
+        hist = [1e-10 + rnd.random() ** 6 * 10 ** rnd.uniform(-3, 3) for _ in range(n - 1)]
+        avg, new = train_continuous(g, hist, alpha)
+        tc.append(dict(grid=g, hist=hist, alpha=alpha, smooth=smooth(hist), rescaled=avg, newgrid=new))
+    G["train_continuous"] = tc
+    td = []
+    for hist, alpha in [([1.0, 2.0, 3.0], 2.0), ([5.0], 2.0), ([1e-10, 7.5, 0.3, 2.0, 9.0, 0.01], 1.5),
+                        ([rnd.random() for _ in range(33)], 2.0)]:
+        d, acc = train_discrete(hist, alpha)
+        td.append(dict(hist=hist, alpha=alpha, dist=d, accum=acc))
+    G["train_discrete"] = td
+
+    # _mean_std against the plain sample statistics (test/statistics.jl:22-46)
+    ms = []
+    for block in (2, 16, 64):
+        m = [rnd.gauss(1.0, 0.3) for _ in range(block)]
+        s, s2 = seqsum(m), seqsum([x * x for x in m])
+        mean, std = mean_std(s, s2, block)
+        mu = sum(m) / block
+        sample_std = math.sqrt(sum((x - mu) ** 2 for x in m) / (block - 1)) / math.sqrt(block)
+        ms.append(dict(block=block, sum=s, sqsum=s2, mean=mean, std=std, sample_mean=mu, sample_std_over_sqrtB=sample_std))
+    G["mean_std"] = ms
+
+    # doReweight!: the fixed point of test/mpi_test.jl:148-168 and generic cases
+    rw = [0.25] * 4
+    seq = []
+    cur = [1.0, 1.0, 1.0, 1.0]
+    cur = [c / 4 for c in cur]
+    for _ in range(5):
+        cur = do_reweight(cur, [1.0, 2.0, 3.0, 4.0], 1.0, [1.0, 2.0, 3.0, 4.0])
+        seq.append(cur)
+    G["reweight"] = dict(
+        mpi_test=dict(visited=[1.0, 2.0, 3.0, 4.0], goal=[1.0, 2.0, 3.0, 4.0], gamma=1.0, start=[0.25] * 4, rounds=seq),
+        generic=[dict(rw=r, visited=v, gamma=g, goal=goal, out=do_reweight(r, v, g, goal))
+                 for r, v, g, goal in [([0.5, 0.5], [10.0, 30.0], 1.0, None), ([0.2, 0.3, 0.5], [0.5, 200.0, 50.0], 0.5, None),
+                                       ([0.2, 0.3, 0.5], [7.0, 200.0, 50.0], 2.0, [1.0, 1.0, 4.0])]])
+
+    # average over iterations (statistics.jl:186-220)
+    means = [rnd.gauss(2.0, 0.01) for _ in range(10)]
+    stds = [abs(rnd.gauss(0.01, 0.002)) for _ in range(10)]
+    G["average"] = [dict(means=means, stds=stds, init=i, out=list(average(means, stds, i))) for i in (1, 2, 10)]
+
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
+    with open(out, "w") as f:
+        json.dump(G, f)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()
