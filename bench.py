@@ -207,12 +207,11 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = maxr(ms)
     value = samples_per_step * args.steps / (ms * 1e-3)
-    # per-launch fill-kernel time (CUDA events around the kernel on its stream), averaged over a few steps
-    eng.set_async(False)
-    for _ in range(3):
-        eng.run_iteration(it); eng.refine(); it += 1
-        fills.append(eng.last_timing()[0])
+    # per-launch fill-kernel time of THE TIMED STEPS: CUDA events recorded around every fill launch on the
+    # library's own stream (mci_fill_history keeps the last 64 pairs)
+    fills = eng.fill_history(min(64, args.steps))
     fill_ms = maxr(sum(fills) / len(fills))
+    eng.set_async(False)
     mean, std = block_statistics(st, cfg, spec.n_block)
 
     # ---------------- end-to-end leg ("e2e"): host buffers every step ----------------
@@ -248,7 +247,14 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = 8.0 * (eng.grid_len + eng.hist_len * info["grid"] + info["tiles_per_block"] * BLOCKS_PER_GPU * 2)
+        # algorithmic HBM bytes per launch (DESIGN.md "Roofline"): read the staged map image once per CTA (L2 hits after
+        # the first), write one histogram partial per CTA and (obs, count) per tile
+        alg_bytes = 8.0 * (2 * eng.hist_len + eng.hist_len * info["grid"] + info["tiles_per_block"] * BLOCKS_PER_GPU * 2)
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_fill_ncu.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         cb = None
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_reference_rate()
@@ -256,14 +262,15 @@ def run_ours(args):
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": WORKLOAD, "samples_per_step": samples_per_step, "n_block": spec.n_block,
-                          "neval_per_block": npb, "l2": "working set (16 KB maps + 64 KB histograms per CTA) lives in "
-                          "shared memory; every step draws fresh Philox samples, nothing is re-read from L2/HBM",
+                          "neval_per_block": npb, "l2": "inputs are generated on chip (Philox counters); the working set (16 KB map + 128 KB "
+                          "striped histogram per CTA) lives in shared memory; every step draws fresh samples, so there is "
+                          "no L2-resident input to flush",
                           "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
                           "smem_bytes": info["smem_bytes"], "hist_mode": info["hist_mode"]},
                "result": {"integral": float(np.ravel(mean[0])[0]), "sigma": float(np.ravel(std[0])[0]),
                           "exact": math.erf(5 / math.sqrt(2)) ** 10},
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "frac": achieved / peak if peak else None, "traffic": traffic,
                             "note": f"{FLOP_PER_SAMPLE:.0f} algorithmic flop/sample (SURVEY 8d) x {BLOCKS_PER_GPU * npb} "
                                     f"samples per launch / {fill_ms:.3f} ms fill kernel (CUDA events, library stream); peak = "
                                     "DFMA probe measured in this run (mci_fp64_peak; MEASURED_PEAKS.json has no fp64 figure)",

@@ -137,7 +137,7 @@ typedef struct mci_problem_t {
   int32_t hist_policy;     /* 0 = auto; see MCI_HIST_* (performance knob, not semantics) */
 } mci_problem_t;
 
-enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3 };
+enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4 };
 
 /*
  * Per-iteration statistics handed back to the host: what `_block!` +
@@ -263,6 +263,10 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
 int mci_launch_count(const mci_handle_t *h, uint64_t *n);
 /* CUDA-event time (ms) of the fill kernel / of the whole device part of the last iteration */
 int mci_last_timing(mci_handle_t *h, float *fill_ms, float *iteration_ms);
+/* CUDA-event durations (ms) of the fill kernel of the most recent iterations, oldest first (at most 64 are kept and
+ * at most `cap` returned; *n = how many).  Synchronises the handle's stream.  Lets a driver that keeps the loop on
+ * the device (mci_launch_iteration) read per-launch kernel times of its timed region afterwards. */
+int mci_fill_history(mci_handle_t *h, float *ms, int32_t cap, int32_t *n);
 /* CUDA-event stopwatch on the handle's stream (all kernels of a handle run on its own stream, which
  * torch.cuda.Event cannot see): start records an event, stop records another, waits for it and returns ms */
 int mci_timer_start(mci_handle_t *h);

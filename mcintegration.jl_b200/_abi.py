@@ -29,7 +29,7 @@ ERR_MCMC_START = -7
 SOLVER_VEGAS, SOLVER_VEGASMC, SOLVER_MCMC = 0, 1, 2
 LEAF_CONTINUOUS, LEAF_DISCRETE = 0, 1
 MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE = 0, 1
-HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE = 0, 1, 2, 3
+HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
 
 # enum mci_integrand_id
 F_GAUSS_ND = 1
@@ -129,6 +129,7 @@ EXPORTS = [
     "mci_launch_info",
     "mci_timer_start",
     "mci_timer_stop",
+    "mci_fill_history",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -182,6 +183,7 @@ def declare(lib, prefix="mci_"):
         f("timer_start", C.c_int, [H])
         f("timer_stop", C.c_int, [H, C.POINTER(C.c_float)])
         f("stats_sync_host", C.c_int, [H])
+        f("fill_history", C.c_int, [H, C.POINTER(C.c_float), C.c_int32, ip])
         f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
     return lib
 

@@ -62,6 +62,8 @@ bool nccl_load() {
 constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 
 thread_local char g_err[256];
+/* auto policy of the pool kernel = 16 bank-striped shared copies: measured 39.8 vs 28.0 G samples/s (one shared copy) on C2, profiles/r1_hist_policies.md */
+constexpr bool MCI_AUTO_STRIPED = true;
 }  // namespace
 
 struct mci_handle_t {
@@ -74,7 +76,11 @@ struct mci_handle_t {
   int rank = 0, world = 1;
   int device = 0, n_sm = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_iter0 = nullptr, ev_fill0 = nullptr, ev_fill1 = nullptr, ev_iter1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_iter0 = nullptr, ev_iter1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  /* ring of event pairs around the fill kernel of the most recent iterations (mci_fill_history) */
+  static constexpr int FILL_RING = 64;
+  cudaEvent_t ev_fill0[FILL_RING] = {}, ev_fill1[FILL_RING] = {};
+  uint64_t n_iterations = 0;
   /* device state */
   double *d_grids = nullptr, *d_dist = nullptr, *d_accum = nullptr, *d_reweight = nullptr, *d_goal = nullptr;
   double *d_alpha = nullptr, *d_gmaps = nullptr;
@@ -172,8 +178,8 @@ int plan(mci_handle_t *h) {
     if (policy == MCI_HIST_WARP_PRIVATE && allow_private && base + nwarp * hist_bytes <= SMEM_MAX) return (int)HIST_WARP_PRIVATE;
     if (policy == MCI_HIST_SMEM_ATOMIC && base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
     if (policy == MCI_HIST_GLOBAL_RED) return (int)HIST_GLOBAL_RED;
-    /* auto: private copies when two CTAs per SM still fit, else one shared copy, else L2 */
-    if (allow_private && base + nwarp * hist_bytes <= 110 * 1024) return (int)HIST_WARP_PRIVATE;
+    /* auto (measured on B200, C2, profiles/r1_hist_policies.md): one CTA-shared fp64 histogram with shared-memory CAS
+     * beats per-warp private copies with MATCH.ANY conflict ranking (ADU-pipe bound) by 2.3x and L2 REDs by 1.5x */
     if (base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
     return (int)HIST_GLOBAL_RED;
   };
@@ -186,14 +192,23 @@ int plan(mci_handle_t *h) {
                        p.measure_kind == MCI_MEASURE_DEFAULT && P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT;
     h->is_pool = false;
     if (pool_layout) {
-      const int nwarp = POOL_THREADS / 32;
-      const size_t red = (size_t)nwarp * (P.ni + 1) * 8;
-      int mode = pick_hist(nwarp, red, true);
+      int nwarp = POOL_THREADS / 32;
+      size_t red = (size_t)nwarp * (P.ni + 1) * 8;
+      int mode = pick_hist(nwarp, red, false); /* the pool kernel has no per-warp private mode */
+      int threads = POOL_THREADS;
+      size_t hs = hist_smem(mode, nwarp);
+      /* 16 bank-striped copies of the histogram, one 1024-thread CTA per SM, when they fit */
+      const size_t red_s = (size_t)(POOL_THREADS_STRIPED / 32) * (P.ni + 1) * 8;
+      const bool striped_fits = map_bytes + (size_t)STRIPE * hist_bytes + red_s <= SMEM_MAX;
+      if (P.any_adapt && striped_fits && (p.hist_policy == MCI_HIST_SMEM_STRIPED || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_STRIPED))) {
+        mode = HIST_SMEM_STRIPED; threads = POOL_THREADS_STRIPED; nwarp = threads / 32; red = red_s;
+        hs = (size_t)STRIPE * hist_bytes; h->maps_in_smem = 1;
+      }
       if (h->maps_in_smem) {
-        const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], mode, &h->kernel_name);
+        const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, mode, &h->kernel_name);
         if (k) {
-          h->kernel = k; h->is_pool = true; h->threads = POOL_THREADS; h->hist_mode = mode;
-          h->smem = map_bytes + hist_smem(mode, nwarp) + red;
+          h->kernel = k; h->is_pool = true; h->threads = threads; h->hist_mode = mode;
+          h->smem = map_bytes + hs + red;
         }
       }
     }
@@ -289,8 +304,10 @@ void mci_destroy(mci_handle_t *h) {
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_err) cudaFreeHost(h->h_err);
   if (h->ev_iter0) cudaEventDestroy(h->ev_iter0);
-  if (h->ev_fill0) cudaEventDestroy(h->ev_fill0);
-  if (h->ev_fill1) cudaEventDestroy(h->ev_fill1);
+  for (int i = 0; i < mci_handle_t::FILL_RING; ++i) {
+    if (h->ev_fill0[i]) cudaEventDestroy(h->ev_fill0[i]);
+    if (h->ev_fill1[i]) cudaEventDestroy(h->ev_fill1[i]);
+  }
   if (h->ev_iter1) cudaEventDestroy(h->ev_iter1);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -444,8 +461,8 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
 #define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, MCI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); mci_destroy(h); *out = nullptr; return MCI_ERR_CUDA; } } while (0)
   CUT(cudaSetDevice(h->device));
   CUT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CUT(cudaEventCreate(&h->ev_iter0)); CUT(cudaEventCreate(&h->ev_fill0));
-  CUT(cudaEventCreate(&h->ev_fill1)); CUT(cudaEventCreate(&h->ev_iter1));
+  CUT(cudaEventCreate(&h->ev_iter0)); CUT(cudaEventCreate(&h->ev_iter1));
+  for (int i = 0; i < mci_handle_t::FILL_RING; ++i) { CUT(cudaEventCreate(&h->ev_fill0[i])); CUT(cudaEventCreate(&h->ev_fill1[i])); }
   TRY(dev_alloc(h, &h->d_grids, go + 1)); TRY(dev_alloc(h, &h->d_dist, dd + 1)); TRY(dev_alloc(h, &h->d_accum, da + 1));
   TRY(dev_alloc(h, &h->d_reweight, nd)); TRY(dev_alloc(h, &h->d_goal, nd)); TRY(dev_alloc(h, &h->d_alpha, nleaf));
   TRY(dev_alloc(h, &h->d_gmaps, mo + 2));
@@ -561,9 +578,11 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;
     args[0] = &h->dp; args[1] = &CA;
   }
-  CU(h, cudaEventRecord(h->ev_fill0, h->stream));
+  const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);
+  CU(h, cudaEventRecord(h->ev_fill0[slot], h->stream));
   CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
-  CU(h, cudaEventRecord(h->ev_fill1, h->stream));
+  CU(h, cudaEventRecord(h->ev_fill1[slot], h->stream));
+  h->n_iterations++;
   h->launches++;
   const int fin_threads = 256;
   const int total_el = h->Y.len;
@@ -597,7 +616,10 @@ int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out) {
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->fill_ms, h->ev_fill0, h->ev_fill1);
+  {
+    const int slot = (int)((h->n_iterations - 1) % mci_handle_t::FILL_RING);
+    cudaEventElapsedTime(&h->fill_ms, h->ev_fill0[slot], h->ev_fill1[slot]);
+  }
   cudaEventElapsedTime(&h->iter_ms, h->ev_iter0, h->ev_iter1);
   const PackedLayout &Y = h->Y;
   const double *pk = h->h_packed;
@@ -757,6 +779,20 @@ int mci_last_timing(mci_handle_t *h, float *fill_ms, float *iteration_ms) {
   if (!h) return MCI_ERR_INVALID;
   if (fill_ms) *fill_ms = h->fill_ms;
   if (iteration_ms) *iteration_ms = h->iter_ms;
+  return MCI_OK;
+}
+
+int mci_fill_history(mci_handle_t *h, float *ms, int32_t cap, int32_t *n) {
+  if (!h || !ms || !n || cap < 0) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  const uint64_t have = std::min<uint64_t>(h->n_iterations, (uint64_t)mci_handle_t::FILL_RING);
+  const int m = (int)std::min<uint64_t>(have, (uint64_t)cap);
+  for (int k = 0; k < m; ++k) { /* ms[0] = oldest of the m most recent iterations */
+    const int slot = (int)((h->n_iterations - m + k) % mci_handle_t::FILL_RING);
+    CU(h, cudaEventElapsedTime(&ms[k], h->ev_fill0[slot], h->ev_fill1[slot]));
+  }
+  *n = m;
   return MCI_OK;
 }
 

@@ -30,6 +30,11 @@ constexpr int HIST_NONE = 0;         /* no adaptive leaf                        
 constexpr int HIST_SMEM_ATOMIC = 1;  /* one CTA-shared fp64 histogram, shared-memory CAS atomics    */
 constexpr int HIST_GLOBAL_RED = 2;   /* RED.ADD.F64 into replicated global copies (L2)              */
 constexpr int HIST_WARP_PRIVATE = 3; /* one private histogram per warp, conflict-ranked plain RMW   */
+constexpr int HIST_SMEM_STRIPED = 4; /* CTA-shared fp64 histogram in 16 bank-striped copies: lane l updates copy l%16, which
+                                        lives in bank pair l%16, so neither the LDS.64 nor the CAS of a random-bin scatter
+                                        ever has a bank conflict (2 wavefronts per instruction instead of ~10)           */
+constexpr int STRIPE_LOG2 = 4;
+constexpr int STRIPE = 1 << STRIPE_LOG2;
 
 struct DevLeaf {
   int kind, nbins, adapt, lower_i;

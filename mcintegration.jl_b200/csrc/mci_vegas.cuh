@@ -41,35 +41,114 @@ struct FillArgs {
 /* pool kernel: ONE top-level variable that is a single Continuous leaf (the reference's         */
 /* idiomatic `var = Continuous(a, b), dof = [[d1], [d2], ...]`).  Everything about a sample      */
 /* lives in registers.                                                                          */
+/*   MAXD   compile-time bound of the pool slots; EXACT: every integrand uses exactly MAXD slots */
+/*          (no run-time predication on the dof at all)                                         */
+/*   HMODE  HIST_NONE | HIST_SMEM_ATOMIC (one CTA-shared fp64 histogram, red.shared.add.f64)     */
+/*          | HIST_SMEM_STRIPED (the same in 16 bank-striped copies, one 1024-thread CTA per SM)  */
+/*          | HIST_GLOBAL_RED (RED.E.ADD.F64 into replicated L2-resident copies)                 */
 /* ------------------------------------------------------------------------------------------ */
-template <int FID, int MAXD, int HMODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+
+/* hist[bin] += v on the CTA's shared histogram.  ptxas expands red.shared.add.f64 into
+ * LDS.64 / DADD / ATOMS.CAST.SPIN.64 / retry-branch; handing it a ready 32-bit shared address keeps the
+ * expansion at 7 instructions (the generic-pointer form recomputes the shared window base every time). */
+__device__ __forceinline__ void red_shared_f64(uint32_t saddr, double v) {
+  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory");
+}
+
+template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD>
+__device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey &K, const double2 *__restrict__ pair,
+                                            uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
+                                            bool active, double *acc, int &cnt, unsigned long long &bad) {
+  using F = Integrand<FID>;
+  constexpr int NI = F::NI;
+  constexpr bool CAN_PAD = NI > 1 && !EXACT; /* one integrand, or EXACT: dof == maxdof by construction */
+  const int nbins = P.leaf[0].nbins;
+  const double nbins_d = P.leaf[0].nbins_d;
+  const int d = EXACT ? MAXD : P.maxdof[0];
+  PoolX<MAXD> X;
+  int bin[MAXD];
+  double prob[CAN_PAD ? MAXD : 1]; /* only live when P.need_pad */
+  double jac = 1.0;
+#pragma unroll
+  for (int j = 0; j < (MAXD + 1) / 2; ++j) {
+    if (2 * j < d) {
+      uint32_t o0, o1, o2, o3;
+      philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
+      double dx;
+      X.v[2 * j] = map_continuous(pair, nbins, nbins_d, u52(o0, o1), bin[2 * j], dx);
+      double ndx = __dmul_rn(nbins_d, dx);
+      jac *= ndx;
+      if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / ndx;
+      if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
+        X.v[2 * j + 1] = map_continuous(pair, nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dx);
+        ndx = __dmul_rn(nbins_d, dx);
+        jac *= ndx;
+        if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / ndx;
+      }
+    }
+  }
+  double w[NI];
+  F::template eval<MAXD>(X, P, w);
+  double pad[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    pad[i] = 1.0;
+    if (CAN_PAD && P.need_pad && !P.same_dof[i]) {
+      const int di = P.dof[i * P.nv];
+#pragma unroll
+      for (int p = 0; p < MAXD; ++p)
+        if (p >= di && p < d) pad[i] *= prob[p];
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
+  if ((!GUARD || active) && !finite) bad++;
+  const bool meas = (!GUARD || active) && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
+  if (meas) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] += w[i] * pad[i] * jac;
+    cnt++;
+  }
+  if (HMODE != HIST_NONE && (!GUARD || active)) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const double a = fabs(w[i]) * jac;
+      const double w2 = a * a;
+      const int di = EXACT ? MAXD : P.dof[i * P.nv];
+#pragma unroll
+      for (int p = 0; p < MAXD; ++p)
+        if (p < di) {
+          if (HMODE == HIST_SMEM_ATOMIC) red_shared_f64(hist_saddr + 8u * (uint32_t)bin[p], w2);
+          else if (HMODE == HIST_SMEM_STRIPED) red_shared_f64(hist_saddr + (8u * STRIPE) * (uint32_t)bin[p], w2); /* base holds the lane's stripe */
+          else atomicAdd(ghist + bin[p], w2); /* RED.E.ADD.F64 */
+        }
+    }
+  }
+}
+
+template <int FID, int MAXD, int HMODE, int THREADS, bool EXACT>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
-  constexpr bool CAN_PAD = NI > 1; /* one integrand: dof == maxdof by construction */
+  static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED,
+                "pool kernel histogram modes");
+  constexpr int NCOPY = HMODE == HIST_SMEM_STRIPED ? STRIPE : (HMODE == HIST_SMEM_ATOMIC ? 1 : 0);
   extern __shared__ __align__(16) double smem[];
   double *smaps = smem;                                 /* P.map_doubles                          */
-  double *shist = smem + P.map_doubles;                 /* per-warp or per-CTA histogram          */
-  double *sred = shist + (HMODE == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (HMODE == HIST_SMEM_ATOMIC ? P.hist_len : 0));
+  double *shist = smem + P.map_doubles;                 /* the CTA's histogram: [bin][copy]       */
+  double *sred = shist + NCOPY * P.hist_len;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nbins = P.leaf[0].nbins;
-  const double nbins_d = P.leaf[0].nbins_d;
-  const int d = P.maxdof[0];
   const bool adapt = P.leaf[0].adapt != 0;
 
   stage_maps(P, smaps, A.gmaps);
-  if (HMODE == HIST_WARP_PRIVATE) {
-    for (int i = tid; i < NWARP * P.hist_len; i += THREADS) shist[i] = 0.0;
-  } else if (HMODE == HIST_SMEM_ATOMIC) {
-    for (int i = tid; i < P.hist_len; i += THREADS) shist[i] = 0.0;
-  }
+  for (int i = tid; i < NCOPY * P.hist_len; i += THREADS) shist[i] = 0.0;
   __syncthreads();
   const double2 *pair = reinterpret_cast<const double2 *>(smaps);
-  double *myhist = HMODE == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
-                   : HMODE == HIST_SMEM_ATOMIC ? shist
-                                               : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
+  const uint32_t hist_saddr = (uint32_t)__cvta_generic_to_shared(shist) + (HMODE == HIST_SMEM_STRIPED ? 8u * (lane & (STRIPE - 1)) : 0u);
+  double *ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
@@ -86,66 +165,22 @@ __global__ void __launch_bounds__(THREADS) vegas_pool_kernel(const __grid_consta
 #pragma unroll
     for (int i = 0; i < NI; ++i) acc[i] = 0.0;
     int cnt = 0;
-    /* whole warps iterate together (hist_add is a warp-collective); lanes past the end are inactive */
-    for (int k = 0; k < A.spt; ++k) {
-      const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
-      const bool active = s < A.neval_per_block;
-      if (!__any_sync(0xffffffffu, active)) break;
-      PoolX<MAXD> X;
-      int bin[MAXD];
-      double prob[MAXD]; /* only live when P.need_pad */
-      double jac = 1.0;
-#pragma unroll
-      for (int j = 0; j < (MAXD + 1) / 2; ++j) {
-        if (2 * j < d) {
-          uint32_t o0, o1, o2, o3;
-          philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
-          double dx;
-          X.v[2 * j] = map_continuous(pair, nbins, nbins_d, u52(o0, o1), bin[2 * j], dx);
-          double ndx = __dmul_rn(nbins_d, dx);
-          jac *= ndx;
-          if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / ndx;
-          if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
-            X.v[2 * j + 1] = map_continuous(pair, nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dx);
-            ndx = __dmul_rn(nbins_d, dx);
-            jac *= ndx;
-            if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / ndx;
-          }
-        }
+    if (s0 + tile_samples <= A.neval_per_block) { /* full tile: no per-lane guards anywhere */
+      if (adapt) {
+        for (int k = 0; k < A.spt; ++k)
+          pool_sample<FID, MAXD, HMODE, EXACT, false>(P, K, pair, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
+                                                       true, acc, cnt, bad);
+      } else {
+        for (int k = 0; k < A.spt; ++k)
+          pool_sample<FID, MAXD, HIST_NONE, EXACT, false>(P, K, pair, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
+                                                           block, true, acc, cnt, bad);
       }
-      double w[NI];
-      F::template eval<MAXD>(X, P, w);
-      double pad[NI];
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        pad[i] = 1.0;
-        if (CAN_PAD && P.need_pad && !P.same_dof[i]) {
-          const int di = P.dof[i * P.nv];
-#pragma unroll
-          for (int p = 0; p < MAXD; ++p)
-            if (p >= di && p < d) pad[i] *= prob[p];
-        }
-      }
-      bool finite = true;
-#pragma unroll
-      for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
-      if (active && !finite) bad++;
-      const bool meas = active && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
-      if (meas) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i) acc[i] += w[i] * pad[i] * jac;
-        cnt++;
-      }
-      if (HMODE != HIST_NONE && adapt) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const double a = fabs(w[i]) * jac;
-          const double w2 = a * a;
-          const int di = P.dof[i * P.nv];
-#pragma unroll
-          for (int p = 0; p < MAXD; ++p)
-            if (p < di) hist_add<HMODE>(myhist, bin[p], w2, active);
-        }
+    } else { /* ragged last tile of a block */
+      for (int k = 0; k < A.spt; ++k) {
+        const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
+        const bool active = s < A.neval_per_block;
+        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true>(P, K, pair, hist_saddr, ghist, s, block, active, acc, cnt, bad);
+        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true>(P, K, pair, hist_saddr, ghist, s, block, active, acc, cnt, bad);
       }
     }
     /* tile flush: warp shuffle -> shared -> one thread sums the warps in order */
@@ -172,17 +207,14 @@ __global__ void __launch_bounds__(THREADS) vegas_pool_kernel(const __grid_consta
     }
   }
   if (bad) atomicAdd(A.flags, bad);
-  /* histogram flush: fixed warp order inside the CTA -> one global partial per CTA */
-  if (HMODE == HIST_WARP_PRIVATE || HMODE == HIST_SMEM_ATOMIC) {
+  /* histogram flush: one global partial per CTA (stripes summed in a fixed order) */
+  if (NCOPY > 0) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
     for (int i = tid; i < P.hist_len; i += THREADS) {
       double t = 0.0;
-      if (HMODE == HIST_WARP_PRIVATE) {
-        for (int wv = 0; wv < NWARP; ++wv) t += shist[wv * P.hist_len + i];
-      } else {
-        t = shist[i];
-      }
+#pragma unroll
+      for (int c = 0; c < NCOPY; ++c) t += shist[i * NCOPY + c];
       out[i] = t;
     }
   }

@@ -2,14 +2,14 @@
 #include "mci_kernels.h"
 #include "mci_vegas.cuh"
 namespace mci {
-const void *lookup_vegas_pool_a(int, int, int, const char **);
-const void *lookup_vegas_pool_b(int, int, int, const char **);
-const void *lookup_vegas_pool_c(int, int, int, const char **);
+const void *lookup_vegas_pool_a(int, int, bool, int, const char **);
+const void *lookup_vegas_pool_b(int, int, bool, int, const char **);
+const void *lookup_vegas_pool_c(int, int, bool, int, const char **);
 
-const void *lookup_vegas_pool(int fid, int d, int hist_mode, const char **name) {
-  const void *f = lookup_vegas_pool_a(fid, d, hist_mode, name);
-  if (!f) f = lookup_vegas_pool_b(fid, d, hist_mode, name);
-  if (!f) f = lookup_vegas_pool_c(fid, d, hist_mode, name);
+const void *lookup_vegas_pool(int fid, int d, bool exact, int hist_mode, const char **name) {
+  const void *f = lookup_vegas_pool_a(fid, d, exact, hist_mode, name);
+  if (!f) f = lookup_vegas_pool_b(fid, d, exact, hist_mode, name);
+  if (!f) f = lookup_vegas_pool_c(fid, d, exact, hist_mode, name);
   return f;
 }
 

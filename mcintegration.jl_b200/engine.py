@@ -193,6 +193,13 @@ class CudaEngine(HandleEngine):
         self._check(self.lib.mci_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def fill_history(self, n=64):
+        """CUDA-event durations (ms) of the fill kernel of the last n launched iterations, oldest first."""
+        buf = (C.c_float * n)()
+        got = C.c_int32()
+        self._check(self.lib.mci_fill_history(self.h, buf, n, C.byref(got)))
+        return [buf[i] for i in range(got.value)]
+
     def stats_sync_host(self):
         self._check(self.lib.mci_stats_sync_host(self.h))
 

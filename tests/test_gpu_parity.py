@@ -79,12 +79,13 @@ def test_L1_vegas_iteration(name):
         gpu.close(); cpu.close()
 
 
-@pytest.mark.parametrize("policy", [_abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED, _abi.HIST_WARP_PRIVATE])
+@pytest.mark.parametrize("policy", [_abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED, _abi.HIST_WARP_PRIVATE, _abi.HIST_SMEM_STRIPED])
 @pytest.mark.parametrize("name", ["gauss10", "sphere2", "bubble", "genz6_comp"])
 def test_L1_hist_policies(name, policy):
     gpu, cpu, _ = _pair(name, "vegas", neval_per_block=3000, hist_policy=policy)
     try:
-        # a policy that does not fit in shared memory (bubble: 8 warps x 32 KB) falls back to the shared CTA copy
+        # a policy that does not fit in shared memory (bubble: 8 warps x 32 KB) or that the kernel of this layout does not
+        # implement (striped copies: pool kernel only) falls back to the shared CTA copy
         assert gpu.launch_info()["hist_mode"] in (policy, _abi.HIST_SMEM_ATOMIC)
         cpu.run_iteration(0); cpu.refine(); _sync_maps(cpu, gpu)
         _assert_stats(gpu.run_iteration(1), cpu.run_iteration(1))
@@ -202,7 +203,10 @@ def test_L3_chain_known_answers(name, solver, ceiling):
     if name == "hypersphere3" and solver == "mcmc":
         pytest.skip("not in the reference's mcmc testset")
     c = case(name)
-    kw = dict(solver=solver, neval=4e5, niter=10, seed=4321, walkers=256)
+    # chains start from a draw of the VEGAS map, not of the target density: a chain must be much longer than
+    # its equilibration time or the start bias shows (lattice_pool at 97 steps/chain was 8 sigma off, on the
+    # oracle as well); 64 chains x 976 steps per block
+    kw = dict(solver=solver, neval=1e6, niter=10, seed=4321, walkers=64)
     g = mci.integrate(c["f"], **kw, **c["cfg"]())
     o = oracle_integrate(c["f"], **kw, **c["cfg"]())
     for k in range(len(g.mean)):

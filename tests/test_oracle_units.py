@@ -1,0 +1,203 @@
+"""CPU tests: the oracle (oracle/mci_oracle.c) against
+  - every deterministic fixture the reference's own tests hold for this path
+    (test/utility.jl, test/statistics.jl, test/mpi_test.jl), and
+  - the golden vectors of tests/golden/golden.json (independent pure-Python restatement,
+    tests/golden/make_golden.py; Philox = published Random123 known-answer vectors).
+Bit-exact for integers / indices; doubles are compared exactly where both sides evaluate the same
+expression with one rounding per operation, and to 4 ulp where libm (log, pow) is involved."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import dptr, iptr, oracle
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+ULP4 = 4 * 2.0 ** -52
+
+
+def arr(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def test_philox_known_answers():
+    lib = oracle()
+    for k in GOLD["philox_kat"]:
+        ctr = (C.c_uint32 * 4)(*k["ctr"])
+        key = (C.c_uint32 * 2)(*k["key"])
+        out = (C.c_uint32 * 4)()
+        lib.orc_philox4x32_10(ctr, key, out)
+        assert list(out) == k["out"]
+
+
+def test_uniform_stream_layout():
+    lib = oracle()
+    for k in GOLD["uniforms"]:
+        out = np.zeros(len(k["u"]))
+        lib.orc_uniforms(k["seed"], k["iter"], k["block"], k["idx"], len(out), dptr(out))
+        assert out.tolist() == k["u"]
+        assert np.all((out >= 0) & (out < 1))
+
+
+def test_locate_reference_fixture():
+    """test/utility.jl:1-10"""
+    lib = oracle()
+    g = GOLD["locate"]
+    acc = arr(g["acc"])
+    for p, want in zip(g["p"], g["idx"]):
+        got = lib.orc_locate(dptr(acc), len(acc), p)
+        assert got == (want if want is not None else -1), (p, got, want)
+    eps = 2.0 ** -52
+    grid = arr([0.0, 0.1, 0.3, 0.5])
+    assert lib.orc_locate(dptr(grid), 4, eps) == 1
+    assert lib.orc_locate(dptr(grid), 4, 0.5 - eps) == 3
+    assert lib.orc_locate(dptr(grid), 4, grid[0]) == 1
+    assert [lib.orc_locate(dptr(grid), 4, p) for p in (0.05, 0.2, 0.31)] == [1, 2, 3]
+
+
+def test_maxdof_reference_fixture():
+    """test/utility.jl:12-15"""
+    lib = oracle()
+    dof = np.array([[1, 2, 3, 5], [3, 1, 2, 7], [2, 4, 1, 2]], dtype=np.int32)
+    out = np.zeros(4, dtype=np.int32)
+    lib.orc_maxdof(iptr(dof), 3, 4, iptr(out))
+    assert out.tolist() == [3, 4, 3, 7]
+
+
+@pytest.mark.parametrize("do_shift", [0, 1])
+def test_probability_identity(do_shift):
+    """test/utility.jl:30-56: total_probability == probability(i) * padding_probability(i)"""
+    lib = oracle()
+    rng = np.random.default_rng(7)
+    d6 = rng.random(6)
+    d6 /= d6.sum()
+    total = np.zeros(1)
+    prob = np.zeros(2)
+    pad = np.zeros(2)
+    for seed in range(5):
+        lib.orc_probability_identity(dptr(arr([0.0, 0.1, 0.4, 1.0])), dptr(arr([0.0, 0.2, 0.6, 1.0])), dptr(arr(d6)), seed,
+                                     do_shift, dptr(total), dptr(prob), dptr(pad))
+        assert total[0] > 0
+        for i in range(2):
+            assert math.isclose(total[0], prob[i] * pad[i], rel_tol=1e-13)
+
+
+def test_map_continuous_golden():
+    lib = oracle()
+    for k in GOLD["map_continuous"]:
+        g = arr(k["grid"])
+        iy = C.c_int32()
+        x, p = C.c_double(), C.c_double()
+        lib.orc_map_continuous(dptr(g), len(g), k["y"], C.byref(iy), C.byref(x), C.byref(p))
+        assert iy.value == k["iy"]
+        assert x.value == k["x"]
+        assert p.value == k["prob"]
+
+
+def test_smooth_rescale_train_continuous_golden():
+    lib = oracle()
+    for k in GOLD["train_continuous"]:
+        hist = arr(k["hist"])
+        sm = np.zeros_like(hist)
+        lib.orc_smooth(dptr(hist), len(hist), 6.0, dptr(sm))
+        assert sm.tolist() == k["smooth"]
+        rs = sm.copy()
+        assert lib.orc_rescale(dptr(rs), len(rs), k["alpha"]) == 0
+        np.testing.assert_allclose(rs, k["rescaled"], rtol=ULP4, atol=0)
+        g = arr(k["grid"])
+        new = np.zeros_like(g)
+        assert lib.orc_train_continuous(dptr(g), len(g), dptr(hist), k["alpha"], dptr(new)) == 0
+        np.testing.assert_allclose(new, k["newgrid"], rtol=1e-13, atol=1e-15)
+        assert new[0] == g[0] and new[-1] == g[-1]
+        assert np.all(np.diff(new) > 0)
+
+
+def test_train_discrete_golden():
+    lib = oracle()
+    for k in GOLD["train_discrete"]:
+        hist = arr(k["hist"])
+        n = len(hist)
+        d, a = np.zeros(n), np.zeros(n + 1)
+        assert lib.orc_train_discrete(dptr(hist), n, k["alpha"], dptr(d), dptr(a)) == 0
+        np.testing.assert_allclose(d, k["dist"], rtol=ULP4)
+        np.testing.assert_allclose(a, k["accum"], rtol=ULP4, atol=0)
+        assert a[0] == 0.0 and math.isclose(a[-1], 1.0, rel_tol=1e-15)
+
+
+def test_train_asserts_like_the_reference():
+    """variable.jl:212-213, common.jl:71: non-positive / non-finite histograms are errors"""
+    lib = oracle()
+    g = arr([0.0, 0.25, 0.5, 1.0])
+    new = np.zeros(4)
+    assert lib.orc_train_continuous(dptr(g), 4, dptr(arr([1.0, 0.0, 2.0])), 2.0, dptr(new)) != 0
+    assert lib.orc_train_continuous(dptr(g), 4, dptr(arr([1.0, float("nan"), 2.0])), 2.0, dptr(new)) != 0
+    assert lib.orc_train_continuous(dptr(g), 4, dptr(arr([1.0, float("inf"), 2.0])), 2.0, dptr(new)) != 0
+
+
+def test_mean_std_reference_fixture():
+    """test/statistics.jl:22-46: _mean_std equals mean and std/sqrt(block) of the block means"""
+    lib = oracle()
+    for k in GOLD["mean_std"]:
+        m, s = np.zeros(1), np.zeros(1)
+        lib.orc_mean_std(dptr(arr([k["sum"]])), dptr(arr([k["sqsum"]])), 1, k["block"], dptr(m), dptr(s))
+        assert m[0] == k["mean"] and math.isclose(s[0], k["std"], rel_tol=1e-15)
+        assert math.isclose(m[0], k["sample_mean"], rel_tol=1e-14)
+        assert math.isclose(s[0], k["sample_std_over_sqrtB"], rel_tol=1e-9)
+    rng = np.random.default_rng(3)
+    for block in (2, 7, 64):  # vector observable
+        x = rng.normal(size=(block, 5))
+        m, s = np.zeros(5), np.zeros(5)
+        lib.orc_mean_std(dptr(arr(x.sum(0))), dptr(arr((x * x).sum(0))), 5, block, dptr(m), dptr(s))
+        np.testing.assert_allclose(m, x.mean(0), rtol=1e-13)
+        np.testing.assert_allclose(s, x.std(0, ddof=1) / math.sqrt(block), rtol=1e-9)
+    m, s = np.zeros(1), np.ones(1)  # block == 1 -> std 0 (main.jl:311-315)
+    lib.orc_mean_std(dptr(arr([2.0])), dptr(arr([4.0])), 1, 1, dptr(m), dptr(s))
+    assert m[0] == 2.0 and s[0] == 0.0
+
+
+def test_reweight_fixed_point_reference_fixture():
+    """test/mpi_test.jl:148-168: visited=[1,2,3,4], goal=[1,2,3,4] -> reweight converges to 1/4 each"""
+    lib = oracle()
+    k = GOLD["reweight"]["mpi_test"]
+    rw = arr(k["start"])
+    for want in k["rounds"]:
+        lib.orc_do_reweight(dptr(rw), dptr(arr(k["visited"])), 4, k["gamma"], dptr(arr(k["goal"])))
+        np.testing.assert_allclose(rw, want, rtol=ULP4)
+    np.testing.assert_allclose(rw, [0.25] * 4, rtol=1e-3)
+    for g in GOLD["reweight"]["generic"]:
+        rw = arr(g["rw"])
+        goal = None if g["goal"] is None else arr(g["goal"])
+        lib.orc_do_reweight(dptr(rw), dptr(arr(g["visited"])), len(rw), g["gamma"], dptr(goal) if goal is not None else None)
+        np.testing.assert_allclose(rw, g["out"], rtol=ULP4)
+        assert math.isclose(rw.sum(), 1.0, rel_tol=1e-14)
+
+
+def test_average_golden():
+    lib = oracle()
+    for k in GOLD["average"]:
+        a, e, c = C.c_double(), C.c_double(), C.c_double()
+        lib.orc_average(dptr(arr(k["means"])), dptr(arr(k["stds"])), len(k["means"]), k["init"], C.byref(a), C.byref(e), C.byref(c))
+        np.testing.assert_allclose([a.value, e.value, c.value], k["out"], rtol=1e-12, atol=1e-300)
+
+
+def test_host_statistics_match_oracle():
+    """the product's host mirror (mcintegration_jl_b200.statistics) against the oracle restatement"""
+    from mcintegration_jl_b200.statistics import average, mean_std
+    lib = oracle()
+    rng = np.random.default_rng(11)
+    x = rng.normal(2.0, 0.1, size=(16, 3))
+    m, s = mean_std(x.sum(0), (x * x).sum(0), 16)
+    mo, so = np.zeros(3), np.zeros(3)
+    lib.orc_mean_std(dptr(arr(x.sum(0))), dptr(arr((x * x).sum(0))), 3, 16, dptr(mo), dptr(so))
+    np.testing.assert_allclose(m, mo, rtol=1e-15)
+    np.testing.assert_allclose(s, so, rtol=1e-12)
+    means = list(rng.normal(1.0, 0.01, 10))
+    stds = list(np.abs(rng.normal(0.01, 0.001, 10)))
+    for init in (1, 2):
+        a, e, c = C.c_double(), C.c_double(), C.c_double()
+        lib.orc_average(dptr(arr(means)), dptr(arr(stds)), 10, init, C.byref(a), C.byref(e), C.byref(c))
+        pa, pe, pc = average(means, stds, init=init)
+        np.testing.assert_allclose([pa, pe, pc], [a.value, e.value, c.value], rtol=1e-12)
