@@ -1,0 +1,151 @@
+# MCIntegrationB200.jl — the reference-side binding of libmcib200.so (include/mcib200.h).
+#
+# This is the thin `ccall` shim the north star asks for: host code stays Julia (Configuration, train!-free driver
+# loop, Result/average/report come from MCIntegration.jl itself); one iteration's blocks run on the B200 through
+# the C ABI.  It replaces the body of `integrate`'s iteration loop (src/main.jl:142-207): `_block!` × block,
+# MPIreduce*, doReweightMPI!, train!.
+#
+# STATUS: written against the header, NOT executed — no Julia runtime exists in the build image (SURVEY §0).  The
+# Python mirror (mcintegration.jl_b200/) drives the very same exports and is what the tests run.
+module MCIntegrationB200
+
+using MCIntegration
+using MCIntegration: Configuration, Continuous, Discrete, CompositeVar, Result, Dist
+
+const LIB = get(ENV, "LIBMCIB200", "libmcib200")
+
+# ---- mirror of the POD structs (include/mcib200.h) -------------------------------------------------------------
+struct MciLeaf
+    kind::Int32; nbins::Int32; adapt::Int32; lower_i::Int32
+    lower::Float64; upper::Float64; alpha::Float64
+end
+
+struct MciProblem
+    solver::Int32; integrand_id::Int32; measure_kind::Int32; n_integrand::Int32; n_topvar::Int32; n_leaf::Int32
+    topvar_nleaf::Ptr{Int32}; topvar_offset::Ptr{Int32}; leaf::Ptr{MciLeaf}; dof::Ptr{Int32}; obs_len::Ptr{Int32}
+    neighbor_ptr::Ptr{Int32}; neighbor_idx::Ptr{Int32}; userdata::Ptr{Float64}
+    n_userdata::Int32; n_block::Int32; neval_per_block::UInt64; seed::UInt64
+    measurefreq::Int32; walkers_per_block::Int32; thermal_ratio::Float64; device::Int32; hist_policy::Int32
+end
+
+struct MciIterationOut
+    block_obs::Ptr{Float64}; block_norm::Ptr{Float64}; hist::Ptr{Float64}; visited::Ptr{Float64}
+    propose::Ptr{Float64}; accept::Ptr{Float64}; neval::Ptr{UInt64}
+end
+
+const SOLVER = Dict(:vegas => Int32(0), :vegasmc => Int32(1), :mcmc => Int32(2))
+
+struct MciError <: Exception
+    code::Int32; msg::String
+end
+check(h, rc) = rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_error, LIB), Cstring, (Ptr{Cvoid},), h))))
+
+leaves(v::Union{Continuous,Discrete}) = [v]
+leaves(v::CompositeVar) = collect(v.vars)
+leafdesc(v::Continuous) = MciLeaf(0, length(v.grid) - 1, v.adapt, 0, v.lower, v.lower + v.range, v.alpha)
+leafdesc(v::Discrete) = MciLeaf(1, v.upper - v.lower + 1, v.adapt, v.lower, 0.0, 0.0, v.alpha)
+
+"""
+    integrate_b200(integrand_id::Integer; userdata=Float64[], measure_kind=0, walkers=4096, device=0, kwargs...)
+
+Same keyword surface as `MCIntegration.integrate` (src/main.jl:71-90): `solver, config, neval, niter, block, gamma,
+adapt, reweight_goal, ignore, measurefreq, thermal_ratio` plus the `Configuration` kwargs (`var, dof, obs, reweight,
+seed, neighbor`).  The integrand is a built-in device function (`enum mci_integrand_id`) instead of a closure.
+"""
+function integrate_b200(integrand_id::Integer; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
+    gamma=1.0, adapt=true, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
+    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, kwargs...)
+    haskey(SOLVER, solver) || error("Solver $solver is not supported!")            # main.jl:263
+    config = isnothing(config) ? Configuration(; kwargs...) : config                # main.jl:95-97
+    nevalperblock, block = MCIntegration._standardize_block(neval, block)          # main.jl:121
+    W = solver == :vegas ? 1 : min(walkers, max(1, nevalperblock ÷ 512))   # chains of >= 512 steps (DESIGN.md 5.3)
+    nevalperblock = (nevalperblock ÷ W) * W
+
+    lv = vcat((leaves(v) for v in config.var)...)
+    topn = Int32[length(leaves(v)) for v in config.var]
+    topoff = Int32[v.offset for v in config.var]
+    desc = MciLeaf[leafdesc(l) for l in lv]
+    N, Nv = config.N, length(config.var)
+    dof = Int32[config.dof[i][v] for i in 1:N for v in 1:Nv]                        # row-major [Ni][Nv]
+    obslen = Int32[length(o) for o in config.observable]
+    nbptr = Int32[0]; nbidx = Int32[]
+    for nb in config.neighbor
+        append!(nbidx, Int32.(nb .- 1)); push!(nbptr, length(nbidx))
+    end
+    ud = Float64.(userdata)
+    seed = UInt64(rand(config.rng, 1:10^6))                                          # main.jl:136
+
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve topn topoff desc dof obslen nbptr nbidx ud begin
+        prob = MciProblem(SOLVER[solver], integrand_id, measure_kind, N, Nv, length(lv), pointer(topn), pointer(topoff),
+            pointer(desc), pointer(dof), pointer(obslen), pointer(nbptr), pointer(nbidx), pointer(ud), length(ud), block,
+            nevalperblock, seed, measurefreq, W, thermal_ratio, device, hist_policy)
+        rc = ccall((:mci_create, LIB), Cint, (Ref{MciProblem}, Ref{Ptr{Cvoid}}), prob, h)
+        rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+    end
+    handle = h[]
+    try
+        # warm restart: push the grids of `config` (main.jl:95-97, docs/src/index.md:129-150)
+        grids = vcat((l.grid for l in lv if l isa Continuous)..., Float64[])
+        dist = vcat((l.distribution for l in lv if l isa Discrete)..., Float64[])
+        accum = vcat((l.accumulation for l in lv if l isa Discrete)..., Float64[])
+        check(handle, ccall((:mci_set_maps, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            handle, grids, dist, accum, config.reweight))
+
+        Nd = N + 1
+        obstot = sum(obslen)
+        histlen = sum(d.nbins for d in desc)
+        pa = max(Nd, Nv)
+        block_obs = zeros(obstot, block)          # C row-major [block][obstot] == Julia column-major (obstot, block)
+        block_norm = zeros(block); hist = zeros(histlen); visited = zeros(Nd)
+        propose = zeros(pa, Nd, 3); accept = zeros(pa, Nd, 3)  # C [3][Nd][pa] == Julia (pa, Nd, 3): permute for config.propose
+        nev = Ref{UInt64}(0)
+        results = []
+        for iter in 1:niter                                                        # main.jl:142
+            GC.@preserve block_obs block_norm hist visited propose accept begin
+                out = MciIterationOut(pointer(block_obs), pointer(block_norm), pointer(hist), pointer(visited),
+                    pointer(propose), pointer(accept), Base.unsafe_convert(Ptr{UInt64}, nev))
+                check(handle, ccall((:mci_run_iteration, LIB), Cint, (Ptr{Cvoid}, UInt64, Ref{MciIterationOut}), handle, iter - 1, out))
+            end
+            config.neval = nev[]; config.visited .= visited
+            config.propose .= permutedims(propose, (3, 2, 1)); config.accept .= permutedims(accept, (3, 2, 1))
+            config.normalization = sum(block_norm)
+            if solver != :vegas                                                    # main.jl:183
+                goal = isnothing(reweight_goal) ? C_NULL : pointer(Float64.(reweight_goal))
+                check(handle, ccall((:mci_reweight, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), handle, gamma, goal))
+            end
+            adapt && check(handle, ccall((:mci_refine, LIB), Cint, (Ptr{Cvoid},), handle))   # main.jl:193-198
+            # per-block means -> _mean_std (main.jl:275-287, 296-320)
+            m = block_obs ./ reshape(block_norm, 1, :)
+            obsSum = vec(sum(m, dims=2)); obsSq = vec(sum(m .^ 2, dims=2))
+            mean, std = MCIntegration._mean_std(obsSum, obsSq, block)
+            push!(results, (mean, std, config))
+        end
+        # pull the trained maps back into `config` so that `config=result.config` keeps working
+        check(handle, ccall((:mci_get_maps, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            handle, grids, dist, accum, config.reweight))
+        go = 0; dd = 0; da = 0
+        for l in lv
+            if l isa Continuous
+                n = length(l.grid); l.grid .= grids[go+1:go+n]; go += n
+            else
+                n = length(l.distribution); l.distribution .= dist[dd+1:dd+n]; l.accumulation .= accum[da+1:da+n+1]
+                dd += n; da += n + 1
+            end
+        end
+        return Result(results, ignore)                                             # statistics.jl:24-55
+    finally
+        ccall((:mci_destroy, LIB), Cvoid, (Ptr{Cvoid},), handle)
+    end
+end
+
+"Attach an NCCL communicator: rank 0 creates the id, MPI carries the 128 bytes (replaces src/utility/parallel.jl)."
+function comm_init!(handle, comm)
+    MPI = Base.require(Base.PkgId(Base.UUID("da04e1cc-30fd-572f-bb4f-1f8673147195"), "MPI"))
+    id = zeros(UInt8, 128)
+    MPI.Comm_rank(comm) == 0 && ccall((:mci_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
+    MPI.Bcast!(id, 0, comm)
+    check(handle, ccall((:mci_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), handle, id, MPI.Comm_rank(comm), MPI.Comm_size(comm)))
+end
+
+end # module

@@ -14,8 +14,11 @@ _SOLVERS = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC, "mcmc": 
 _MEASURES = {None: _abi.MEASURE_DEFAULT, "default": _abi.MEASURE_DEFAULT,
              "bin_by_discrete": _abi.MEASURE_BIN_BY_DISCRETE}
 
-# concurrent chains per block for the chain solvers when the caller does not say (SURVEY §7 hard part 3)
+# concurrent chains per block for the chain solvers when the caller does not say (SURVEY §7 hard part 3), and the
+# shortest chain the default will cut a block into: a chain starts from a draw of the VEGAS map, not of the target
+# density, so chains much shorter than the equilibration time bias the estimate
 DEFAULT_WALKERS = 4096
+MIN_CHAIN_STEPS = 512
 
 
 def _standardize_block(neval, nblock, nworker=1):
@@ -101,7 +104,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
     if solver == "vegas":
         W = 1
     else:
-        W = int(walkers) if walkers else min(DEFAULT_WALKERS, max(1, nevalperblock // 64))
+        W = int(walkers) if walkers else min(DEFAULT_WALKERS, max(1, nevalperblock // MIN_CHAIN_STEPS))
         nevalperblock = (nevalperblock // W) * W
     spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
