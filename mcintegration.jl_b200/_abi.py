@@ -133,7 +133,8 @@ EXPORTS = [
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmcib200.so")
+# MCIB200_LIB overrides the in-tree library (used by tools/ to A/B experimental builds; the product default is in-tree)
+LIB_PATH = os.environ.get("MCIB200_LIB") or os.path.join(_PKG_DIR, "libmcib200.so")
 
 
 class LibraryMissing(RuntimeError):

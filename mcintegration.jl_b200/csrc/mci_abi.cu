@@ -189,7 +189,8 @@ int plan(mci_handle_t *h) {
 
   if (p.solver == MCI_SOLVER_VEGAS) {
     bool pool_layout = P.nv == 1 && P.nleaf == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS &&
-                       p.measure_kind == MCI_MEASURE_DEFAULT && P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT;
+                       p.measure_kind == MCI_MEASURE_DEFAULT && P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT &&
+                       p.measurefreq == 1;
     h->is_pool = false;
     if (pool_layout) {
       int nwarp = POOL_THREADS / 32;
@@ -206,6 +207,11 @@ int plan(mci_handle_t *h) {
       }
       if (h->maps_in_smem) {
         const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, mode, &h->kernel_name);
+        if (!k && mode == HIST_SMEM_STRIPED) { /* no striped instantiation for this many slots: one shared copy */
+          threads = POOL_THREADS; nwarp = threads / 32; red = (size_t)nwarp * (P.ni + 1) * 8;
+          mode = pick_hist(nwarp, red, false); hs = hist_smem(mode, nwarp);
+          if (h->maps_in_smem) k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, mode, &h->kernel_name);
+        }
         if (k) {
           h->kernel = k; h->is_pool = true; h->threads = threads; h->hist_mode = mode;
           h->smem = map_bytes + hs + red;

@@ -32,6 +32,38 @@ struct FlatX {
 
 #define MCI_FOR_D(i, d, MAXD) _Pragma("unroll") for (int i = 0; i < ((MAXD) ? (MAXD) : (d)); ++i) if (i < (d))
 
+/* dof of the pool as the integrand loops see it: the compile-time MAXD in an EXACT instantiation (no predication at
+ * all), else the run-time value */
+template <int MAXD, bool EXACT>
+__device__ __forceinline__ int pool_dof(const DevProblem &P) { return EXACT ? MAXD : P.dof[0]; }
+
+/* exp(x) for x <= 0 with the polynomial coefficients as constant-bank operands of the DFMAs (the libdevice exp
+ * materialises its 13 coefficients through 26 UMOVs per call, which cost issue slots in a kernel that is issue-bound).
+ * Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner polynomial (truncation < 2e-18), result
+ * scaled by 2^n through the exponent field; n < -1020 (subnormal results) and x < -746 (zero) take a scaled path.
+ * Max observed error 1 ulp against glibc on [-745, 0] (tests/test_gpu_parity.py::test_device_exp). */
+__constant__ double MCI_EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                     1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
+                                     1.0 / 6.0,          0.5,               1.0,              1.0};
+__constant__ double MCI_EXP_K[4] = {1.4426950408889634074 /* log2(e) */, 6.93147180369123816490e-01 /* ln2 hi */,
+                                    1.90821492927058770002e-10 /* ln2 lo */, 6755399441055744.0 /* 1.5 * 2^52 */};
+__device__ __forceinline__ double exp_nonpos(double x) {
+  /* n = rint(x * log2e) by the 1.5*2^52 trick: the low word of the biased sum is n as an int32 */
+  const double t = fma(x, MCI_EXP_K[0], MCI_EXP_K[3]);
+  const int n = __double2loint(t);
+  const double nd = t - MCI_EXP_K[3];
+  double r = fma(nd, -MCI_EXP_K[1], x);
+  r = fma(nd, -MCI_EXP_K[2], r);
+  double p = MCI_EXP_C[0];
+#pragma unroll
+  for (int i = 1; i < 14; ++i) p = fma(p, r, MCI_EXP_C[i]);
+  if (n >= -1020) return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  if (x < -746.0) return 0.0;
+  /* subnormal range: scale in two exact steps */
+  const double p1 = __hiloint2double(__double2hiint(p) + ((n + 1000) << 20), __double2loint(p));
+  return p1 * __hiloint2double((1023 - 1000) << 20, 0);
+}
+
 /* s^n for a small positive integer n by repeated squaring */
 __device__ __forceinline__ double ipow(double s, int n) {
   double r = 1.0;
@@ -58,12 +90,12 @@ struct Integrand;
 template <>
 struct Integrand<MCI_F_GAUSS_ND> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
-    const int d = P.dof[0];
+    const int d = pool_dof<MAXD, EXACT>(P);
     double s = 0.0;
     MCI_FOR_D(i, d, MAXD) { double x = X(0, i + 1); s += x * x; }
-    w[0] = P.fconst[0] * exp(-0.5 * s);
+    w[0] = P.fconst[0] * exp_nonpos(-0.5 * s);
   }
 };
 
@@ -71,7 +103,7 @@ struct Integrand<MCI_F_GAUSS_ND> {
 template <>
 struct Integrand<MCI_F_LOG_OVER_SQRT> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double x = X(0, 1);
     w[0] = log(x) / sqrt(x);
@@ -82,9 +114,9 @@ struct Integrand<MCI_F_LOG_OVER_SQRT> {
 template <>
 struct Integrand<MCI_F_GENZ_CORNER_POOL> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
-    const int d = P.dof[0];
+    const int d = pool_dof<MAXD, EXACT>(P);
     double s = 1.0;
     MCI_FOR_D(i, d, MAXD) s += P.userdata[i] * X(0, i + 1);
     w[0] = 1.0 / ipow(s, d + 1);
@@ -95,7 +127,7 @@ struct Integrand<MCI_F_GENZ_CORNER_POOL> {
 template <>
 struct Integrand<MCI_F_GENZ_CORNER_COMP> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     const int d = P.nleaf;
     double s = 1.0;
@@ -108,7 +140,7 @@ struct Integrand<MCI_F_GENZ_CORNER_COMP> {
 template <>
 struct Integrand<MCI_F_BUBBLE> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     const double *ud = P.userdata;
     double kF = ud[0], beta = ud[1], me = ud[2], spin = ud[3];
@@ -136,9 +168,9 @@ struct Integrand<MCI_F_BUBBLE> {
 template <>
 struct Integrand<MCI_F_PRODUCT_4> {
   static constexpr int NI = 4;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
-    const int d = P.dof[0];
+    const int d = pool_dof<MAXD, EXACT>(P);
     double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
     MCI_FOR_D(i, d, MAXD) {
       double xc = X(0, i + 1) - 0.5;
@@ -155,7 +187,7 @@ struct Integrand<MCI_F_PRODUCT_4> {
 template <>
 struct Integrand<MCI_F_SPHERE1> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double a = X(0, 1), b = X(0, 2);
     w[0] = (__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)) < 1.0) ? 1.0 : 0.0;
@@ -166,7 +198,7 @@ struct Integrand<MCI_F_SPHERE1> {
 template <>
 struct Integrand<MCI_F_SPHERE2> {
   static constexpr int NI = 2;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double a = X(0, 1), b = X(0, 2), z = X(0, 3);
     double r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
@@ -179,7 +211,7 @@ struct Integrand<MCI_F_SPHERE2> {
 template <>
 struct Integrand<MCI_F_DISCRETE_X> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = X(0, 1); }
 };
 
@@ -187,7 +219,7 @@ struct Integrand<MCI_F_DISCRETE_X> {
 template <>
 struct Integrand<MCI_F_DISCRETE2_CONST> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = 1.0; }
 };
 
@@ -195,7 +227,7 @@ struct Integrand<MCI_F_DISCRETE2_CONST> {
 template <>
 struct Integrand<MCI_F_LATTICE_POOL> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(0, 2)) * cos(X(0, 3))) / (MCI_PI * MCI_PI * MCI_PI);
   }
@@ -205,7 +237,7 @@ struct Integrand<MCI_F_LATTICE_POOL> {
 template <>
 struct Integrand<MCI_F_LATTICE_COMP> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(1, 1)) * cos(X(2, 1))) / (MCI_PI * MCI_PI * MCI_PI);
   }
@@ -215,7 +247,7 @@ struct Integrand<MCI_F_LATTICE_COMP> {
 template <>
 struct Integrand<MCI_F_HYPERSPHERE3> {
   static constexpr int NI = 3;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double x1 = X(0, 1);
     double s = __dmul_rn(x1, x1);
@@ -232,7 +264,7 @@ struct Integrand<MCI_F_HYPERSPHERE3> {
 template <>
 struct Integrand<MCI_F_POLY3> {
   static constexpr int NI = 3;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double x = X(0, 1);
     w[0] = x; w[1] = x * x; w[2] = x * x * x;
@@ -243,7 +275,7 @@ struct Integrand<MCI_F_POLY3> {
 template <>
 struct Integrand<MCI_F_X2_PLUS_Y2> {
   static constexpr int NI = 1;
-  template <int MAXD, class XA>
+  template <int MAXD, class XA, bool EXACT = false>
   __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
     double a = X(0, 1), b = X(0, 2);
     w[0] = a * a + b * b;

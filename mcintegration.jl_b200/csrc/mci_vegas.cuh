@@ -55,6 +55,43 @@ __device__ __forceinline__ void red_shared_f64(uint32_t saddr, double v) {
   asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory");
 }
 
+/* hist[bin[p]] += v for p0 <= p < min(p0 + B, n) on the striped shared histogram, B updates in flight together:
+ * the B loads are issued back to back, then the B compare-and-swaps, so one sample pays ~2 shared-memory round trips
+ * per batch instead of 2 per update (ncu: the serial LDS -> DADD -> CAS chains were 1/3 of a warp's time, stall
+ * short_scoreboard).  A CAS that lost a race — another thread, or an earlier slot of this thread on the same bin —
+ * falls back to the looping red.shared.add.f64. */
+template <int B, int MAXD, bool EXACT>
+__device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, int p0, int n, double v) {
+  uint32_t a[B];
+  unsigned long long old[B], got[B];
+#pragma unroll
+  for (int q = 0; q < B; ++q)
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) {
+      a[q] = hist_saddr + (8u * STRIPE) * (uint32_t)bin[p0 + q];
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(old[q]) : "r"(a[q]) : "memory");
+    }
+#pragma unroll
+  for (int q = 0; q < B; ++q)
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) {
+      const unsigned long long nw = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[q]) + v);
+      asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(got[q]) : "r"(a[q]), "l"(old[q]), "l"(nw) : "memory");
+    }
+  bool lost = false;
+#pragma unroll
+  for (int q = 0; q < B; ++q)
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) lost = lost || (got[q] != old[q]);
+  if (lost) {
+#pragma unroll
+    for (int q = 0; q < B; ++q)
+      if (p0 + q < MAXD && (EXACT || p0 + q < n))
+        if (got[q] != old[q]) red_shared_f64(a[q], v);
+  }
+}
+
+#ifndef MCI_HIST_BATCH
+#define MCI_HIST_BATCH 5
+#endif
+
 template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD>
 __device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey &K, const double2 *__restrict__ pair,
                                             uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
@@ -88,7 +125,7 @@ __device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey
     }
   }
   double w[NI];
-  F::template eval<MAXD>(X, P, w);
+  F::template eval<MAXD, PoolX<MAXD>, EXACT>(X, P, w);
   double pad[NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
@@ -104,8 +141,7 @@ __device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey
 #pragma unroll
   for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
   if ((!GUARD || active) && !finite) bad++;
-  const bool meas = (!GUARD || active) && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
-  if (meas) {
+  if (!GUARD || active) { /* measurefreq == 1 on this kernel (the planner sends other values to the generic kernel) */
 #pragma unroll
     for (int i = 0; i < NI; ++i) acc[i] += w[i] * pad[i] * jac;
     cnt++;
@@ -116,19 +152,31 @@ __device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey
       const double a = fabs(w[i]) * jac;
       const double w2 = a * a;
       const int di = EXACT ? MAXD : P.dof[i * P.nv];
+      if constexpr (HMODE == HIST_SMEM_STRIPED && MCI_HIST_BATCH > 1) {
 #pragma unroll
-      for (int p = 0; p < MAXD; ++p)
-        if (p < di) {
-          if (HMODE == HIST_SMEM_ATOMIC) red_shared_f64(hist_saddr + 8u * (uint32_t)bin[p], w2);
-          else if (HMODE == HIST_SMEM_STRIPED) red_shared_f64(hist_saddr + (8u * STRIPE) * (uint32_t)bin[p], w2); /* base holds the lane's stripe */
-          else atomicAdd(ghist + bin[p], w2); /* RED.E.ADD.F64 */
-        }
+        for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) hist_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, w2);
+      } else {
+#pragma unroll
+        for (int p = 0; p < MAXD; ++p)
+          if (p < di) {
+            if (HMODE == HIST_SMEM_ATOMIC) red_shared_f64(hist_saddr + 8u * (uint32_t)bin[p], w2);
+            else if (HMODE == HIST_SMEM_STRIPED) red_shared_f64(hist_saddr + (8u * STRIPE) * (uint32_t)bin[p], w2); /* base holds the lane's stripe */
+            else atomicAdd(ghist + bin[p], w2); /* RED.E.ADD.F64 */
+          }
+      }
     }
   }
 }
 
+/* resident CTAs per SM the register allocation aims at: 64 registers per thread up to 12 slots (and always for the
+ * 1024-thread striped variant), 80 up to 16 slots, 128 beyond — x[] and bin[] of a sample live in registers */
+template <int MAXD, int THREADS>
+struct PoolMinBlocks {
+  static constexpr int value = THREADS >= 1024 ? 1 : (MAXD <= 12 ? 1024 / THREADS : (MAXD <= 16 ? 768 / THREADS : 512 / THREADS));
+};
+
 template <int FID, int MAXD, int HMODE, int THREADS, bool EXACT>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+__global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;

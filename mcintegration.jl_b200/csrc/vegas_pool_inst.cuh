@@ -8,7 +8,9 @@
     case mci::HIST_NONE: return (const void *)mci::vegas_pool_kernel<FID, MAXD, mci::HIST_NONE, mci::POOL_THREADS, EXACT>;        \
     case mci::HIST_SMEM_ATOMIC: return (const void *)mci::vegas_pool_kernel<FID, MAXD, mci::HIST_SMEM_ATOMIC, mci::POOL_THREADS, EXACT>; \
     case mci::HIST_GLOBAL_RED: return (const void *)mci::vegas_pool_kernel<FID, MAXD, mci::HIST_GLOBAL_RED, mci::POOL_THREADS, EXACT>;   \
-    case mci::HIST_SMEM_STRIPED: return (const void *)mci::vegas_pool_kernel<FID, MAXD, mci::HIST_SMEM_STRIPED, mci::POOL_THREADS_STRIPED, EXACT>; \
+    case mci::HIST_SMEM_STRIPED:                                                                                                 \
+      if (MAXD <= 20) return (const void *)mci::vegas_pool_kernel<FID, (MAXD <= 20 ? MAXD : 1), mci::HIST_SMEM_STRIPED, mci::POOL_THREADS_STRIPED, EXACT>; \
+      return nullptr; /* 1024 threads x 64 registers cannot hold more than 20 slots without spilling */                           \
   }
 
 /* run-time dof <= MAXD, predicated */

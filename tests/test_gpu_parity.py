@@ -55,6 +55,25 @@ def test_L0_samples(name):
         gpu.close(); cpu.close()
 
 
+def test_device_exp():
+    """exp_nonpos (csrc/mci_integrands.cuh) against glibc over its whole range, through the 1-D Gaussian on (-39, 39):
+    -x^2/2 runs from 0 to -760, i.e. normal results, subnormal results and exact zero."""
+    import math
+    cfg = mci.Configuration(var=mci.Continuous(-39.0, 39.0), dof=[[1]], seed=11)
+    spec = mci.problem_from_config(cfg, mci.integrands.gauss_nd, solver=_abi.SOLVER_VEGAS, measure_kind=0, n_block=2,
+                                   neval_per_block=1 << 14)
+    gpu = mci.CudaEngine(spec)
+    try:
+        x, _, _, w = gpu.trace_samples(0, 1, 0, 1 << 14)
+        want = np.array([math.exp(-0.5 * v * v) for v in x[:, 0]]) * (2 * math.pi) ** -0.5
+        normal = want > 1e-300
+        assert normal.sum() > 1000 and (~normal).sum() > 100
+        np.testing.assert_allclose(w[normal, 0], want[normal], rtol=4e-16 * 2)
+        np.testing.assert_allclose(w[~normal, 0], want[~normal], rtol=0, atol=1e-315)
+    finally:
+        gpu.close()
+
+
 def _assert_stats(a, b, *, obs_rtol=1e-11, hist_rtol=1e-10, counts_exact=True):
     scale = np.abs(b.block_obs).max() + 1e-300
     np.testing.assert_allclose(a.block_obs, b.block_obs, rtol=obs_rtol, atol=obs_rtol * scale)
