@@ -4,7 +4,7 @@
 namespace mci {
 const void *lookup_vegasmc(int fid, const char **name) {
   switch (fid) {
-#define M(FID) case FID: if (name) *name = "vegasmc_kernel<" #FID ">"; return (const void *)vegasmc_kernel<FID, CHAIN_THREADS>;
+#define M(FID) case FID: if (name) *name = "vegasmc_kernel<" #FID ">"; return (const void *)vegasmc_kernel<FID>;
     MCI_FOR_EACH_FID(M)
 #undef M
   }

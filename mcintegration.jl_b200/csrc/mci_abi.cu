@@ -98,7 +98,7 @@ struct mci_handle_t {
   bool is_pool = false;
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
   size_t smem = 0;
-  int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0;
+  int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0, chain_rows = 0, coop_ci = 0;
   uint64_t steps = 0;
   bool maps_dirty = true, have_iteration = false, async_mode = false;
   nccl_comm_t comm = nullptr;
@@ -169,6 +169,7 @@ int plan(mci_handle_t *h) {
   const size_t SMEM_MAX = 227 * 1024;
   int policy = p.hist_policy;
   if (!P.any_adapt) policy = -1;
+  int best_mis = 1;
 
   auto pick_hist = [&](int nwarp, size_t extra, bool allow_private) {
     /* returns mode and sets maps_in_smem */
@@ -228,13 +229,44 @@ int plan(mci_handle_t *h) {
       h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
     }
   } else {
-    const int nwarp = CHAIN_THREADS / 32;
-    const size_t red = (size_t)nwarp * 8 + (p.solver == MCI_SOLVER_MCMC ? 2 * (size_t)h->pa_len * 4 : 0) + 8;
-    int mode = pick_hist(nwarp, red, true);
+    /* chain solvers: walker state in shared memory rows [row][thread]; pick the CTA size that keeps most walkers
+     * resident per SM (the maps and the histogram are per CTA, so larger CTAs amortise them) */
     h->kernel = p.solver == MCI_SOLVER_VEGASMC ? lookup_vegasmc(P.fid, &h->kernel_name) : lookup_mcmc(P.fid, &h->kernel_name);
     if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no chain kernel", P.fid);
-    h->threads = CHAIN_THREADS; h->hist_mode = mode;
-    h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
+    int max_nl = 1;
+    for (int v = 0; v < P.nv; ++v) max_nl = std::max(max_nl, P.top_nleaf[v]);
+    h->chain_rows = P.n_draw + max_nl;
+    { /* largest number of (slot, leaf) items one changeIntegrand creates or removes, over the neighbour graph */
+      int worst = 0;
+      for (int a = 0; a < P.nd; ++a)
+        for (int k = P.nb_ptr[a]; k < P.nb_ptr[a + 1]; ++k) {
+          int items = 0;
+          for (int v = 0; v < P.nv; ++v) items += std::abs(P.dof[a * P.nv + v] - P.dof[P.nb_idx[k] * P.nv + v]) * P.top_nleaf[v];
+          worst = std::max(worst, items);
+        }
+      h->coop_ci = worst >= 8; /* measured: 20 items 1.8x faster cooperatively, 2-4 items 1.6x slower */
+    }
+    const size_t row_bytes = (size_t)h->chain_rows * (8 + 4 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0));
+    const size_t fixed = 32 * 8 + (((size_t)2 * h->pa_len + 1) / 2) * 8;
+    const int W = std::max(1, p.walkers_per_block);
+    CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    int best_score = -1;
+    for (int T = 1024; T >= 128; T >>= 1) {
+      if (T > 128 && T / 2 >= W) continue; /* more than half of the CTA would idle */
+      const int nwarp = T / 32;
+      const size_t extra = fixed + row_bytes * T;
+      if (extra > SMEM_MAX) continue;
+      int policy_mode = pick_hist(nwarp, extra, false);
+      if (policy_mode == HIST_WARP_PRIVATE) policy_mode = HIST_SMEM_ATOMIC;
+      const int mis = h->maps_in_smem;
+      const size_t smem = (mis ? map_bytes : 0) + hist_smem(policy_mode, nwarp) + extra;
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, T, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+      const int score = occ * T * 4 + (mis ? 2 : 0) + (policy_mode == HIST_SMEM_ATOMIC ? 1 : 0);
+      if (score > best_score) { best_score = score; h->threads = T; h->hist_mode = policy_mode; h->smem = smem; best_mis = mis; }
+    }
+    if (best_score < 0) return fail(h, MCI_ERR_UNSUPPORTED, "walker state of %d rows does not fit in shared memory", h->chain_rows);
+    h->maps_in_smem = best_mis;
   }
   CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   int occ = 0;
@@ -420,6 +452,8 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
       const DevLeaf &E = P.leaf[nleaf - 1];
       if (E.kind != MCI_LEAF_DISCRETE || P.obs_len[0] < E.nbins || P.maxdof[E.top] < 1)
         BAIL(MCI_ERR_INVALID, "bin-by-discrete measure needs a Discrete last leaf and obs_len[0] >= its size");
+      if (p->solver != MCI_SOLVER_VEGAS && E.nbins > CHAIN_MAX_BINNED_OBS)
+        BAIL(MCI_ERR_UNSUPPORTED, "bin-by-discrete measure of the chain solvers keeps at most %d bins", CHAIN_MAX_BINNED_OBS);
     } else if (p->measure_kind != MCI_MEASURE_DEFAULT) BAIL(MCI_ERR_INVALID, "unknown measure kind %d", p->measure_kind);
   }
   /* neighbor graph: configuration.jl:201-209 default, or the caller's CSR */
@@ -582,6 +616,7 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, p.walkers_per_block);
     CA.ctas_per_block = h->ctas_per_block; CA.n_local_blocks = n_local; CA.rank = h->rank; CA.world = h->world;
     CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;
+    CA.rows = h->chain_rows; CA.coop_ci = h->coop_ci;
     args[0] = &h->dp; args[1] = &CA;
   }
   const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);

@@ -7,14 +7,25 @@
  *   pool operations     create!/remove!/shift!/swap! and rollbacks, src/distribution/sampler.jl:13-97, 293-462
  *   probabilities       src/distribution/variable.jl:587-641
  *
- * The reference runs ONE chain of neval_per_block steps per block.  A GPU needs ~10^5 concurrent
- * chains, so a block is `walkers_per_block` independent chains of neval_per_block/walkers steps
- * (recorded in mci_problem_t; walkers = 1 is the reference's decomposition).  Walker w of block b
- * draws sequentially from the Philox stream (seed, iter, b, w).  Per-step arithmetic follows the
- * reference operation by operation (stateful shift! ratios, rollback caches, padding products).
+ * The reference runs ONE chain of neval_per_block steps per block.  A GPU needs ~10^5 concurrent chains, so a
+ * block is `walkers_per_block` independent chains of neval_per_block/walkers steps (recorded in mci_problem_t;
+ * walkers = 1 is the reference's decomposition).  Walker w of block b draws sequentially from the Philox stream
+ * (seed, iter, b, w).  Per-step arithmetic follows the reference operation by operation (stateful shift! ratios,
+ * rollback caches, padding products).
  *
- * Statistics: observable / normalisation / visited / propose / accept are accumulated per thread
- * and reduced per CTA in a fixed order; all walkers of a CTA belong to one block.
+ * Walker state lives in SHARED memory as rows [row][thread]: data (x), gidx (bin) and — VegasMC only — the stateful
+ * prob of every (leaf, slot), plus one backup row per leaf of a variable for the rollback of shift!.  A thread only
+ * ever touches column `tid`, and the row stride is a multiple of 16 doubles, so every access is bank-conflict free
+ * whatever slot a lane picks at random (round 1's first cut kept 64-entry arrays per thread in local memory:
+ * ncu long_scoreboard 4.9-5.7 warps per issue, 12 % occupancy).  A CompositeVar's probability is the product of its
+ * leaves' probabilities in leaf order, recomputed on demand (the reference caches the same product).
+ *
+ * MCMC evaluates ONE integrand per proposal whatever the update type, so the step is written as
+ * propose (divergent, cheap) -> evaluate (convergent, the expensive part) -> accept/rollback (divergent, cheap):
+ * the three update types share one integrand call site instead of serialising three copies of it.
+ *
+ * Statistics: observable / normalisation / visited / propose / accept are accumulated per thread and reduced per CTA
+ * in a fixed order; all walkers of a CTA belong to one block.
  */
 #pragma once
 #include "mci_integrands.cuh"
@@ -32,18 +43,18 @@ struct ChainArgs {
   int walkers_per_block, ctas_per_block;
   int n_local_blocks, rank, world;
   int hist_mode, n_hist_copies, maps_in_smem;
+  int rows;               /* walker rows in shared memory = n_draw + max leaves of one variable  */
+  int coop_ci;            /* mcmc: changeIntegrand creates/removes enough slots for the warp-cooperative path */
 };
 
-/* per-walker pool state.  Flat index of (leaf, slot) = leaf.base + (slot-1)*leaf.stride, the same
- * indexing the integrands use; tprob holds the CompositeVar products per (variable, slot). */
+/* a walker's columns of the shared state; T = row stride (threads per CTA) */
+template <bool HAS_PROB>
 struct Walker {
-  double data[MAX_DRAW];
-  double prob[MAX_DRAW];
-  double tprob[MAX_DRAW];
-  int gidx[MAX_DRAW]; /* 0-based bin: grid increment (Continuous) / value - lower (Discrete) */
-  /* rollback cache of the last shift! (the reference keeps it in the pool's last element) */
-  double bk_data[MCI_MAX_LEAF], bk_prob[MCI_MAX_LEAF], bk_tprob;
-  int bk_gidx[MCI_MAX_LEAF];
+  double *data;
+  double *prob; /* HAS_PROB only */
+  int *gidx;    /* 0-based bin: grid increment (Continuous) / value - lower (Discrete) */
+  int T;
+  int bk0;      /* first backup row */
 };
 
 struct ChainCtx {
@@ -54,32 +65,46 @@ struct ChainCtx {
   __device__ __forceinline__ ChainCtx(const DevProblem &p, const double *m, const PhiloxKey &k) : P(p), maps(m), K(k) {}
 };
 
-__device__ __forceinline__ int fidx(const DevLeaf &L, int pos) { return L.base + (pos - 1) * L.stride; }
+/* integrand accessor on the shared walker rows: X(leaf, pos), pos 1-based like the reference's x[pos] */
+struct ChainX {
+  const double *data;
+  const DevProblem *P;
+  int T;
+  __device__ __forceinline__ double operator()(int leaf, int pos) const {
+    return data[(P->leaf[leaf].base + (pos - 1) * P->leaf[leaf].stride) * T];
+  }
+};
+
+__device__ __forceinline__ int frow(const DevLeaf &L, int pos) { return L.base + (pos - 1) * L.stride; }
 
 /* create! : sampler.jl:293-305 (Continuous), :13-22 (Discrete).  Returns 1/prob. */
-__device__ __forceinline__ double leaf_create(ChainCtx &C, Walker &W, const DevLeaf &L, int pos) {
-  const int f = fidx(L, pos);
+template <bool HP>
+__device__ __forceinline__ double leaf_create(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos) {
+  const int f = frow(L, pos) * W.T;
   const double u = C.rng.rand(C.K);
   if (L.kind == MCI_LEAF_CONTINUOUS) {
     int iy;
     double dx;
     W.data[f] = map_continuous(reinterpret_cast<const double2 *>(C.maps + L.smem_off), L.nbins, L.nbins_d, u, iy, dx);
     W.gidx[f] = iy;
-    W.prob[f] = __ddiv_rn(1.0, __dmul_rn(L.nbins_d, dx));
-    return __ddiv_rn(1.0, W.prob[f]);
+    if (!HP) return __dmul_rn(L.nbins_d, dx); /* 1/prob = N dx (the reference's 1/(1/(N dx)) to 1 ulp) */
+    const double pr = __ddiv_rn(1.0, __dmul_rn(L.nbins_d, dx));
+    W.prob[f] = pr;
+    return __ddiv_rn(1.0, pr);
   } else {
     const double *dist = C.maps + L.smem_off;
     const int g = locate_clamped(dist + L.nbins, L.nbins, u);
     W.data[f] = (double)(L.lower_i + g);
     W.gidx[f] = g;
-    W.prob[f] = dist[g];
+    if (HP) W.prob[f] = dist[g];
     return __ddiv_rn(1.0, dist[g]);
   }
 }
 
 /* remove! : sampler.jl:317-322, :37-41 */
-__device__ __forceinline__ double leaf_remove(ChainCtx &C, Walker &W, const DevLeaf &L, int pos) {
-  const int f = fidx(L, pos);
+template <bool HP>
+__device__ __forceinline__ double leaf_remove(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos) {
+  const int f = frow(L, pos) * W.T;
   if (L.kind == MCI_LEAF_CONTINUOUS) {
     const double2 g = reinterpret_cast<const double2 *>(C.maps + L.smem_off)[W.gidx[f]];
     return __ddiv_rn(1.0, __dmul_rn(g.y, L.nbins_d));
@@ -88,13 +113,15 @@ __device__ __forceinline__ double leaf_remove(ChainCtx &C, Walker &W, const DevL
   }
 }
 
-/* shift! : sampler.jl:336-386, :57-71.  k = leaf number inside its variable (rollback slot). */
-__device__ __forceinline__ double leaf_shift(ChainCtx &C, Walker &W, const DevLeaf &L, int pos, int k) {
-  const int f = fidx(L, pos);
-  W.bk_data[k] = W.data[f];
-  W.bk_gidx[k] = W.gidx[f];
-  W.bk_prob[k] = W.prob[f];
+/* shift! : sampler.jl:336-386, :57-71.  k = leaf number inside its variable (backup row). */
+template <bool HP>
+__device__ __forceinline__ double leaf_shift(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos, int k) {
+  const int f = frow(L, pos) * W.T;
+  const int b = (W.bk0 + k) * W.T;
+  W.data[b] = W.data[f];
   const int curr = W.gidx[f];
+  W.gidx[b] = curr;
+  if (HP) W.prob[b] = W.prob[f];
   const double u = C.rng.rand(C.K);
   double ratio;
   if (L.kind == MCI_LEAF_CONTINUOUS) {
@@ -111,222 +138,215 @@ __device__ __forceinline__ double leaf_shift(ChainCtx &C, Walker &W, const DevLe
     W.gidx[f] = g;
     ratio = __ddiv_rn(dist[g], dist[curr]);
   }
-  W.prob[f] = __dmul_rn(W.prob[f], ratio);
+  if (HP) W.prob[f] = __dmul_rn(W.prob[f], ratio);
   return __ddiv_rn(1.0, ratio);
 }
 
-/* probability of (variable v, slot pos): the leaf's own for plain variables, the cached product for CompositeVar */
-__device__ __forceinline__ double top_prob(const DevProblem &P, const Walker &W, int v, int pos) {
-  if (P.top_nleaf[v] == 1) return W.prob[fidx(P.leaf[P.top_first[v]], pos)];
-  return W.tprob[P.top_tslot[v] + pos - 1];
+/* probability of (variable v, slot pos): the leaf's own for plain variables, the product over the leaves in leaf
+ * order for a CompositeVar (sampler.jl:431-440 keeps exactly this product in its cache) */
+__device__ __forceinline__ double top_prob(const DevProblem &P, const Walker<true> &W, int v, int pos) {
+  const int nl = P.top_nleaf[v];
+  if (nl == 1) return W.prob[frow(P.leaf[P.top_first[v]], pos) * W.T];
+  double tp = 1.0;
+  for (int k = 0; k < nl; ++k) tp = __dmul_rn(tp, W.prob[frow(P.leaf[P.top_first[v] + k], pos) * W.T]);
+  return tp;
 }
 
 /* top-level dispatch incl. CompositeVar: sampler.jl:410-462 */
-__device__ __forceinline__ double var_create(ChainCtx &C, Walker &W, int v, int pos) {
+template <bool HP>
+__device__ __forceinline__ double var_create(ChainCtx &C, Walker<HP> &W, int v, int pos) {
   const DevProblem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_create(C, W, P.leaf[P.top_first[v]], pos);
-  double prop = 1.0, tp = 1.0;
-  for (int k = 0; k < nl; ++k) {
-    const DevLeaf &L = P.leaf[P.top_first[v] + k];
-    prop = __dmul_rn(prop, leaf_create(C, W, L, pos));
-    tp = __dmul_rn(tp, W.prob[fidx(L, pos)]);
-  }
-  W.tprob[P.top_tslot[v] + pos - 1] = tp;
+  double prop = 1.0;
+  for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_create(C, W, P.leaf[P.top_first[v] + k], pos));
   return prop;
 }
-__device__ __forceinline__ double var_remove(ChainCtx &C, Walker &W, int v, int pos) {
+template <bool HP>
+__device__ __forceinline__ double var_remove(ChainCtx &C, Walker<HP> &W, int v, int pos) {
   const DevProblem &P = C.P;
-  double prop = 1.0;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_remove(C, W, P.leaf[P.top_first[v]], pos);
+  double prop = 1.0;
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_remove(C, W, P.leaf[P.top_first[v] + k], pos));
   return prop;
 }
-__device__ __forceinline__ double var_shift(ChainCtx &C, Walker &W, int v, int pos) {
+template <bool HP>
+__device__ __forceinline__ double var_shift(ChainCtx &C, Walker<HP> &W, int v, int pos) {
   const DevProblem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_shift(C, W, P.leaf[P.top_first[v]], pos, 0);
-  double prop = 1.0, tp = 1.0;
-  W.bk_tprob = W.tprob[P.top_tslot[v] + pos - 1];
-  for (int k = 0; k < nl; ++k) {
-    const DevLeaf &L = P.leaf[P.top_first[v] + k];
-    prop = __dmul_rn(prop, leaf_shift(C, W, L, pos, k));
-    tp = __dmul_rn(tp, W.prob[fidx(L, pos)]);
-  }
-  W.tprob[P.top_tslot[v] + pos - 1] = tp;
+  double prop = 1.0;
+  for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_shift(C, W, P.leaf[P.top_first[v] + k], pos, k));
   return prop;
 }
-__device__ __forceinline__ void var_shift_rollback(ChainCtx &C, Walker &W, int v, int pos) {
-  const DevProblem &P = C.P;
+template <bool HP>
+__device__ __forceinline__ void var_shift_rollback(const DevProblem &P, Walker<HP> &W, int v, int pos) {
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k) {
-    const int f = fidx(P.leaf[P.top_first[v] + k], pos);
-    W.data[f] = W.bk_data[k];
-    W.gidx[f] = W.bk_gidx[k];
-    W.prob[f] = W.bk_prob[k];
+    const int f = frow(P.leaf[P.top_first[v] + k], pos) * W.T;
+    const int b = (W.bk0 + k) * W.T;
+    W.data[f] = W.data[b];
+    W.gidx[f] = W.gidx[b];
+    if (HP) W.prob[f] = W.prob[b];
   }
-  if (nl > 1) W.tprob[P.top_tslot[v] + pos - 1] = W.bk_tprob;
 }
 /* swap! (its own inverse): sampler.jl:85-97, 395-408, 443-462 */
-__device__ __forceinline__ void var_swap(ChainCtx &C, Walker &W, int v, int p1, int p2) {
-  const DevProblem &P = C.P;
+template <bool HP>
+__device__ __forceinline__ void var_swap(const DevProblem &P, Walker<HP> &W, int v, int p1, int p2) {
   const int nl = P.top_nleaf[v];
-  if (nl > 1) {
-    double t = W.tprob[P.top_tslot[v] + p1 - 1];
-    W.tprob[P.top_tslot[v] + p1 - 1] = W.tprob[P.top_tslot[v] + p2 - 1];
-    W.tprob[P.top_tslot[v] + p2 - 1] = t;
-  }
   for (int k = 0; k < nl; ++k) {
     const DevLeaf &L = P.leaf[P.top_first[v] + k];
-    const int a = fidx(L, p1), b = fidx(L, p2);
+    const int a = frow(L, p1) * W.T, b = frow(L, p2) * W.T;
     double t = W.data[a]; W.data[a] = W.data[b]; W.data[b] = t;
     int g = W.gidx[a]; W.gidx[a] = W.gidx[b]; W.gidx[b] = g;
-    t = W.prob[a]; W.prob[a] = W.prob[b]; W.prob[b] = t;
+    if (HP) { t = W.prob[a]; W.prob[a] = W.prob[b]; W.prob[b] = t; }
   }
 }
 
 /* initialize!: variable.jl:576-580 / :497-507 — leaf-major, slots 1..maxdof */
-__device__ __forceinline__ void var_initialize(ChainCtx &C, Walker &W, int v) {
+template <bool HP>
+__device__ __forceinline__ void var_initialize(ChainCtx &C, Walker<HP> &W, int v) {
   const DevProblem &P = C.P;
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k)
     for (int pos = 1; pos <= P.maxdof[v]; ++pos) leaf_create(C, W, P.leaf[P.top_first[v] + k], pos);
-  if (nl > 1)
-    for (int pos = 1; pos <= P.maxdof[v]; ++pos) {
-      double tp = 1.0;
-      for (int k = 0; k < nl; ++k) tp = __dmul_rn(tp, W.prob[fidx(P.leaf[P.top_first[v] + k], pos)]);
-      W.tprob[P.top_tslot[v] + pos - 1] = tp;
-    }
 }
 
 /* variable.jl:606-619 / :628-641 */
-__device__ __forceinline__ double probability(const DevProblem &P, const Walker &W, int i) {
+__device__ __forceinline__ double probability(const DevProblem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
   for (int v = 0; v < P.nv; ++v)
     for (int pos = 1; pos <= P.dof[i * P.nv + v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
   return pr;
 }
-__device__ __forceinline__ double padding_probability(const DevProblem &P, const Walker &W, int i) {
+__device__ __forceinline__ double padding_probability(const DevProblem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
   for (int v = 0; v < P.nv; ++v)
     for (int pos = P.dof[i * P.nv + v] + 1; pos <= P.maxdof[v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
   return pr;
 }
 
-/* accumulate! on every adaptive leaf of (variable v, slot pos); warp-collective */
-__device__ __forceinline__ void var_accumulate(const DevProblem &P, const Walker &W, int hmode, double *hist, int v,
-                                               int pos, double wgt, bool active) {
-  for (int k = 0; k < P.top_nleaf[v]; ++k) {
-    const DevLeaf &L = P.leaf[P.top_first[v] + k];
-    if (L.adapt) hist_add_rt(hmode, hist + L.hist_off, W.gidx[fidx(L, pos)], wgt, active);
-  }
+/* hist[bin] += v on the CTA's shared histogram (32-bit shared address) or on an L2-resident global partial */
+__device__ __forceinline__ void chain_hist_add(int hmode, uint32_t hist_saddr, double *ghist, int bin, double v) {
+  if (hmode == HIST_SMEM_ATOMIC) asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(hist_saddr + 8u * (uint32_t)bin), "d"(v) : "memory");
+  else atomicAdd(ghist + bin, v);
 }
 
 /* CTA reduction of one per-thread value in a fixed order; returns the total in thread 0 */
-template <int THREADS>
 __device__ __forceinline__ double cta_sum(double v, double *sred) {
-  constexpr int NWARP = THREADS / 32;
+  const int nwarp = blockDim.x >> 5;
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
   __syncthreads();
   double t = 0.0;
   if (threadIdx.x == 0)
-    for (int wv = 0; wv < NWARP; ++wv) t += sred[wv];
+    for (int wv = 0; wv < nwarp; ++wv) t += sred[wv];
   return t;
 }
 
+/* shared-memory carve-up of the chain kernels:
+ *   [maps (if they fit)] [histogram (HIST_SMEM_ATOMIC)] [reduction scratch: 32 doubles] [mcmc: 2*pa_len u32 counters]
+ *   [walker data rows*T doubles] [walker prob rows*T doubles (VegasMC)] [walker gidx rows*T ints]                  */
 struct ChainSmem {
-  double *maps_s, *shist, *sred;
   const double *maps;
-  double *myhist;
+  double *shist, *sred;
+  unsigned int *scount;
+  uint32_t hist_saddr;
+  double *ghist;
 };
 
-template <int THREADS>
-__device__ __forceinline__ ChainSmem chain_setup(const DevProblem &P, const ChainArgs &A, double *smem) {
-  constexpr int NWARP = THREADS / 32;
+template <bool HP>
+__device__ __forceinline__ ChainSmem chain_setup(const DevProblem &P, const ChainArgs &A, double *smem, int n_count, Walker<HP> &W) {
+  const int T = blockDim.x, tid = threadIdx.x;
   ChainSmem S;
-  S.maps_s = smem;
+  double *maps_s = smem;
   const int map_smem = A.maps_in_smem ? P.map_doubles : 0;
   S.shist = smem + map_smem;
-  const int nsh = A.hist_mode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (A.hist_mode == HIST_SMEM_ATOMIC ? P.hist_len : 0);
+  const int nsh = A.hist_mode == HIST_SMEM_ATOMIC ? P.hist_len : 0;
   S.sred = S.shist + nsh;
-  if (A.maps_in_smem) stage_maps(P, S.maps_s, A.gmaps);
-  for (int i = threadIdx.x; i < nsh; i += THREADS) S.shist[i] = 0.0;
+  S.scount = reinterpret_cast<unsigned int *>(S.sred + 32);
+  double *wbase = S.sred + 32 + ((n_count + 1) >> 1);
+  W.T = T;
+  W.bk0 = P.n_draw;
+  W.data = wbase + tid;
+  W.prob = HP ? wbase + (size_t)A.rows * T + tid : nullptr;
+  W.gidx = reinterpret_cast<int *>(wbase + (size_t)(HP ? 2 : 1) * A.rows * T) + tid;
+  if (A.maps_in_smem) stage_maps(P, maps_s, A.gmaps);
+  for (int i = tid; i < nsh; i += T) S.shist[i] = 0.0;
+  for (int i = tid; i < n_count; i += T) S.scount[i] = 0u;
   __syncthreads();
-  S.maps = A.maps_in_smem ? S.maps_s : A.gmaps;
-  const int warp = threadIdx.x >> 5;
-  S.myhist = A.hist_mode == HIST_WARP_PRIVATE ? S.shist + warp * P.hist_len
-             : A.hist_mode == HIST_SMEM_ATOMIC ? S.shist
-                                               : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
+  S.maps = A.maps_in_smem ? maps_s : A.gmaps;
+  S.hist_saddr = (uint32_t)__cvta_generic_to_shared(S.shist);
+  S.ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
   return S;
 }
 
-template <int THREADS>
 __device__ __forceinline__ void chain_flush_hist(const DevProblem &P, const ChainArgs &A, const ChainSmem &S) {
-  constexpr int NWARP = THREADS / 32;
-  if (A.hist_mode == HIST_WARP_PRIVATE || A.hist_mode == HIST_SMEM_ATOMIC) {
+  if (A.hist_mode == HIST_SMEM_ATOMIC) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
-    for (int i = threadIdx.x; i < P.hist_len; i += THREADS) {
-      double t = 0.0;
-      if (A.hist_mode == HIST_WARP_PRIVATE) {
-        for (int wv = 0; wv < NWARP; ++wv) t += S.shist[wv * P.hist_len + i];
-      } else {
-        t = S.shist[i];
-      }
-      out[i] = t;
-    }
+    for (int i = threadIdx.x; i < P.hist_len; i += blockDim.x) out[i] = S.shist[i];
   }
 }
 
+/* bin-by-Discrete observables of the chain kernels are kept in this many per-thread accumulators (mci_create checks) */
+constexpr int CHAIN_MAX_BINNED_OBS = 8;
 #define PA_IDX(P, u, i, j) (((u) * (P).nd + (i)) * (P).pa_dim + (j))
-constexpr int MAX_PA = 3 * MAX_ND * (MCI_MAX_TOPVAR > MAX_ND ? MCI_MAX_TOPVAR : MAX_ND);
 
 /* ------------------------------------------------------------------------------------------ */
 /* VegasMC                                                                                      */
 /* ------------------------------------------------------------------------------------------ */
-template <int FID, int THREADS>
-__global__ void __launch_bounds__(THREADS) vegasmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
+template <int FID>
+__global__ void __launch_bounds__(1024, 1) vegasmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   extern __shared__ __align__(16) double smem[];
-  ChainSmem S = chain_setup<THREADS>(P, A, smem);
+  Walker<true> W;
+  const int pa_len = P.pa_len_();
+  /* propose/accept[2, 1, vi] counters of the CTA (updates.jl:90,92): u32 in shared memory (native ATOMS.ADD) */
+  ChainSmem S = chain_setup<true>(P, A, smem, 2 * pa_len, W);
+  unsigned int *s_prop = S.scount, *s_acc = S.scount + pa_len;
   const int tid = threadIdx.x;
   const int lb = blockIdx.x / A.ctas_per_block;
   const int cb = blockIdx.x - lb * A.ctas_per_block;
   const uint32_t block = (uint32_t)(A.rank + lb * A.world);
-  const int walker = cb * THREADS + tid;
+  const int walker = cb * blockDim.x + tid;
   const bool active = walker < A.walkers_per_block;
-  const int N = P.ni;
+  constexpr int N = NI;
   const int hmode = A.hist_mode;
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
   ChainCtx C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
-  Walker W;
-  FlatX X{W.data, &P};
+  ChainX X{W.data, &P, W.T};
 
-  double rw[MAX_ND];
+  double rw[NI + 1];
+#pragma unroll
   for (int i = 0; i <= N; ++i) rw[i] = A.reweight[i];
 
-  double obs[MCI_MAX_OBS];
-  for (int o = 0; o < P.obs_total; ++o) obs[o] = 0.0;
-  double visited[MAX_ND];
+  /* per-thread statistics.  Default measure: one accumulator per integrand; bin-by-Discrete: one per bin, selected
+   * with a short compare chain so that the accumulators stay in registers */
+  constexpr int NOBS = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+  double obs[NOBS];
+#pragma unroll
+  for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
+  double visited[NI + 1];
+#pragma unroll
   for (int i = 0; i <= N; ++i) visited[i] = 0.0;
   double normalization = 0.0;
-  unsigned int n_prop[MCI_MAX_TOPVAR], n_acc[MCI_MAX_TOPVAR]; /* propose/accept[2, 1, vi] (updates.jl:90,92) */
-  for (int v = 0; v < P.nv; ++v) { n_prop[v] = 0; n_acc[v] = 0; }
   unsigned long long neval = 0, bad = 0;
 
   double weights[NI], nweights[NI], pad[NI + 1], npad[NI + 1];
   /* montecarlo.jl:151-166 */
   for (int v = 0; v < P.nv; ++v) var_initialize(C, W, v);
   F::template eval<0>(X, P, nweights);
-  for (int i = 0; i <= N; ++i) pad[i] = padding_probability(P, W, i);
+#pragma unroll
+  for (int i = 0; i <= N; ++i) pad[i] = P.need_pad || i == N ? padding_probability(P, W, i) : 1.0;
   double prob_cur = __dmul_rn(rw[N], pad[N]);
+#pragma unroll
   for (int i = 0; i < N; ++i) {
     weights[i] = nweights[i];
     prob_cur = __dadd_rn(prob_cur, __dmul_rn(__dmul_rn(fabs(nweights[i]), rw[i]), pad[i]));
@@ -344,43 +364,68 @@ __global__ void __launch_bounds__(THREADS) vegasmc_kernel(const __grid_constant_
           F::template eval<0>(X, P, nweights);
           neval++;
           bool finite = true;
+#pragma unroll
           for (int i = 0; i < N; ++i) finite = finite && isfinite(nweights[i]);
           if (!finite) bad++;
-          for (int i = 0; i <= N; ++i) npad[i] = padding_probability(P, W, i);
+#pragma unroll
+          for (int i = 0; i <= N; ++i) npad[i] = P.need_pad || i == N ? padding_probability(P, W, i) : 1.0;
           double prob_new = __dmul_rn(rw[N], npad[N]);
+#pragma unroll
           for (int i = 0; i < N; ++i)
             prob_new = __dadd_rn(prob_new, __dmul_rn(__dmul_rn(fabs(nweights[i]), rw[i]), npad[i]));
           const double R = __ddiv_rn(__dmul_rn(prop, prob_new), prob_cur);
-          n_prop[vi]++;
+          atomicAdd(&s_prop[PA_IDX(P, 1, 0, vi)], 1u);
           if (C.rng.rand(K) < R) {
-            n_acc[vi]++;
+            atomicAdd(&s_acc[PA_IDX(P, 1, 0, vi)], 1u);
+#pragma unroll
             for (int i = 0; i < N; ++i) weights[i] = nweights[i];
+#pragma unroll
             for (int i = 0; i <= N; ++i) pad[i] = npad[i];
             prob_cur = prob_new;
           } else {
-            var_shift_rollback(C, W, vi, pos);
+            var_shift_rollback(P, W, vi, pos);
           }
         }
       }
     }
     __syncwarp();
-    /* histogram of every step: montecarlo.jl:198-211 */
-    if (hmode != HIST_NONE) {
+    /* histogram of every step: montecarlo.jl:198-211.  hist[bin of (v, pos)] += wf2_i for every integrand i with
+     * pos <= dof[i][v]: the contributions of the integrands to one slot are summed first, one update per slot */
+    if (hmode != HIST_NONE && active) {
+      double wf2[NI];
+#pragma unroll
       for (int i = 0; i < N; ++i) {
         const double aw = fabs(weights[i]);
         const double f2 = __ddiv_rn(__dmul_rn(aw, aw), probability(P, W, i));
-        const double wf2 = __ddiv_rn(__dmul_rn(f2, pad[i]), prob_cur);
-        for (int v = 0; v < P.nv; ++v)
-          for (int pos = 1; pos <= P.dof[i * P.nv + v]; ++pos) var_accumulate(P, W, hmode, S.myhist, v, pos, wf2, active);
+        wf2[i] = __ddiv_rn(__dmul_rn(f2, pad[i]), prob_cur);
       }
+      for (int v = 0; v < P.nv; ++v)
+        for (int pos = 1; pos <= P.maxdof[v]; ++pos) {
+          double t = 0.0;
+          bool any = false;
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (pos <= P.dof[i * P.nv + v]) { t += wf2[i]; any = true; }
+          if (any)
+            for (int k = 0; k < P.top_nleaf[v]; ++k) {
+              const DevLeaf &L = P.leaf[P.top_first[v] + k];
+              if (L.adapt) chain_hist_add(hmode, S.hist_saddr + 8u * (uint32_t)L.hist_off, S.ghist + L.hist_off, W.gidx[frow(L, pos) * W.T], t);
+            }
+        }
     }
+    __syncwarp();
     /* measurement: montecarlo.jl:213-232 */
-    if (active && (ne % (uint64_t)P.measurefreq) == 0 && (double)ne >= meas_from) {
+    if (active && (P.measurefreq == 1 || (ne % (uint64_t)P.measurefreq) == 0) && (double)ne >= meas_from) {
+#pragma unroll
       for (int i = 0; i < N; ++i) {
         visited[i] += __ddiv_rn(fabs(__dmul_rn(__dmul_rn(weights[i], pad[i]), rw[i])), prob_cur);
         const double relw = __ddiv_rn(__dmul_rn(weights[i], pad[i]), prob_cur);
-        if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[P.obs_off[i]] += relw;
-        else if (i == 0) obs[P.obs_off[0] + W.gidx[P.leaf[P.nleaf - 1].base]] += relw;
+        if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[i] += relw;
+        else if (i == 0) {
+          const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
+#pragma unroll
+          for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
+        }
       }
       normalization += __ddiv_rn(pad[N], prob_cur);
       visited[N] += __ddiv_rn(__dmul_rn(rw[N], pad[N]), prob_cur);
@@ -389,52 +434,135 @@ __global__ void __launch_bounds__(THREADS) vegasmc_kernel(const __grid_constant_
   if (bad) atomicAdd(A.flags, bad);
 
   /* per-CTA statistics, fixed order */
-  const int stat_len = P.obs_total + 1 + P.nd + 2 * P.pa_len_() + 1;
+  const int stat_len = P.obs_total + 1 + P.nd + 2 * pa_len + 1;
   double *out = A.cta_stats + (size_t)blockIdx.x * stat_len;
-  for (int i = tid; i < stat_len; i += THREADS) out[i] = 0.0;
+  for (int i = tid; i < stat_len; i += blockDim.x) out[i] = 0.0;
   __syncthreads();
-  for (int o = 0; o < P.obs_total; ++o) { double t = cta_sum<THREADS>(obs[o], S.sred); if (tid == 0) out[o] = t; }
-  { double t = cta_sum<THREADS>(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
-  for (int i = 0; i <= N; ++i) { double t = cta_sum<THREADS>(visited[i], S.sred); if (tid == 0) out[P.obs_total + 1 + i] = t; }
-  double *prop_o = out + P.obs_total + 1 + P.nd, *acc_o = prop_o + P.pa_len_();
-  for (int v = 0; v < P.nv; ++v) {
-    double t = cta_sum<THREADS>((double)n_prop[v], S.sred); if (tid == 0) prop_o[PA_IDX(P, 1, 0, v)] = t;
-    t = cta_sum<THREADS>((double)n_acc[v], S.sred); if (tid == 0) acc_o[PA_IDX(P, 1, 0, v)] = t;
+  if (P.measure_kind == MCI_MEASURE_DEFAULT) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o)
+      if (o < P.obs_len[0]) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[P.obs_off[0] + o] = t; }
   }
-  { double t = cta_sum<THREADS>((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
-  chain_flush_hist<THREADS>(P, A, S);
+  { double t = cta_sum(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
+#pragma unroll
+  for (int i = 0; i <= N; ++i) { double t = cta_sum(visited[i], S.sred); if (tid == 0) out[P.obs_total + 1 + i] = t; }
+  __syncthreads();
+  double *prop_o = out + P.obs_total + 1 + P.nd, *acc_o = prop_o + pa_len;
+  for (int i = tid; i < pa_len; i += blockDim.x) { prop_o[i] = (double)s_prop[i]; acc_o[i] = (double)s_acc[i]; }
+  { double t = cta_sum((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
+  chain_flush_hist(P, A, S);
 }
 
 /* ------------------------------------------------------------------------------------------ */
 /* MCMC                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
-template <int FID>
-__device__ __forceinline__ double eval_one(const DevProblem &P, const FlatX &X, int idx) {
-  double w[Integrand<FID>::NI];
-  Integrand<FID>::template eval<0>(X, P, w);
-  double r = w[0];
+/* weight of integrand `idx` at the walker's point.  Integrands whose components are independent pay for one. */
+template <int FID, class XA>
+__device__ __forceinline__ double eval_one(const DevProblem &P, const XA &X, int idx) {
+  if constexpr (FID == MCI_F_PRODUCT_4) {
+    const int d = P.dof[0];
+    const double a = P.userdata[idx];
+    double p = 1.0;
+    for (int i = 0; i < d; ++i) p *= (1 + a * (X(0, i + 1) - 0.5));
+    return p;
+  } else {
+    double w[Integrand<FID>::NI];
+    Integrand<FID>::template eval<0>(X, P, w);
+    double r = w[0];
 #pragma unroll
-  for (int i = 1; i < Integrand<FID>::NI; ++i) if (i == idx) r = w[i];
-  return r;
+    for (int i = 1; i < Integrand<FID>::NI; ++i) if (i == idx) r = w[i];
+    return r;
+  }
 }
 
-template <int FID, int THREADS>
-__global__ void __launch_bounds__(THREADS) mcmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
+/* Warp-cooperative create!/remove! of changeIntegrand (updates.jl:14-33).  Moving between integrands of different
+ * dof creates or removes up to maxdof slots; a lane doing that alone serialises ~90 instructions per slot while the
+ * other 31 lanes wait (ncu: 1.0 active threads on those lines, 70 % of the kernel for the 20-D C5 workload).  Because
+ * the stream is counter based, the slots of the proposing lane `src` are instead spread over the 32 lanes: lane j
+ * draws uniform q0 + j of src's stream, maps it, writes src's column of the shared walker rows, and the 1/prob (create)
+ * or prob (remove) factors are multiplied with a shuffle tree.  The product is associated differently from the
+ * reference's left-to-right loop (last-bit differences in the acceptance ratio, inside the envelope of the integrand's
+ * own rounding).  Returns the product on every lane; advances *q past the draws it consumed and leaves in
+ * *b_out the buffered half when the new position is odd. */
+__device__ __forceinline__ double coop_change_dof(const DevProblem &P, const double *maps, const PhiloxKey &K, double *wdata0,
+                                                  int *wgidx0, int T, int src_tid, int curr, int nw, uint32_t c0, uint32_t c1,
+                                                  uint32_t c3, uint32_t *q, double *b_out) {
+  const int lane = threadIdx.x & 31;
+  double prop = 1.0;
+  double *data = wdata0 + src_tid;
+  int *gidx = wgidx0 + src_tid;
+  for (int v = 0; v < P.nv; ++v) {
+    const int cd = P.dof[curr * P.nv + v], nd_ = P.dof[nw * P.nv + v];
+    if (cd == nd_) continue;
+    const int nl = P.top_nleaf[v];
+    const int lo = cd < nd_ ? cd : nd_;
+    const int n = (cd < nd_ ? nd_ - cd : cd - nd_) * nl; /* items in the reference's order: slot outer, leaf inner */
+    for (int base = 0; base < n; base += 32) {
+      const int item = base + lane;
+      double term = 1.0, other = 0.0;
+      if (item < n) {
+        const int pos = lo + 1 + item / nl;
+        const DevLeaf &L = P.leaf[P.top_first[v] + item % nl];
+        const int f = frow(L, pos) * T;
+        if (cd < nd_) { /* create! */
+          const double u = stream_uniform(c0, c1, c3, *q + (uint32_t)item, K, &other);
+          if (L.kind == MCI_LEAF_CONTINUOUS) {
+            int iy;
+            double dx;
+            data[f] = map_continuous(reinterpret_cast<const double2 *>(maps + L.smem_off), L.nbins, L.nbins_d, u, iy, dx);
+            gidx[f] = iy;
+            term = __dmul_rn(L.nbins_d, dx);
+          } else {
+            const double *dist = maps + L.smem_off;
+            const int g = locate_clamped(dist + L.nbins, L.nbins, u);
+            data[f] = (double)(L.lower_i + g);
+            gidx[f] = g;
+            term = __ddiv_rn(1.0, dist[g]);
+          }
+        } else { /* remove! */
+          if (L.kind == MCI_LEAF_CONTINUOUS) {
+            const double2 g = reinterpret_cast<const double2 *>(maps + L.smem_off)[gidx[f]];
+            term = __ddiv_rn(1.0, __dmul_rn(g.y, L.nbins_d));
+          } else {
+            term = (maps + L.smem_off)[gidx[f]];
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) term *= __shfl_xor_sync(0xffffffffu, term, o);
+      prop *= term;
+      if (cd < nd_) {
+        const int cnt = n - base < 32 ? n - base : 32;
+        /* the lane that drew the last uniform of this batch holds the other half of that Philox call */
+        const double ob = __shfl_sync(0xffffffffu, other, cnt - 1);
+        *q += (uint32_t)cnt;
+        if (*q & 1u) *b_out = ob;
+      }
+    }
+  }
+  __syncwarp();
+  return prop;
+}
+
+template <int FID>
+__global__ void __launch_bounds__(1024, 1) mcmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
+  constexpr int NI = Integrand<FID>::NI;
   extern __shared__ __align__(16) double smem[];
-  ChainSmem S = chain_setup<THREADS>(P, A, smem);
-  /* propose/accept counters of the CTA: [2][pa_len] u32 in shared memory after the reduction scratch */
-  unsigned int *s_prop = reinterpret_cast<unsigned int *>(S.sred + THREADS / 32);
   const int pa_len = P.pa_len_();
-  unsigned int *s_acc = s_prop + pa_len;
+  Walker<false> W;
+  /* propose/accept counters of the CTA: [2][pa_len] u32 in shared memory (native ATOMS.ADD) */
+  ChainSmem S = chain_setup<false>(P, A, smem, 2 * pa_len, W);
+  unsigned int *s_prop = S.scount, *s_acc = S.scount + pa_len;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * pa_len; i += THREADS) s_prop[i] = 0u;
-  __syncthreads();
   const int lb = blockIdx.x / A.ctas_per_block;
   const int cb = blockIdx.x - lb * A.ctas_per_block;
   const uint32_t block = (uint32_t)(A.rank + lb * A.world);
-  const int walker = cb * THREADS + tid;
+  const int walker = cb * blockDim.x + tid;
   const bool active = walker < A.walkers_per_block;
-  const int N = P.ni;
+  constexpr int N = NI;
   const int hmode = A.hist_mode;
   const double TINY = 4.9406564584124654e-324 * 1e50;
   const double EPS0 = 4.9406564584124654e-324;
@@ -443,14 +571,17 @@ __global__ void __launch_bounds__(THREADS) mcmc_kernel(const __grid_constant__ D
   philox_expand_key(P.seed, A.iter, K);
   ChainCtx C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
-  Walker W;
-  FlatX X{W.data, &P};
-  double rw[MAX_ND];
+  ChainX X{W.data, &P, W.T};
+  double rw[NI + 1];
+#pragma unroll
   for (int i = 0; i <= N; ++i) rw[i] = A.reweight[i];
 
-  double obs[MCI_MAX_OBS];
-  for (int o = 0; o < P.obs_total; ++o) obs[o] = 0.0;
-  unsigned int visited[MAX_ND];
+  constexpr int NOBS = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+  double obs[NOBS];
+#pragma unroll
+  for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
+  unsigned int visited[NI + 1];
+#pragma unroll
   for (int i = 0; i <= N; ++i) visited[i] = 0u;
   double normalization = 0.0;
   unsigned long long neval = 0, bad = 0;
@@ -472,91 +603,123 @@ __global__ void __launch_bounds__(THREADS) mcmc_kernel(const __grid_constant__ D
   const uint64_t total = A.steps + nburnin;
 
   for (uint64_t it = 1; it <= total; ++it) {
+    /* ---- propose (divergent, cheap) ---- */
+    int kind = 0;   /* 0 none, 1 changeIntegrand, 2 changeVariable, 3 swapVariable (= first index of propose/accept + 1) */
+    int tgt = curr; /* integrand to evaluate */
+    int vi = 0, p1 = 0, p2 = 0;
+    double prop = 1.0;
+    bool ci = false, ci_dof = false; /* changeIntegrand proposed (to tgt); it changes some dof */
     if (active) {
-      visited[curr] += 1u;
+#pragma unroll
+      for (int i = 0; i <= N; ++i) visited[i] += (i == curr);
       const int u = C.rng.randint(K, nupdates);
       if (u == 1) {
-        /* changeIntegrand: updates.jl:1-70 */
+        /* changeIntegrand: updates.jl:1-70.  The create!/remove! of the dof difference is done by the whole warp below */
         const int nnb = P.nb_ptr[curr + 1] - P.nb_ptr[curr];
         const int nw = P.nb_idx[P.nb_ptr[curr] + C.rng.randint(K, nnb) - 1];
         if (nw != curr) {
-          double prop = __ddiv_rn((double)nnb, (double)(P.nb_ptr[nw + 1] - P.nb_ptr[nw]));
-          for (int v = 0; v < P.nv; ++v) {
-            const int cd = P.dof[curr * P.nv + v], nd_ = P.dof[nw * P.nv + v];
-            if (cd < nd_) { for (int pos = cd + 1; pos <= nd_; ++pos) prop = __dmul_rn(prop, var_create(C, W, v, pos)); }
-            else if (cd > nd_) { for (int pos = nd_ + 1; pos <= cd; ++pos) prop = __dmul_rn(prop, var_remove(C, W, v, pos)); }
-          }
-          if (prop > EPS0) {
-            const double nwgt = (nw == N) ? 0.0 : eval_one<FID>(P, X, nw);
-            neval++;
-            if (!isfinite(nwgt)) bad++;
-            const double nprob = (nw == N) ? rw[nw] : __dmul_rn(fabs(nwgt), rw[nw]);
-            const double R = __ddiv_rn(__dmul_rn(prop, nprob), prob_cur);
-            atomicAdd(&s_prop[PA_IDX(P, 0, curr, nw)], 1u);
-            if (C.rng.rand(K) < R) {
-              atomicAdd(&s_acc[PA_IDX(P, 0, curr, nw)], 1u);
-              curr = nw; weight = nwgt; prob_cur = nprob;
+          prop = __ddiv_rn((double)nnb, (double)(P.nb_ptr[nw + 1] - P.nb_ptr[nw]));
+          ci = true; tgt = nw;
+          if (A.coop_ci) { /* many slots to create!/remove!: the whole warp does it below */
+            for (int v = 0; v < P.nv; ++v) ci_dof = ci_dof || (P.dof[curr * P.nv + v] != P.dof[nw * P.nv + v]);
+          } else {
+            for (int v = 0; v < P.nv; ++v) {
+              const int cd = P.dof[curr * P.nv + v], nd_ = P.dof[nw * P.nv + v];
+              if (cd < nd_) { for (int pos = cd + 1; pos <= nd_; ++pos) prop = __dmul_rn(prop, var_create(C, W, v, pos)); }
+              else if (cd > nd_) { for (int pos = nd_ + 1; pos <= cd; ++pos) prop = __dmul_rn(prop, var_remove(C, W, v, pos)); }
             }
           }
         }
       } else if (curr != N) {
         if (u == 2) {
           /* swapVariable: updates.jl:111-147 */
-          const int vi = C.rng.randint(K, P.nv) - 1;
+          vi = C.rng.randint(K, P.nv) - 1;
           const int cd = P.dof[curr * P.nv + vi];
           if (cd > 0) {
-            const int p1 = C.rng.randint(K, cd);
-            const int p2 = C.rng.randint(K, cd);
-            if (p1 != p2) {
-              var_swap(C, W, vi, p1, p2);
-              const double nwgt = eval_one<FID>(P, X, curr);
-              neval++;
-              if (!isfinite(nwgt)) bad++;
-              const double nprob = __dmul_rn(fabs(nwgt), rw[curr]);
-              const double R = __ddiv_rn(__dmul_rn(1.0, nprob), prob_cur);
-              atomicAdd(&s_prop[PA_IDX(P, 2, curr, vi)], 1u);
-              if (C.rng.rand(K) < R) { atomicAdd(&s_acc[PA_IDX(P, 2, curr, vi)], 1u); weight = nwgt; prob_cur = nprob; }
-              else var_swap(C, W, vi, p1, p2);
-            }
+            p1 = C.rng.randint(K, cd);
+            p2 = C.rng.randint(K, cd);
+            if (p1 != p2) { var_swap(P, W, vi, p1, p2); kind = 3; }
           }
         } else {
           /* changeVariable: updates.jl:72-109 */
-          const int vi = C.rng.randint(K, P.nv) - 1;
+          vi = C.rng.randint(K, P.nv) - 1;
           const int cd = P.dof[curr * P.nv + vi];
           if (!P.top_skip[vi] && cd > 0) {
-            const int pos = C.rng.randint(K, cd);
-            const double prop = var_shift(C, W, vi, pos);
-            if (prop > EPS0) {
-              const double nwgt = eval_one<FID>(P, X, curr);
-              neval++;
-              if (!isfinite(nwgt)) bad++;
-              const double nprob = __dmul_rn(fabs(nwgt), rw[curr]);
-              const double R = __ddiv_rn(__dmul_rn(prop, nprob), prob_cur);
-              atomicAdd(&s_prop[PA_IDX(P, 1, curr, vi)], 1u);
-              if (C.rng.rand(K) < R) { atomicAdd(&s_acc[PA_IDX(P, 1, curr, vi)], 1u); weight = nwgt; prob_cur = nprob; }
-              else var_shift_rollback(C, W, vi, pos);
-            }
+            p1 = C.rng.randint(K, cd);
+            prop = var_shift(C, W, vi, p1);
+            if (prop > EPS0) kind = 2;
           }
         }
       }
     }
+    /* ---- changeIntegrand: create!/remove! the dof difference, one proposing lane at a time, 32 lanes per lane ---- */
+    __syncwarp();
+    {
+      unsigned need = A.coop_ci ? __ballot_sync(0xffffffffu, ci_dof) : 0u;
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int s_curr = __shfl_sync(0xffffffffu, curr, src), s_nw = __shfl_sync(0xffffffffu, tgt, src);
+        const uint32_t s_c0 = __shfl_sync(0xffffffffu, C.rng.c0, src), s_c1 = __shfl_sync(0xffffffffu, C.rng.c1, src);
+        uint32_t s_q = __shfl_sync(0xffffffffu, C.rng.q, src);
+        double s_b = 0.0;
+        const double f = coop_change_dof(P, S.maps, K, W.data - tid, W.gidx - tid, W.T, (tid & ~31) + src, s_curr, s_nw, s_c0, s_c1,
+                                         C.rng.c3, &s_q, &s_b);
+        if ((tid & 31) == src) {
+          prop = __dmul_rn(prop, f);
+          if (s_q != C.rng.q) { C.rng.q = s_q; if (s_q & 1u) C.rng.b = s_b; }
+        }
+      }
+      if (ci) { if (prop > EPS0) kind = 1; else tgt = curr; }
+    }
+    /* ---- evaluate (convergent): one integrand call site for all update types.  Independent thread scheduling does
+     * not reconverge the lanes by itself after the divergent proposal code: without the barrier the warp drifts apart
+     * for good (ncu: 4 active threads per instruction) ---- */
+    __syncwarp();
+    double nwgt = 0.0;
+    if (kind != 0 && tgt != N) nwgt = eval_one<FID>(P, X, tgt);
+    __syncwarp();
+    /* ---- accept / rollback (divergent, cheap) ---- */
+    if (kind != 0) {
+      neval++;
+      if (!isfinite(nwgt)) bad++;
+      const double nprob = (tgt == N) ? rw[N] : __dmul_rn(fabs(nwgt), rw[tgt]);
+      const double R = __ddiv_rn(__dmul_rn(prop, nprob), prob_cur);
+      const int j = kind == 1 ? tgt : vi;
+      const int pa = PA_IDX(P, kind - 1, curr, j);
+      atomicAdd(&s_prop[pa], 1u);
+      if (C.rng.rand(K) < R) {
+        atomicAdd(&s_acc[pa], 1u);
+        curr = tgt; weight = nwgt; prob_cur = nprob;
+      } else if (kind == 2) {
+        var_shift_rollback(P, W, vi, p1);
+      } else if (kind == 3) {
+        var_swap(P, W, vi, p1, p2);
+      }
+    }
     __syncwarp();
     /* measurement: montecarlo.jl:145-170 */
-    if ((it % (uint64_t)P.measurefreq) == 0 && it >= nburnin) {
-      if (hmode != HIST_NONE) {
-        /* every lane walks the slots of ITS integrand; lanes on shorter dofs idle (warp-collective scatter) */
-        for (int v = 0; v < P.nv; ++v)
-          for (int pos = 1; pos <= P.maxdof[v]; ++pos) {
-            const bool on = active && curr != N && pos <= P.dof[curr * P.nv + v];
-            var_accumulate(P, W, hmode, S.myhist, v, pos, 1.0, on);
+    if (active && (P.measurefreq == 1 || (it % (uint64_t)P.measurefreq) == 0) && it >= nburnin) {
+      if (curr == N) {
+        normalization += __ddiv_rn(1.0, rw[N]);
+      } else {
+        if (hmode != HIST_NONE)
+          for (int v = 0; v < P.nv; ++v) {
+            const int cd = P.dof[curr * P.nv + v];
+            for (int pos = 1; pos <= cd; ++pos)
+              for (int k = 0; k < P.top_nleaf[v]; ++k) {
+                const DevLeaf &L = P.leaf[P.top_first[v] + k];
+                if (L.adapt) chain_hist_add(hmode, S.hist_saddr + 8u * (uint32_t)L.hist_off, S.ghist + L.hist_off, W.gidx[frow(L, pos) * W.T], 1.0);
+              }
           }
-      }
-      if (active) {
-        if (curr == N) normalization += __ddiv_rn(1.0, rw[N]);
-        else {
-          const double relw = __ddiv_rn(weight, prob_cur);
-          if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[P.obs_off[curr]] += relw;
-          else obs[P.obs_off[0] + W.gidx[P.leaf[P.nleaf - 1].base]] += relw;
+        const double relw = __ddiv_rn(weight, prob_cur);
+        if (P.measure_kind == MCI_MEASURE_DEFAULT) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) obs[i] += (i == curr) ? relw : 0.0;
+        } else {
+          const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
+#pragma unroll
+          for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
         }
       }
     }
@@ -565,15 +728,24 @@ __global__ void __launch_bounds__(THREADS) mcmc_kernel(const __grid_constant__ D
 
   const int stat_len = P.obs_total + 1 + P.nd + 2 * pa_len + 1;
   double *out = A.cta_stats + (size_t)blockIdx.x * stat_len;
+  for (int i = tid; i < stat_len; i += blockDim.x) out[i] = 0.0;
   __syncthreads();
-  for (int o = 0; o < P.obs_total; ++o) { double t = cta_sum<THREADS>(obs[o], S.sred); if (tid == 0) out[o] = t; }
-  { double t = cta_sum<THREADS>(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
-  for (int i = 0; i <= N; ++i) { double t = cta_sum<THREADS>((double)visited[i], S.sred); if (tid == 0) out[P.obs_total + 1 + i] = t; }
+  if (P.measure_kind == MCI_MEASURE_DEFAULT) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o)
+      if (o < P.obs_len[0]) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[P.obs_off[0] + o] = t; }
+  }
+  { double t = cta_sum(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
+#pragma unroll
+  for (int i = 0; i <= N; ++i) { double t = cta_sum((double)visited[i], S.sred); if (tid == 0) out[P.obs_total + 1 + i] = t; }
   __syncthreads();
   double *prop_o = out + P.obs_total + 1 + P.nd, *acc_o = prop_o + pa_len;
-  for (int i = tid; i < pa_len; i += THREADS) { prop_o[i] = (double)s_prop[i]; acc_o[i] = (double)s_acc[i]; }
-  { double t = cta_sum<THREADS>((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
-  chain_flush_hist<THREADS>(P, A, S);
+  for (int i = tid; i < pa_len; i += blockDim.x) { prop_o[i] = (double)s_prop[i]; acc_o[i] = (double)s_acc[i]; }
+  { double t = cta_sum((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
+  chain_flush_hist(P, A, S);
 }
 
 }  // namespace mci

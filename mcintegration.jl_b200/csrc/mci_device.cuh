@@ -114,20 +114,22 @@ __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
   return __dsub_rn(__hiloint2double((int)h, (int)l), 1.0);
 }
 
-/* sequential stream for the Markov-chain solvers: rand(config.rng) */
+/* sequential stream for the Markov-chain solvers: rand(config.rng).  Uniform number q of the stream is half (q & 1)
+ * of Philox call (q >> 1) with counter (idx_lo, idx_hi, q >> 1, block): the position is explicit, so other lanes of
+ * the warp can compute draws of this stream on the owner's behalf (cooperative create!, mci_chain.cuh). */
 struct Rng {
-  uint32_t c0, c1, c2, c3;
-  uint32_t b2, b3;
-  int have;
+  uint32_t c0, c1, c3;
+  uint32_t q;  /* uniforms consumed so far */
+  double b;    /* second half of call q >> 1, valid while q is odd */
   __device__ __forceinline__ void init(uint64_t idx, uint32_t block) {
-    c0 = (uint32_t)idx; c1 = (uint32_t)(idx >> 32); c2 = 0; c3 = block; have = 0;
+    c0 = (uint32_t)idx; c1 = (uint32_t)(idx >> 32); c3 = block; q = 0; b = 0.0;
   }
   __device__ __forceinline__ double rand(const PhiloxKey &K) {
-    if (have) { have = 0; return u52(b2, b3); }
-    uint32_t o0, o1;
-    philox4x32_10(c0, c1, c2, c3, K, o0, o1, b2, b3);
-    c2 += 1;
-    have = 1;
+    if (q & 1u) { q++; return b; }
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(c0, c1, q >> 1, c3, K, o0, o1, o2, o3);
+    b = u52(o2, o3);
+    q++;
     return u52(o0, o1);
   }
   /* rand(rng, 1:n) -> 1 + floor(u*n) */
@@ -136,6 +138,16 @@ struct Rng {
     return k > n ? n : k;
   }
 };
+
+/* uniform number `q` of the stream (c0, c1, ., c3); *other = the other half of the same Philox call */
+__device__ __forceinline__ double stream_uniform(uint32_t c0, uint32_t c1, uint32_t c3, uint32_t q, const PhiloxKey &K,
+                                                  double *other) {
+  uint32_t o0, o1, o2, o3;
+  philox4x32_10(c0, c1, q >> 1, c3, K, o0, o1, o2, o3);
+  const double u0 = u52(o0, o1), u1 = u52(o2, o3);
+  *other = (q & 1u) ? u0 : u1;
+  return (q & 1u) ? u1 : u0;
+}
 
 /* ---------------------------------------------------------------------------------------- */
 /* maps                                                                                      */

@@ -8,7 +8,6 @@ namespace mci {
 constexpr int POOL_THREADS = 256;
 constexpr int POOL_THREADS_STRIPED = 1024; /* HIST_SMEM_STRIPED: one CTA per SM owns the 16-way striped histogram */
 constexpr int GENERIC_THREADS = 256;
-constexpr int CHAIN_THREADS = 128;
 
 /* vegas, single Continuous pool: returns NULL when (fid, d) has no pool instantiation for hist_mode
  * (HIST_NONE / HIST_SMEM_ATOMIC / HIST_SMEM_STRIPED / HIST_GLOBAL_RED).  exact: every integrand uses exactly d slots. */
