@@ -25,13 +25,20 @@
 #ifndef MCIB200_H
 #define MCIB200_H
 
+#ifdef __CUDACC_RTC__ /* compiled by NVRTC for a JIT-specialised kernel: no host headers there */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MCI_ABI_VERSION 1
+#define MCI_ABI_VERSION 2
 
 /* ---- limits of the POD problem description ------------------------------ */
 #define MCI_MAX_TOPVAR 16    /* top-level variables (`config.var` tuple, configuration.jl:40) */
@@ -81,7 +88,15 @@ enum mci_integrand_id {
   MCI_F_LATTICE_COMP = 12,  /* same with CompositeVar(X,Y,Z), dof=1           test/montecarlo.jl:149-164  */
   MCI_F_HYPERSPHERE3 = 13,  /* 3 nested unit balls, dof=[[2],[3],[4]] test/montecarlo.jl:200-216         */
   MCI_F_POLY3 = 14,         /* (x, x^2, x^3), dof=[[1],[1],[1]]       test/thread.jl                       */
-  MCI_F_X2_PLUS_Y2 = 15     /* x1^2+x2^2, pool dof=[[2]]              main.jl:64, vegas/montecarlo.jl:69   */
+  MCI_F_X2_PLUS_Y2 = 15,    /* x1^2+x2^2, pool dof=[[2]]              main.jl:64, vegas/montecarlo.jl:69   */
+  MCI_F_USER = 100          /* the caller's own integrand: CUDA C++ source in mci_problem_t.user_source, compiled with
+                               NVRTC at mci_create into a kernel specialised to the problem — the equivalent of the
+                               reference taking any closure f(x, c) (main.jl:25-33).  The source defines
+                                 template <class XA> __device__ void mci_user_integrand(const XA &X,
+                                                                   const double *userdata, double *w);
+                               X(leaf, pos): value of pool slot pos (1-based, the reference's x[pos]) of leaf variable
+                               `leaf` (0-based: top-level order, then leaf order inside a CompositeVar);
+                               w[0 .. n_integrand-1] receives the integrand values.                                */
 };
 
 /* `measure` kwarg (main.jl:35-37, 83).  Default = obs[i] += relw[i]. */
@@ -135,8 +150,14 @@ typedef struct mci_problem_t {
   double thermal_ratio;    /* mcmc burn-in (mcmc/montecarlo.jl:77,133)                   */
   int32_t device;          /* CUDA device ordinal                                        */
   int32_t hist_policy;     /* 0 = auto; see MCI_HIST_* (performance knob, not semantics) */
+  int32_t jit;             /* MCI_JIT_*: compile the kernel for this problem with NVRTC, its layout baked in as
+                              compile-time tables.  AUTO: when one iteration has >= 2^24 samples (and NVRTC loads),
+                              else the ahead-of-time kernel; MCI_F_USER always jits                                */
+  int32_t reserved_;
+  const char *user_source; /* MCI_F_USER: NUL-terminated CUDA C++ source, copied by mci_create; else NULL         */
 } mci_problem_t;
 
+enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };
 enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4 };
 
 /*
@@ -155,6 +176,8 @@ typedef struct mci_iteration_out_t {
 } mci_iteration_out_t;
 
 typedef struct mci_handle_t mci_handle_t;
+
+#ifndef __CUDACC_RTC__ /* host entry points: not visible to the device-only JIT compilation */
 
 /* library / ABI version (MCI_ABI_VERSION) */
 int mci_abi_version(void);
@@ -258,6 +281,13 @@ int mci_stats_sync_host(mci_handle_t *h);
 int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t first, int32_t count, double *x,
                       int32_t *bins, double *jac, double *weights);
 
+/*
+ * Compile-only check of the JIT path (no GPU needed): builds the device description of `problem`, generates the
+ * specialised program for its solver and runs NVRTC on it.  Returns MCI_OK, or MCI_ERR_UNSUPPORTED with the compiler
+ * log in `log` (NUL-terminated, at most log_cap bytes).  Lets a host validate user_source before it has a device.
+ */
+int mci_jit_check(const mci_problem_t *problem, char *log, int32_t log_cap);
+
 /* measurement helpers ---------------------------------------------------- */
 /* number of kernel launches issued by this handle so far */
 int mci_launch_count(const mci_handle_t *h, uint64_t *n);
@@ -279,6 +309,8 @@ int mci_launch_info(const mci_handle_t *h, int32_t *grid, int32_t *threads, int6
                     int32_t *tiles_per_block, int32_t *samples_per_thread);
 /* name of the fill kernel variant chosen for this handle (static string) */
 const char *mci_kernel_name(const mci_handle_t *h);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MAX_TOPVAR = 16
 MAX_LEAF = 32
@@ -29,6 +29,7 @@ ERR_MCMC_START = -7
 SOLVER_VEGAS, SOLVER_VEGASMC, SOLVER_MCMC = 0, 1, 2
 LEAF_CONTINUOUS, LEAF_DISCRETE = 0, 1
 MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE = 0, 1
+JIT_AUTO, JIT_ON, JIT_OFF = 0, 1, 2
 HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
 
 # enum mci_integrand_id
@@ -47,6 +48,7 @@ F_LATTICE_COMP = 12
 F_HYPERSPHERE3 = 13
 F_POLY3 = 14
 F_X2_PLUS_Y2 = 15
+F_USER = 100
 
 
 class Leaf(C.Structure):
@@ -86,6 +88,9 @@ class Problem(C.Structure):
         ("thermal_ratio", C.c_double),
         ("device", C.c_int32),
         ("hist_policy", C.c_int32),
+        ("jit", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("user_source", C.c_char_p),
     ]
 
 
@@ -130,6 +135,7 @@ EXPORTS = [
     "mci_timer_start",
     "mci_timer_stop",
     "mci_fill_history",
+    "mci_jit_check",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -185,6 +191,7 @@ def declare(lib, prefix="mci_"):
         f("timer_stop", C.c_int, [H, C.POINTER(C.c_float)])
         f("stats_sync_host", C.c_int, [H])
         f("fill_history", C.c_int, [H, C.POINTER(C.c_float), C.c_int32, ip])
+        f("jit_check", C.c_int, [C.POINTER(Problem), C.c_char_p, C.c_int32])
         f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
     return lib
 

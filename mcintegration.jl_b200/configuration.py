@@ -147,6 +147,8 @@ class ProblemSpec:
     thermal_ratio: float = 0.1
     device: int = 0
     hist_policy: int = 0
+    jit: int = 0
+    user_source: str | None = None
 
     def to_ctypes(self):
         keep = []
@@ -188,13 +190,18 @@ class ProblemSpec:
         p.thermal_ratio = self.thermal_ratio
         p.device = self.device
         p.hist_policy = self.hist_policy
+        p.jit = self.jit
+        if self.user_source is not None:
+            src = self.user_source.encode()
+            keep.append(src)
+            p.user_source = src
         return p, keep
 
 
 def problem_from_config(config: Configuration, integrand, *, solver: int, measure_kind: int, n_block: int,
                         neval_per_block: int, measurefreq: int = 1, walkers_per_block: int = 1,
                         thermal_ratio: float = 0.1, device: int = 0, hist_policy: int = 0,
-                        default_neighbor: bool = False) -> ProblemSpec:
+                        default_neighbor: bool = False, jit: int = 0) -> ProblemSpec:
     leaves = []
     for L in config.leaves():
         if isinstance(L, Continuous):
@@ -210,7 +217,8 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
         leaves=leaves, dof=[list(d) for d in config.dof[:-1]], obs_len=config.obs_len(),
         neighbor=None if default_neighbor else config.neighbor, userdata=list(integrand.userdata),
         n_block=n_block, neval_per_block=neval_per_block, seed=config.seed, measurefreq=measurefreq,
-        walkers_per_block=walkers_per_block, thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy)
+        walkers_per_block=walkers_per_block, thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit,
+        user_source=getattr(integrand, "source", None))
 
 
 def maps_from_config(config: Configuration):

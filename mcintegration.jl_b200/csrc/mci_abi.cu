@@ -17,10 +17,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "mci_aux.cuh"
 #include "mci_chain.cuh"
+#include "mci_jit.h"
 #include "mci_kernels.h"
 #include "mci_vegas.cuh"
 
@@ -102,6 +104,12 @@ struct mci_handle_t {
   uint64_t steps = 0;
   bool maps_dirty = true, have_iteration = false, async_mode = false;
   nccl_comm_t comm = nullptr;
+  /* JIT specialisation (mci_jit.cu) */
+  bool use_jit = false;
+  std::string user_source, kernel_name_jit;
+  const void *jit_lib = nullptr, *trace_kernel = nullptr;
+  bool jit_failed = false;
+  int jit_mode = 0, chain_maxt = 1024;
   uint64_t launches = 0;
   float fill_ms = 0.f, iter_ms = 0.f;
   char err[256];
@@ -142,6 +150,7 @@ bool fid_info(int fid, FidInfo &I) {
     case MCI_F_HYPERSPHERE3: I = {3, 1, 4}; return true;
     case MCI_F_POLY3: I = {3, 1, 1}; return true;
     case MCI_F_X2_PLUS_Y2: I = {1, 1, 2}; return true;
+    case MCI_F_USER: I = {0, 1, 0}; return true; /* any number of values, any layout: the source decides */
   }
   return false;
 }
@@ -157,6 +166,68 @@ int dev_alloc(mci_handle_t *h, T **p, size_t n) {
   CU(h, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
   CU(h, cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
   return MCI_OK;
+}
+
+/* kernel of one family for this handle: the ahead-of-time instantiation, or — user integrand / jit requested — the
+ * NVRTC build of the same template specialised to the problem (mci_jit.cu).  kind: 0 pool, 1 generic, 2 vegasmc, 3 mcmc */
+const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, bool exact) {
+  const DevProblem &P = h->dp;
+  if (!h->use_jit) {
+    switch (kind) {
+      case 0: return lookup_vegas_pool(P.fid, P.maxdof[0], exact, mode, &h->kernel_name);
+      case 1: return lookup_vegas_generic(P.fid, &h->kernel_name);
+      case 2: return lookup_vegasmc(P.fid, &h->kernel_name);
+      default: return lookup_mcmc(P.fid, &h->kernel_name);
+    }
+  }
+  if (kind == 0 && h->jit_mode == MCI_JIT_AUTO && P.fid != MCI_F_USER) {
+    /* an exact ahead-of-time pool instantiation is already what the JIT would build */
+    const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], exact, mode, &h->kernel_name);
+    if (k && strstr(h->kernel_name, ",exact>")) return k;
+  }
+  char name[160];
+  switch (kind) {
+    case 0:
+      if (mode == HIST_SMEM_STRIPED && P.maxdof[0] > 20) return nullptr; /* 1024 threads x 64 registers */
+      snprintf(name, sizeof name, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0], mode, threads, exact ? "true" : "false");
+      break;
+    case 1: snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, GENERIC_THREADS); break;
+    case 2: snprintf(name, sizeof name, "mci::vegasmc_kernel<%d>", P.fid); break;
+    default: snprintf(name, sizeof name, "mci::mcmc_kernel<%d>", P.fid); break;
+  }
+  std::vector<std::string> exprs{name};
+  if (kind <= 1) { char t[64]; snprintf(t, sizeof t, "mci::vegas_trace_kernel<%d>", P.fid); exprs.push_back(t); }
+  std::vector<const void *> ks;
+  std::string err;
+  int rc = jit_compile(P, h->user_source.c_str(), exprs, ks, err);
+  h->chain_maxt = 1024;
+  if (rc == 0 && kind >= 2) { /* specialised chain code that spills under the 64-register cap: 512 threads x 128 registers */
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, ks[0]) == cudaSuccess && fa.localSizeBytes > 192) {
+      std::vector<const void *> ks2;
+      std::string err2;
+      if (jit_compile(P, h->user_source.c_str(), exprs, ks2, err2, "#define MCI_CHAIN_MAXT 512\n") == 0) {
+        jit_unload(ks.back());
+        ks = ks2;
+        h->chain_maxt = 512;
+      }
+    }
+  }
+  if (rc != 0) {
+    if (h->jit_mode == MCI_JIT_AUTO && P.fid != MCI_F_USER) { /* auto: the ahead-of-time kernel serves as well */
+      h->use_jit = false;
+      return resolve_kernel(h, kind, mode, threads, exact);
+    }
+    snprintf(h->err, sizeof h->err, "%.*s", (int)sizeof h->err - 1, err.c_str());
+    h->jit_failed = true;
+    return nullptr;
+  }
+  if (h->jit_lib) jit_unload(h->jit_lib);
+  h->jit_lib = ks.back();
+  h->trace_kernel = kind <= 1 ? ks[1] : nullptr;
+  h->kernel_name_jit = std::string(name) + " [jit]";
+  h->kernel_name = h->kernel_name_jit.c_str();
+  return ks[0];
 }
 
 /* choose kernel, histogram policy, shared memory and grid for the current partition */
@@ -207,11 +278,13 @@ int plan(mci_handle_t *h) {
         hs = (size_t)STRIPE * hist_bytes; h->maps_in_smem = 1;
       }
       if (h->maps_in_smem) {
-        const void *k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, mode, &h->kernel_name);
+        const void *k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
+        if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
         if (!k && mode == HIST_SMEM_STRIPED) { /* no striped instantiation for this many slots: one shared copy */
           threads = POOL_THREADS; nwarp = threads / 32; red = (size_t)nwarp * (P.ni + 1) * 8;
           mode = pick_hist(nwarp, red, false); hs = hist_smem(mode, nwarp);
-          if (h->maps_in_smem) k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, mode, &h->kernel_name);
+          if (h->maps_in_smem) k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
+          if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
         }
         if (k) {
           h->kernel = k; h->is_pool = true; h->threads = threads; h->hist_mode = mode;
@@ -223,7 +296,8 @@ int plan(mci_handle_t *h) {
       const int nwarp = GENERIC_THREADS / 32;
       const size_t red = (size_t)nwarp * (P.obs_total + 1) * 8;
       int mode = pick_hist(nwarp, red, true);
-      h->kernel = lookup_vegas_generic(P.fid, &h->kernel_name);
+      h->kernel = resolve_kernel(h, 1, mode, GENERIC_THREADS, false);
+      if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
       if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no vegas kernel", P.fid);
       h->threads = GENERIC_THREADS; h->hist_mode = mode;
       h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
@@ -231,7 +305,8 @@ int plan(mci_handle_t *h) {
   } else {
     /* chain solvers: walker state in shared memory rows [row][thread]; pick the CTA size that keeps most walkers
      * resident per SM (the maps and the histogram are per CTA, so larger CTAs amortise them) */
-    h->kernel = p.solver == MCI_SOLVER_VEGASMC ? lookup_vegasmc(P.fid, &h->kernel_name) : lookup_mcmc(P.fid, &h->kernel_name);
+    h->kernel = resolve_kernel(h, p.solver == MCI_SOLVER_VEGASMC ? 2 : 3, 0, 0, false);
+    if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
     if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no chain kernel", P.fid);
     int max_nl = 1;
     for (int v = 0; v < P.nv; ++v) max_nl = std::max(max_nl, P.top_nleaf[v]);
@@ -251,7 +326,7 @@ int plan(mci_handle_t *h) {
     const int W = std::max(1, p.walkers_per_block);
     CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     int best_score = -1;
-    for (int T = 1024; T >= 128; T >>= 1) {
+    for (int T = h->use_jit ? h->chain_maxt : 1024; T >= 128; T >>= 1) {
       if (T > 128 && T / 2 >= W) continue; /* more than half of the CTA would idle */
       const int nwarp = T / 32;
       const size_t extra = fixed + row_bytes * T;
@@ -334,6 +409,7 @@ void mci_destroy(mci_handle_t *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  if (h->jit_lib) jit_unload(h->jit_lib);
   cudaFree(h->d_grids); cudaFree(h->d_dist); cudaFree(h->d_accum); cudaFree(h->d_reweight); cudaFree(h->d_goal);
   cudaFree(h->d_alpha); cudaFree(h->d_gmaps); cudaFree(h->d_leaf_grid_off); cudaFree(h->d_leaf_dist_off);
   cudaFree(h->d_leaf_acc_off); cudaFree(h->d_tile_obs); cudaFree(h->d_tile_cnt); cudaFree(h->d_cta_hist);
@@ -353,9 +429,10 @@ void mci_destroy(mci_handle_t *h) {
   delete h;
 }
 
-int mci_create(const mci_problem_t *p, mci_handle_t **out) {
-  if (!p || !out) return fail(nullptr, MCI_ERR_INVALID, "null argument");
-  *out = nullptr;
+}  // extern "C"
+
+/* validation of the POD problem + the device-side description (DevProblem, packed layout); no device is touched */
+static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
   if (p->n_topvar < 1 || p->n_topvar > MCI_MAX_TOPVAR || p->n_leaf < 1 || p->n_leaf > MCI_MAX_LEAF ||
       p->n_integrand < 1 || p->n_integrand > MCI_MAX_INTEGRAND || p->n_block < 1 || p->measurefreq < 1 ||
       p->neval_per_block < 1)
@@ -363,21 +440,14 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   if (p->solver < MCI_SOLVER_VEGAS || p->solver > MCI_SOLVER_MCMC) return fail(nullptr, MCI_ERR_INVALID, "Solver %d is not supported!", p->solver);
   FidInfo FI;
   if (!fid_info(p->integrand_id, FI)) return fail(nullptr, MCI_ERR_UNSUPPORTED, "unknown integrand id %d", p->integrand_id);
-  if (FI.ni != p->n_integrand)
+  if (p->integrand_id == MCI_F_USER && (!p->user_source || !*p->user_source))
+    return fail(nullptr, MCI_ERR_INVALID, "integrand_id = MCI_F_USER needs user_source (CUDA C++ defining mci_user_integrand)");
+  if (p->integrand_id != MCI_F_USER && FI.ni != p->n_integrand)
     return fail(nullptr, MCI_ERR_INVALID, "integrand %d returns %d values but n_integrand = %d", p->integrand_id, FI.ni, p->n_integrand);
   if (p->n_leaf < FI.nleaf_min) return fail(nullptr, MCI_ERR_INVALID, "integrand %d needs %d leaf variables", p->integrand_id, FI.nleaf_min);
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || p->device < 0 || p->device >= ndev)
-    return fail(nullptr, MCI_ERR_NO_DEVICE, "no CUDA device %d (found %d): libmcib200 has no CPU fallback", p->device, ndev);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
-    return fail(nullptr, MCI_ERR_NO_DEVICE, "device %d is not a Blackwell (sm_100a) GPU", p->device);
-
-  mci_handle_t *h = new mci_handle_t();
   h->err[0] = 0;
   h->p = *p;
   h->device = p->device;
-  h->n_sm = prop.multiProcessorCount;
   DevProblem &P = h->dp;
   memset(&P, 0, sizeof P);
   const int ni = p->n_integrand, nd = ni + 1, nv = p->n_topvar, nleaf = p->n_leaf;
@@ -387,7 +457,7 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   P.thermal_ratio = p->thermal_ratio; P.seed = p->seed;
   int first = 0;
   for (int v = 0; v < nv; ++v) { P.top_nleaf[v] = p->topvar_nleaf[v]; P.top_first[v] = first; first += p->topvar_nleaf[v]; }
-#define BAIL(code, ...) do { int rc_ = fail(nullptr, code, __VA_ARGS__); delete h; return rc_; } while (0)
+#define BAIL(code, ...) return fail(nullptr, code, __VA_ARGS__)
   if (first != nleaf) BAIL(MCI_ERR_INVALID, "sum(topvar_nleaf) != n_leaf");
   for (int i = 0; i < ni; ++i)
     for (int v = 0; v < nv; ++v) {
@@ -444,7 +514,7 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
     P.top_skip[v] = (P.top_nleaf[v] == 1 && P.leaf[P.top_first[v]].kind == MCI_LEAF_DISCRETE && P.leaf[P.top_first[v]].nbins == 1);
   /* the slots the integrand reads must exist */
   {
-    int need0 = FI.slots0 < 0 ? P.dof[0] : FI.slots0;
+    int need0 = P.fid == MCI_F_USER ? 0 : (FI.slots0 < 0 ? P.dof[0] : FI.slots0);
     if (P.maxdof[0] < need0 && FI.nleaf_min == 1) BAIL(MCI_ERR_INVALID, "integrand %d reads %d slots of variable 1 but maxdof = %d", P.fid, need0, P.maxdof[0]);
     if (FI.nleaf_min > 1)
       for (int l = 0; l < FI.nleaf_min; ++l) if (P.maxdof[P.leaf[l].top] < 1) BAIL(MCI_ERR_INVALID, "integrand %d needs one slot of every variable", P.fid);
@@ -493,8 +563,40 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   /* own the pointers of the problem copy */
   h->p.topvar_nleaf = nullptr; h->p.topvar_offset = nullptr; h->p.leaf = nullptr; h->p.dof = nullptr; h->p.obs_len = nullptr;
   h->p.neighbor_ptr = nullptr; h->p.neighbor_idx = nullptr; h->p.userdata = nullptr;
+  if (p->user_source) h->user_source = p->user_source;
+  h->p.user_source = nullptr;
+  /* JIT policy: user source always; MCI_JIT_ON / MCI_JIT_OFF as told; auto = specialise when one iteration is big
+   * enough (>= 2^24 samples) to repay ~1 s of NVRTC, except on the exact ahead-of-time pool kernels, which already are
+   * what the JIT would build */
+  h->jit_mode = p->jit;
+  if (const char *e = getenv("MCIB200_JIT")) h->jit_mode = atoi(e) == 0 ? MCI_JIT_OFF : MCI_JIT_ON;
+  h->use_jit = p->integrand_id == MCI_F_USER || h->jit_mode == MCI_JIT_ON ||
+               (h->jit_mode == MCI_JIT_AUTO && (double)p->n_block * (double)p->neval_per_block >= 16777216.0);
 #undef BAIL
 
+  return MCI_OK;
+}
+
+extern "C" {
+
+int mci_create(const mci_problem_t *p, mci_handle_t **out) {
+  if (!p || !out) return fail(nullptr, MCI_ERR_INVALID, "null argument");
+  *out = nullptr;
+  mci_handle_t *h = new mci_handle_t();
+  {
+    const int rc = describe_problem(p, h);
+    if (rc) { delete h; return rc; }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || p->device < 0 || p->device >= ndev)
+    { delete h; return fail(nullptr, MCI_ERR_NO_DEVICE, "no CUDA device %d (found %d): libmcib200 has no CPU fallback", p->device, ndev); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
+    { delete h; return fail(nullptr, MCI_ERR_NO_DEVICE, "device %d is not a Blackwell (sm_100a) GPU", p->device); }
+
+  h->n_sm = prop.multiProcessorCount;
+  const int nd = h->nd, nleaf = h->nleaf, go = h->grid_len, dd = h->disc_len, da = h->accum_len, mo = h->dp.map_doubles;
+  const PackedLayout &Y = h->Y;
   /* ---- device resources ---- */
   *out = h; /* so that failures below can be cleaned up by the caller through mci_destroy */
 #define TRY(x) do { int rc_ = (x); if (rc_) { snprintf(g_err, 256, "%s", h->err); mci_destroy(h); *out = nullptr; return rc_; } } while (0)
@@ -785,7 +887,7 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
   if (h->p.solver != MCI_SOLVER_VEGAS) return fail(h, MCI_ERR_UNSUPPORTED, "mci_trace_samples: VEGAS sampler only");
   if (count == 0) return MCI_OK;
   CU(h, cudaSetDevice(h->device));
-  const void *k = lookup_vegas_trace(h->dp.fid);
+  const void *k = h->use_jit ? h->trace_kernel : lookup_vegas_trace(h->dp.fid);
   if (!k) return fail(h, MCI_ERR_UNSUPPORTED, "no trace kernel for integrand %d", h->dp.fid);
   if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
   const int nd = h->dp.n_draw, ni = h->ni;
@@ -807,6 +909,51 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
   if (e == cudaSuccess && weights) e = cudaMemcpy(weights, dw, sizeof(double) * (size_t)count * ni, cudaMemcpyDeviceToHost);
   cudaFree(dx); cudaFree(db); cudaFree(dj); cudaFree(dw);
   if (e != cudaSuccess) return fail(h, MCI_ERR_CUDA, "mci_trace_samples: %s", cudaGetErrorString(e));
+  return MCI_OK;
+}
+
+int mci_jit_check(const mci_problem_t *p, char *log, int32_t log_cap) {
+  if (!p) return MCI_ERR_INVALID;
+  if (log && log_cap > 0) log[0] = 0;
+  mci_handle_t *h = new mci_handle_t();
+  int rc = describe_problem(p, h);
+  if (rc) {
+    if (log && log_cap > 0) snprintf(log, log_cap, "%s", g_err);
+    delete h;
+    return rc;
+  }
+  const DevProblem &P = h->dp;
+  /* the kernels mci_create would pick with the automatic policies */
+  char name[160];
+  std::vector<std::string> exprs;
+  if (p->solver == MCI_SOLVER_VEGAS) {
+    const bool pool = P.nv == 1 && P.nleaf == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS && p->measure_kind == MCI_MEASURE_DEFAULT &&
+                      P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT && p->measurefreq == 1;
+    if (pool) {
+      const bool striped = P.any_adapt && P.maxdof[0] <= 20;
+      snprintf(name, sizeof name, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0],
+               !P.any_adapt ? HIST_NONE : (striped ? HIST_SMEM_STRIPED : HIST_SMEM_ATOMIC), striped ? POOL_THREADS_STRIPED : POOL_THREADS,
+               P.need_pad ? "false" : "true");
+    } else {
+      snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, GENERIC_THREADS);
+    }
+    exprs.push_back(name);
+    snprintf(name, sizeof name, "mci::vegas_trace_kernel<%d>", P.fid);
+    exprs.push_back(name);
+  } else {
+    snprintf(name, sizeof name, p->solver == MCI_SOLVER_VEGASMC ? "mci::vegasmc_kernel<%d>" : "mci::mcmc_kernel<%d>", P.fid);
+    exprs.push_back(name);
+  }
+  std::vector<const void *> ks;
+  std::string err;
+  setenv("MCIB200_JIT_COMPILE_ONLY", "1", 1);
+  rc = jit_compile(P, p->user_source, exprs, ks, err);
+  unsetenv("MCIB200_JIT_COMPILE_ONLY");
+  delete h;
+  if (rc != 0) {
+    if (log && log_cap > 0) snprintf(log, log_cap, "%s", err.c_str());
+    return MCI_ERR_UNSUPPORTED;
+  }
   return MCI_OK;
 }
 

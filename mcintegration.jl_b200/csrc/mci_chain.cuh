@@ -58,17 +58,17 @@ struct Walker {
 };
 
 struct ChainCtx {
-  const DevProblem &P;
+  const Problem &P;
   const double *maps;
   const PhiloxKey &K;
   Rng rng;
-  __device__ __forceinline__ ChainCtx(const DevProblem &p, const double *m, const PhiloxKey &k) : P(p), maps(m), K(k) {}
+  __device__ __forceinline__ ChainCtx(const Problem &p, const double *m, const PhiloxKey &k) : P(p), maps(m), K(k) {}
 };
 
 /* integrand accessor on the shared walker rows: X(leaf, pos), pos 1-based like the reference's x[pos] */
 struct ChainX {
   const double *data;
-  const DevProblem *P;
+  const Problem *P;
   int T;
   __device__ __forceinline__ double operator()(int leaf, int pos) const {
     return data[(P->leaf[leaf].base + (pos - 1) * P->leaf[leaf].stride) * T];
@@ -144,7 +144,7 @@ __device__ __forceinline__ double leaf_shift(ChainCtx &C, Walker<HP> &W, const D
 
 /* probability of (variable v, slot pos): the leaf's own for plain variables, the product over the leaves in leaf
  * order for a CompositeVar (sampler.jl:431-440 keeps exactly this product in its cache) */
-__device__ __forceinline__ double top_prob(const DevProblem &P, const Walker<true> &W, int v, int pos) {
+__device__ __forceinline__ double top_prob(const Problem &P, const Walker<true> &W, int v, int pos) {
   const int nl = P.top_nleaf[v];
   if (nl == 1) return W.prob[frow(P.leaf[P.top_first[v]], pos) * W.T];
   double tp = 1.0;
@@ -155,7 +155,7 @@ __device__ __forceinline__ double top_prob(const DevProblem &P, const Walker<tru
 /* top-level dispatch incl. CompositeVar: sampler.jl:410-462 */
 template <bool HP>
 __device__ __forceinline__ double var_create(ChainCtx &C, Walker<HP> &W, int v, int pos) {
-  const DevProblem &P = C.P;
+  const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_create(C, W, P.leaf[P.top_first[v]], pos);
   double prop = 1.0;
@@ -164,7 +164,7 @@ __device__ __forceinline__ double var_create(ChainCtx &C, Walker<HP> &W, int v, 
 }
 template <bool HP>
 __device__ __forceinline__ double var_remove(ChainCtx &C, Walker<HP> &W, int v, int pos) {
-  const DevProblem &P = C.P;
+  const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_remove(C, W, P.leaf[P.top_first[v]], pos);
   double prop = 1.0;
@@ -173,7 +173,7 @@ __device__ __forceinline__ double var_remove(ChainCtx &C, Walker<HP> &W, int v, 
 }
 template <bool HP>
 __device__ __forceinline__ double var_shift(ChainCtx &C, Walker<HP> &W, int v, int pos) {
-  const DevProblem &P = C.P;
+  const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_shift(C, W, P.leaf[P.top_first[v]], pos, 0);
   double prop = 1.0;
@@ -181,7 +181,7 @@ __device__ __forceinline__ double var_shift(ChainCtx &C, Walker<HP> &W, int v, i
   return prop;
 }
 template <bool HP>
-__device__ __forceinline__ void var_shift_rollback(const DevProblem &P, Walker<HP> &W, int v, int pos) {
+__device__ __forceinline__ void var_shift_rollback(const Problem &P, Walker<HP> &W, int v, int pos) {
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k) {
     const int f = frow(P.leaf[P.top_first[v] + k], pos) * W.T;
@@ -193,7 +193,7 @@ __device__ __forceinline__ void var_shift_rollback(const DevProblem &P, Walker<H
 }
 /* swap! (its own inverse): sampler.jl:85-97, 395-408, 443-462 */
 template <bool HP>
-__device__ __forceinline__ void var_swap(const DevProblem &P, Walker<HP> &W, int v, int p1, int p2) {
+__device__ __forceinline__ void var_swap(const Problem &P, Walker<HP> &W, int v, int p1, int p2) {
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k) {
     const DevLeaf &L = P.leaf[P.top_first[v] + k];
@@ -207,20 +207,20 @@ __device__ __forceinline__ void var_swap(const DevProblem &P, Walker<HP> &W, int
 /* initialize!: variable.jl:576-580 / :497-507 — leaf-major, slots 1..maxdof */
 template <bool HP>
 __device__ __forceinline__ void var_initialize(ChainCtx &C, Walker<HP> &W, int v) {
-  const DevProblem &P = C.P;
+  const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k)
     for (int pos = 1; pos <= P.maxdof[v]; ++pos) leaf_create(C, W, P.leaf[P.top_first[v] + k], pos);
 }
 
 /* variable.jl:606-619 / :628-641 */
-__device__ __forceinline__ double probability(const DevProblem &P, const Walker<true> &W, int i) {
+__device__ __forceinline__ double probability(const Problem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
   for (int v = 0; v < P.nv; ++v)
     for (int pos = 1; pos <= P.dof[i * P.nv + v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
   return pr;
 }
-__device__ __forceinline__ double padding_probability(const DevProblem &P, const Walker<true> &W, int i) {
+__device__ __forceinline__ double padding_probability(const Problem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
   for (int v = 0; v < P.nv; ++v)
     for (int pos = P.dof[i * P.nv + v] + 1; pos <= P.maxdof[v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
@@ -258,7 +258,7 @@ struct ChainSmem {
 };
 
 template <bool HP>
-__device__ __forceinline__ ChainSmem chain_setup(const DevProblem &P, const ChainArgs &A, double *smem, int n_count, Walker<HP> &W) {
+__device__ __forceinline__ ChainSmem chain_setup(const Problem &P, const ChainArgs &A, double *smem, int n_count, Walker<HP> &W) {
   const int T = blockDim.x, tid = threadIdx.x;
   ChainSmem S;
   double *maps_s = smem;
@@ -283,7 +283,7 @@ __device__ __forceinline__ ChainSmem chain_setup(const DevProblem &P, const Chai
   return S;
 }
 
-__device__ __forceinline__ void chain_flush_hist(const DevProblem &P, const ChainArgs &A, const ChainSmem &S) {
+__device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainArgs &A, const ChainSmem &S) {
   if (A.hist_mode == HIST_SMEM_ATOMIC) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
@@ -291,6 +291,11 @@ __device__ __forceinline__ void chain_flush_hist(const DevProblem &P, const Chai
   }
 }
 
+/* largest CTA the chain kernels are compiled for: 1024 threads cap the kernel at 64 registers; a JIT build whose
+ * specialised (unrolled) code spills under that cap is rebuilt for 512 threads x 128 registers (mci_abi.cu) */
+#ifndef MCI_CHAIN_MAXT
+#define MCI_CHAIN_MAXT 1024
+#endif
 /* bin-by-Discrete observables of the chain kernels are kept in this many per-thread accumulators (mci_create checks) */
 constexpr int CHAIN_MAX_BINNED_OBS = 8;
 #define PA_IDX(P, u, i, j) (((u) * (P).nd + (i)) * (P).pa_dim + (j))
@@ -299,7 +304,8 @@ constexpr int CHAIN_MAX_BINNED_OBS = 8;
 /* VegasMC                                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 template <int FID>
-__global__ void __launch_bounds__(1024, 1) vegasmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
+__global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid_constant__ DevProblem Pp, const ChainArgs A) {
+  MCI_VIEW(P, Pp);
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   extern __shared__ __align__(16) double smem[];
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(1024, 1) vegasmc_kernel(const __grid_constant_
 /* ------------------------------------------------------------------------------------------ */
 /* weight of integrand `idx` at the walker's point.  Integrands whose components are independent pay for one. */
 template <int FID, class XA>
-__device__ __forceinline__ double eval_one(const DevProblem &P, const XA &X, int idx) {
+__device__ __forceinline__ double eval_one(const Problem &P, const XA &X, int idx) {
   if constexpr (FID == MCI_F_PRODUCT_4) {
     const int d = P.dof[0];
     const double a = P.userdata[idx];
@@ -487,7 +493,7 @@ __device__ __forceinline__ double eval_one(const DevProblem &P, const XA &X, int
  * reference's left-to-right loop (last-bit differences in the acceptance ratio, inside the envelope of the integrand's
  * own rounding).  Returns the product on every lane; advances *q past the draws it consumed and leaves in
  * *b_out the buffered half when the new position is odd. */
-__device__ __forceinline__ double coop_change_dof(const DevProblem &P, const double *maps, const PhiloxKey &K, double *wdata0,
+__device__ __forceinline__ double coop_change_dof(const Problem &P, const double *maps, const PhiloxKey &K, double *wdata0,
                                                   int *wgidx0, int T, int src_tid, int curr, int nw, uint32_t c0, uint32_t c1,
                                                   uint32_t c3, uint32_t *q, double *b_out) {
   const int lane = threadIdx.x & 31;
@@ -548,7 +554,8 @@ __device__ __forceinline__ double coop_change_dof(const DevProblem &P, const dou
 }
 
 template <int FID>
-__global__ void __launch_bounds__(1024, 1) mcmc_kernel(const __grid_constant__ DevProblem P, const ChainArgs A) {
+__global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_constant__ DevProblem Pp, const ChainArgs A) {
+  MCI_VIEW(P, Pp);
   constexpr int NI = Integrand<FID>::NI;
   extern __shared__ __align__(16) double smem[];
   const int pa_len = P.pa_len_();

@@ -14,8 +14,10 @@
  * reference's expressions; see DESIGN.md "Numerics".
  */
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/mcib200.h"
 
@@ -71,6 +73,22 @@ struct DevProblem {
   uint64_t seed;
   __host__ __device__ int pa_len_() const { return 3 * nd * pa_dim; }
 };
+
+/* `Problem` is what the device code reads the problem description through.  Ahead-of-time kernels read the
+ * __grid_constant__ kernel parameter (constant bank).  A JIT build (mci_jit.cu: NVRTC, one program per problem) defines
+ * MCI_JIT and supplies "mci_jit_problem.h", whose JitProblem serves every layout field from compile-time tables — all
+ * loops over variables / leaves / slots / integrands then have constant bounds and unroll, per-sample arrays become
+ * registers — and forwards only the run-time values (userdata, seed, ...) from the kernel parameter. */
+#ifdef MCI_JIT
+}  // namespace mci
+#include "mci_jit_problem.h"
+namespace mci {
+using Problem = JitProblem;
+#define MCI_VIEW(P, Pp) const ::mci::JitProblem P(Pp)
+#else
+using Problem = DevProblem;
+#define MCI_VIEW(P, Pp) const ::mci::DevProblem &P = Pp
+#endif
 
 /* ---------------------------------------------------------------------------------------- */
 /* Philox4x32-10 (Salmon et al. 2011).  Stream layout (DESIGN.md "RNG"):                     */
@@ -236,7 +254,7 @@ __device__ __forceinline__ void hist_add_rt(int mode, double *h, int bin, double
 
 /* stage all maps into shared memory with 16-byte loads: Continuous leaves as (grid, width)
  * pairs, Discrete leaves as [dist(n) | accumulation(n+1)] */
-__device__ __forceinline__ void stage_maps(const DevProblem &P, double *smaps, const double *__restrict__ gmaps) {
+__device__ __forceinline__ void stage_maps(const Problem &P, double *smaps, const double *__restrict__ gmaps) {
   const int n2 = P.map_doubles >> 1; /* map area is padded to an even number of doubles */
   const double2 *src = reinterpret_cast<const double2 *>(gmaps);
   double2 *dst = reinterpret_cast<double2 *>(smaps);

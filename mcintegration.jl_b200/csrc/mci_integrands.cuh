@@ -24,7 +24,7 @@ struct PoolX {
 };
 struct FlatX {
   const double *v;
-  const DevProblem *P;
+  const Problem *P;
   __device__ __forceinline__ double operator()(int leaf, int pos) const {
     return v[P->leaf[leaf].base + (pos - 1) * P->leaf[leaf].stride];
   }
@@ -35,7 +35,7 @@ struct FlatX {
 /* dof of the pool as the integrand loops see it: the compile-time MAXD in an EXACT instantiation (no predication at
  * all), else the run-time value */
 template <int MAXD, bool EXACT>
-__device__ __forceinline__ int pool_dof(const DevProblem &P) { return EXACT ? MAXD : P.dof[0]; }
+__device__ __forceinline__ int pool_dof(const Problem &P) { return EXACT ? MAXD : P.dof[0]; }
 
 /* exp(x) for x <= 0 with the polynomial coefficients as constant-bank operands of the DFMAs (the libdevice exp
  * materialises its 13 coefficients through 26 UMOVs per call, which cost issue slots in a kernel that is issue-bound).
@@ -91,7 +91,7 @@ template <>
 struct Integrand<MCI_F_GAUSS_ND> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     const int d = pool_dof<MAXD, EXACT>(P);
     double s = 0.0;
     MCI_FOR_D(i, d, MAXD) { double x = X(0, i + 1); s += x * x; }
@@ -104,7 +104,7 @@ template <>
 struct Integrand<MCI_F_LOG_OVER_SQRT> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double x = X(0, 1);
     w[0] = log(x) / sqrt(x);
   }
@@ -115,7 +115,7 @@ template <>
 struct Integrand<MCI_F_GENZ_CORNER_POOL> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     const int d = pool_dof<MAXD, EXACT>(P);
     double s = 1.0;
     MCI_FOR_D(i, d, MAXD) s += P.userdata[i] * X(0, i + 1);
@@ -128,7 +128,7 @@ template <>
 struct Integrand<MCI_F_GENZ_CORNER_COMP> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     const int d = P.nleaf;
     double s = 1.0;
     for (int i = 0; i < d; ++i) s += P.userdata[i] * X(i, 1);
@@ -141,7 +141,7 @@ template <>
 struct Integrand<MCI_F_BUBBLE> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     const double *ud = P.userdata;
     double kF = ud[0], beta = ud[1], me = ud[2], spin = ud[3];
     double R = X(0, 1), th = X(1, 1), ph = X(2, 1), T = X(3, 1);
@@ -169,7 +169,7 @@ template <>
 struct Integrand<MCI_F_PRODUCT_4> {
   static constexpr int NI = 4;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     const int d = pool_dof<MAXD, EXACT>(P);
     double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
     MCI_FOR_D(i, d, MAXD) {
@@ -188,7 +188,7 @@ template <>
 struct Integrand<MCI_F_SPHERE1> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double a = X(0, 1), b = X(0, 2);
     w[0] = (__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)) < 1.0) ? 1.0 : 0.0;
   }
@@ -199,7 +199,7 @@ template <>
 struct Integrand<MCI_F_SPHERE2> {
   static constexpr int NI = 2;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double a = X(0, 1), b = X(0, 2), z = X(0, 3);
     double r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
     w[0] = (r2 < 1.0) ? 1.0 : 0.0;
@@ -212,7 +212,7 @@ template <>
 struct Integrand<MCI_F_DISCRETE_X> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = X(0, 1); }
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) { w[0] = X(0, 1); }
 };
 
 /* test/montecarlo.jl:113-120 */
@@ -220,7 +220,7 @@ template <>
 struct Integrand<MCI_F_DISCRETE2_CONST> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) { w[0] = 1.0; }
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) { w[0] = 1.0; }
 };
 
 /* test/montecarlo.jl:136-147 */
@@ -228,7 +228,7 @@ template <>
 struct Integrand<MCI_F_LATTICE_POOL> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(0, 2)) * cos(X(0, 3))) / (MCI_PI * MCI_PI * MCI_PI);
   }
 };
@@ -238,7 +238,7 @@ template <>
 struct Integrand<MCI_F_LATTICE_COMP> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     w[0] = 1.0 / (1.0 - cos(X(0, 1)) * cos(X(1, 1)) * cos(X(2, 1))) / (MCI_PI * MCI_PI * MCI_PI);
   }
 };
@@ -248,7 +248,7 @@ template <>
 struct Integrand<MCI_F_HYPERSPHERE3> {
   static constexpr int NI = 3;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double x1 = X(0, 1);
     double s = __dmul_rn(x1, x1);
 #pragma unroll
@@ -265,7 +265,7 @@ template <>
 struct Integrand<MCI_F_POLY3> {
   static constexpr int NI = 3;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double x = X(0, 1);
     w[0] = x; w[1] = x * x; w[2] = x * x * x;
   }
@@ -276,7 +276,7 @@ template <>
 struct Integrand<MCI_F_X2_PLUS_Y2> {
   static constexpr int NI = 1;
   template <int MAXD, class XA, bool EXACT = false>
-  __device__ __forceinline__ static void eval(const XA &X, const DevProblem &P, double *w) {
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
     double a = X(0, 1), b = X(0, 2);
     w[0] = a * a + b * b;
   }

@@ -93,7 +93,7 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
 #endif
 
 template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD>
-__device__ __forceinline__ void pool_sample(const DevProblem &P, const PhiloxKey &K, const double2 *__restrict__ pair,
+__device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const double2 *__restrict__ pair,
                                             uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
                                             bool active, double *acc, int &cnt, unsigned long long &bad) {
   using F = Integrand<FID>;
@@ -176,7 +176,8 @@ struct PoolMinBlocks {
 };
 
 template <int FID, int MAXD, int HMODE, int THREADS, bool EXACT>
-__global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) vegas_pool_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+__global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) vegas_pool_kernel(const __grid_constant__ DevProblem Pp, const FillArgs A) {
+  MCI_VIEW(P, Pp);
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
 /* sampler.jl:431-440).  tprob[] = probability of each (variable, slot), only when need_pad.     */
 /* ------------------------------------------------------------------------------------------ */
 template <int FID>
-__device__ __forceinline__ void vegas_sample_generic(const DevProblem &P, const double *maps, const PhiloxKey &K,
+__device__ __forceinline__ void vegas_sample_generic(const Problem &P, const double *maps, const PhiloxKey &K,
                                                      uint64_t s, uint32_t block, double *x, int *bin, double *tprob,
                                                      double &jac, double *w, double *pad) {
   using F = Integrand<FID>;
@@ -326,7 +327,8 @@ __device__ __forceinline__ void vegas_sample_generic(const DevProblem &P, const 
 }
 
 template <int FID, int THREADS>
-__global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_constant__ DevProblem P, const FillArgs A) {
+__global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_constant__ DevProblem Pp, const FillArgs A) {
+  MCI_VIEW(P, Pp);
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
@@ -429,8 +431,9 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
 
 /* L0 parity probe (mci_trace_samples): regenerate `count` samples with the generic sampler */
 template <int FID>
-__global__ void vegas_trace_kernel(const __grid_constant__ DevProblem P, const double *gmaps, uint64_t iter, uint32_t block,
+__global__ void vegas_trace_kernel(const __grid_constant__ DevProblem Pp, const double *gmaps, uint64_t iter, uint32_t block,
                                    uint64_t first, int count, double *xo, int *bo, double *jo, double *wo) {
+  MCI_VIEW(P, Pp);
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   PhiloxKey K;

@@ -20,9 +20,21 @@ class Integrand:
     n_integrand: int
     userdata: tuple = ()
     doc: str = ""
+    source: str | None = None  # CUDA C++ source of a user integrand (id == F_USER)
 
     def with_userdata(self, data: Sequence[float]) -> "Integrand":
-        return Integrand(self.name, self.id, self.n_integrand, tuple(float(x) for x in data), self.doc)
+        return Integrand(self.name, self.id, self.n_integrand, tuple(float(x) for x in data), self.doc, self.source)
+
+
+def user_integrand(source: str, n_integrand: int = 1, userdata: Sequence[float] = (), name: str = "user") -> Integrand:
+    """The reference takes any closure f(x, c) (main.jl:25-33); here the integrand is CUDA C++ source compiled by NVRTC
+    at engine creation into a kernel specialised to the problem.  `source` must define
+
+        template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w);
+
+    X(leaf, pos): value of pool slot `pos` (1-based, the reference's x[pos]) of leaf variable `leaf` (0-based, top-level
+    order then leaf order); w[0..n_integrand-1] receives the values."""
+    return Integrand(name, _abi.F_USER, int(n_integrand), tuple(float(x) for x in userdata), "user source (NVRTC)", source)
 
 
 gauss_nd = Integrand("gauss_nd", _abi.F_GAUSS_ND, 1, doc="(2π)^(-d/2) exp(-|x|²/2); one Continuous pool, dof=[[d]]")

@@ -1,0 +1,137 @@
+"""NVRTC path (csrc/mci_jit.cu): user integrands given as CUDA C++ source — the drop-in for the reference's "any
+closure f(x, c)" (src/main.jl:25-33) — and problem-specialised builds of the built-in integrands (jit=1).
+CPU part: the generated program compiles (mci_jit_check needs no GPU) and compiler errors come back readable.
+GPU part: a user-source Gaussian reproduces the built-in one; jit=1 kernels pass the same L1 parity against the oracle
+as the ahead-of-time kernels."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import mcintegration_jl_b200 as mci
+from mcintegration_jl_b200 import _abi, integrands as I
+from cases import make_spec
+
+GAUSS_SRC = """
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  double s = 0.0;
+  for (int i = 1; i <= 10; ++i) { double x = X(0, i); s += x * x; }
+  w[0] = userdata[0] * exp(-0.5 * s);
+}
+"""
+# two integrands on a tuple of variables: f1 = x*y (x in [0,1), y in [0,2)), f2 = k (Discrete 1..4)
+MIXED_SRC = """
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  w[0] = X(0, 1) * X(1, 1);
+  w[1] = X(2, 1);
+}
+"""
+
+
+def _check(spec):
+    lib = _abi.load_library()
+    p, keep = spec.to_ctypes()
+    log = C.create_string_buffer(16384)
+    rc = lib.mci_jit_check(C.byref(p), log, 16384)
+    return rc, log.value.decode()
+
+
+def _user_gauss_spec(solver=_abi.SOLVER_VEGAS, **kw):
+    cfg = mci.Configuration(var=mci.Continuous(-5.0, 5.0), dof=[[10]], seed=1234)
+    f = I.user_integrand(GAUSS_SRC, 1, [(2 * math.pi) ** -5])
+    return mci.problem_from_config(cfg, f, solver=solver, measure_kind=0, n_block=16, neval_per_block=4096, **kw), cfg
+
+
+@pytest.mark.parametrize("solver", [_abi.SOLVER_VEGAS, _abi.SOLVER_VEGASMC, _abi.SOLVER_MCMC])
+def test_user_source_compiles_for_every_solver(solver):
+    spec, _ = _user_gauss_spec(solver, walkers_per_block=64 if solver else 1)
+    rc, log = _check(spec)
+    assert rc == 0, log
+
+
+def test_user_source_errors_are_reported():
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[1]], seed=1)
+    bad = I.user_integrand("template <class XA> __device__ void mci_user_integrand(const XA &X, const double *u, double *w) "
+                           "{ w[0] = no_such_symbol; }")
+    spec = mci.problem_from_config(cfg, bad, solver=_abi.SOLVER_VEGAS, measure_kind=0, n_block=16, neval_per_block=64)
+    rc, log = _check(spec)
+    assert rc == _abi.ERR_UNSUPPORTED
+    assert "no_such_symbol" in log and "user_source(1)" in log
+    spec.user_source = None  # MCI_F_USER without a source
+    rc, log = _check(spec)
+    assert rc == _abi.ERR_INVALID and "user_source" in log
+
+
+@pytest.mark.parametrize("name,solver", [("gauss10", "vegas"), ("bubble", "vegas"), ("bubble", "vegasmc"), ("product4", "mcmc"),
+                                          ("discrete2", "vegasmc"), ("genz6_comp", "vegas"), ("sphere2_offset", "mcmc")])
+def test_builtin_integrands_compile_specialised(name, solver):
+    spec, _ = make_spec(name, solver, walkers=64 if solver != "vegas" else 1)
+    spec.jit = 1
+    rc, log = _check(spec)
+    assert rc == 0, log
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_user_gaussian_matches_builtin():
+    spec_u, _ = _user_gauss_spec()
+    spec_b, _ = make_spec("gauss10", "vegas", neval_per_block=4096)
+    u, b = mci.CudaEngine(spec_u), mci.CudaEngine(spec_b)
+    try:
+        assert "[jit]" in u.kernel_name() and "MCI_F_GAUSS_ND" in b.kernel_name()
+        for it in range(3):
+            a, c = u.run_iteration(it), b.run_iteration(it)
+            np.testing.assert_allclose(a.block_obs, c.block_obs, rtol=1e-12)  # libdevice exp vs exp_nonpos: <= 2 ulp per weight
+            assert np.array_equal(a.block_norm, c.block_norm)
+            np.testing.assert_allclose(a.hist, c.hist, rtol=1e-10)
+            b.refine()
+            u.set_maps(*b.get_maps())
+        xu, bu, ju, wu = u.trace_samples(2, 5, 1000, 256)
+        xb, bb, jb, wb = b.trace_samples(2, 5, 1000, 256)
+        assert np.array_equal(bu, bb) and np.array_equal(xu, xb) and np.array_equal(ju, jb)
+        np.testing.assert_allclose(wu, wb, rtol=1e-14)
+    finally:
+        u.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+def test_user_integrand_end_to_end(solver):
+    """integrate() with a source integrand on a tuple of variables (Continuous, Continuous, Discrete), two integrands:
+    int x*y over [0,1)x[0,2) = 1 and sum_{k=1..4} k = 10; the reference's 7 sigma rule."""
+    f = I.user_integrand(MIXED_SRC, 2)
+    res = mci.integrate(f, solver=solver, neval=4e5, niter=10, seed=5, walkers=64,
+                        var=(mci.Continuous(0.0, 1.0), mci.Continuous(0.0, 2.0), mci.Discrete(1, 4)), dof=[[1, 1, 0], [0, 0, 1]])
+    for k, ex in enumerate((1.0, 10.0)):
+        assert abs(res.mean[k] - ex) < 7 * res.stdev[k] + 1e-12, (k, res.mean[k], res.stdev[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,solver", [("gauss10", "vegas"), ("sphere2", "vegas"), ("bubble", "vegas"), ("genz6_comp", "vegas"),
+                                          ("discrete2", "vegas"), ("bubble", "vegasmc"), ("sphere2", "vegasmc"),
+                                          ("product4_d6", "vegasmc"), ("bubble", "mcmc"), ("sphere2_offset", "mcmc"),
+                                          ("product4_d6", "mcmc"), ("lattice_comp", "mcmc")])
+def test_specialised_kernels_keep_parity(name, solver):
+    """jit=1: the same templates compiled against compile-time layout tables must reproduce the oracle like the
+    ahead-of-time kernels do (tolerances of tests/test_gpu_parity.py)."""
+    from oracle_lib import OracleEngine
+    kw = dict(neval_per_block=5000) if solver == "vegas" else dict(n_block=4, neval_per_block=96 * 200, walkers=96)
+    spec, _ = make_spec(name, solver, **kw)
+    spec.jit = 1
+    gpu, cpu = mci.CudaEngine(spec), OracleEngine(spec)
+    try:
+        assert "[jit]" in gpu.kernel_name()
+        for it in range(2):
+            a, b = gpu.run_iteration(it), cpu.run_iteration(it)
+            tol = 1e-11 if solver == "vegas" else 1e-9
+            scale = np.abs(b.block_obs).max() + 1e-300
+            np.testing.assert_allclose(a.block_obs, b.block_obs, rtol=tol, atol=tol * scale)
+            np.testing.assert_allclose(a.block_norm, b.block_norm, rtol=tol)
+            np.testing.assert_allclose(a.hist, b.hist, rtol=1e-9)
+            np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
+            assert a.neval == b.neval
+            cpu.refine()
+            gpu.set_maps(*cpu.get_maps())
+    finally:
+        gpu.close(); cpu.close()
