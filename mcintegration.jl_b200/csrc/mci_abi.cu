@@ -201,18 +201,6 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   std::string err;
   int rc = jit_compile(P, h->user_source.c_str(), exprs, ks, err);
   h->chain_maxt = 1024;
-  if (rc == 0 && kind >= 2) { /* specialised chain code that spills under the 64-register cap: 512 threads x 128 registers */
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, ks[0]) == cudaSuccess && fa.localSizeBytes > 192) {
-      std::vector<const void *> ks2;
-      std::string err2;
-      if (jit_compile(P, h->user_source.c_str(), exprs, ks2, err2, "#define MCI_CHAIN_MAXT 512\n") == 0) {
-        jit_unload(ks.back());
-        ks = ks2;
-        h->chain_maxt = 512;
-      }
-    }
-  }
   if (rc != 0) {
     if (h->jit_mode == MCI_JIT_AUTO && P.fid != MCI_F_USER) { /* auto: the ahead-of-time kernel serves as well */
       h->use_jit = false;

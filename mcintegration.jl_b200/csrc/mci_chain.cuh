@@ -291,8 +291,9 @@ __device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainAr
   }
 }
 
-/* largest CTA the chain kernels are compiled for: 1024 threads cap the kernel at 64 registers; a JIT build whose
- * specialised (unrolled) code spills under that cap is rebuilt for 512 threads x 128 registers (mci_abi.cu) */
+/* largest CTA the chain kernels are compiled for: 1024 threads cap the kernel at 64 registers.  (Measured on the
+ * bubble under mcmc: a 512-thread / 128-register build removes the spills but halves the resident walkers and is
+ * 1.3x slower, so the cap stays; a JIT program may still override it with a #define.) */
 #ifndef MCI_CHAIN_MAXT
 #define MCI_CHAIN_MAXT 1024
 #endif
