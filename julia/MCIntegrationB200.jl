@@ -26,6 +26,7 @@ struct MciProblem
     neighbor_ptr::Ptr{Int32}; neighbor_idx::Ptr{Int32}; userdata::Ptr{Float64}
     n_userdata::Int32; n_block::Int32; neval_per_block::UInt64; seed::UInt64
     measurefreq::Int32; walkers_per_block::Int32; thermal_ratio::Float64; device::Int32; hist_policy::Int32
+    jit::Int32; reserved_::Int32; user_source::Cstring       # ABI v2: NVRTC specialisation / user integrand source
 end
 
 struct MciIterationOut
@@ -46,15 +47,21 @@ leafdesc(v::Continuous) = MciLeaf(0, length(v.grid) - 1, v.adapt, 0, v.lower, v.
 leafdesc(v::Discrete) = MciLeaf(1, v.upper - v.lower + 1, v.adapt, v.lower, 0.0, 0.0, v.alpha)
 
 """
-    integrate_b200(integrand_id::Integer; userdata=Float64[], measure_kind=0, walkers=4096, device=0, kwargs...)
+    integrate_b200(integrand::Union{Integer,AbstractString}; userdata=Float64[], measure_kind=0, walkers=4096, device=0, jit=0, kwargs...)
 
 Same keyword surface as `MCIntegration.integrate` (src/main.jl:71-90): `solver, config, neval, niter, block, gamma,
 adapt, reweight_goal, ignore, measurefreq, thermal_ratio` plus the `Configuration` kwargs (`var, dof, obs, reweight,
-seed, neighbor`).  The integrand is a built-in device function (`enum mci_integrand_id`) instead of a closure.
+seed, neighbor`).  The integrand is a built-in device function (`enum mci_integrand_id`) or CUDA C++ source instead of a
+closure.
 """
-function integrate_b200(integrand_id::Integer; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
+function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
     gamma=1.0, adapt=true, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
-    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, kwargs...)
+    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, jit=0, kwargs...)
+    # `integrand` is a built-in id (enum mci_integrand_id) or a String holding CUDA C++ source that defines
+    # `template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w)`
+    # (MCI_F_USER = 100, compiled by NVRTC inside mci_create) — the device-side equivalent of the closure f(x, c).
+    integrand_id = integrand isa AbstractString ? 100 : Int(integrand)
+    source = integrand isa AbstractString ? String(integrand) : ""
     haskey(SOLVER, solver) || error("Solver $solver is not supported!")            # main.jl:263
     config = isnothing(config) ? Configuration(; kwargs...) : config                # main.jl:95-97
     nevalperblock, block = MCIntegration._standardize_block(neval, block)          # main.jl:121
@@ -76,10 +83,11 @@ function integrate_b200(integrand_id::Integer; solver=:vegasmc, config=nothing, 
     seed = UInt64(rand(config.rng, 1:10^6))                                          # main.jl:136
 
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve topn topoff desc dof obslen nbptr nbidx ud begin
+    GC.@preserve topn topoff desc dof obslen nbptr nbidx ud source begin
         prob = MciProblem(SOLVER[solver], integrand_id, measure_kind, N, Nv, length(lv), pointer(topn), pointer(topoff),
             pointer(desc), pointer(dof), pointer(obslen), pointer(nbptr), pointer(nbidx), pointer(ud), length(ud), block,
-            nevalperblock, seed, measurefreq, W, thermal_ratio, device, hist_policy)
+            nevalperblock, seed, measurefreq, W, thermal_ratio, device, hist_policy, jit, 0,
+            isempty(source) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, source))
         rc = ccall((:mci_create, LIB), Cint, (Ref{MciProblem}, Ref{Ptr{Cvoid}}), prob, h)
         rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
     end

@@ -79,10 +79,12 @@ def drive(engine, config, *, solver, niter, block, gamma=1.0, adapt=True, reweig
 def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, block=16, verbose=-1, gamma=1.0,
               adapt=True, debug=False, reweight_goal=None, ignore=None, measure=None, measurefreq=1,
               thermal_ratio=0.1, inplace=False, parallel="nothread", print=-1, walkers=None, device=0,
-              hist_policy=0, comm=None, **kwargs):
+              hist_policy=0, comm=None, jit=0, **kwargs):
     """Drop-in for MCIntegration.integrate (main.jl:71-90) on one B200.
 
-    `integrand` is a built-in device integrand (mcintegration_jl_b200.integrands) instead of a closure;
+    `integrand` is a built-in device integrand (mcintegration_jl_b200.integrands) or CUDA C++ source
+    (integrands.user_integrand, compiled by NVRTC into a kernel specialised to the problem) instead of a closure;
+    `jit` = 0 auto / 1 always specialise with NVRTC / 2 ahead-of-time kernels only;
     `measure` is None or "bin_by_discrete".  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
     `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU).
     Everything else keeps the reference's meaning; `neval` is per iteration.
@@ -108,7 +110,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
         nevalperblock = (nevalperblock // W) * W
     spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
-                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy)
+                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit)
     engine = CudaEngine(spec)
     try:
         engine.set_maps(*maps_from_config(config))  # warm restart: config=result.config (main.jl:95-97)
