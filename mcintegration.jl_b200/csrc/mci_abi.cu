@@ -240,7 +240,9 @@ int plan(mci_handle_t *h) {
     if (policy == MCI_HIST_GLOBAL_RED) return (int)HIST_GLOBAL_RED;
     /* auto (measured on B200, C2, profiles/r1_hist_policies.md): one CTA-shared fp64 histogram with shared-memory CAS
      * beats per-warp private copies with MATCH.ANY conflict ranking (ADU-pipe bound) by 2.3x and L2 REDs by 1.5x */
-    if (base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
+    /* a shared histogram that leaves room for only one 256-thread CTA per SM starves the SM of warps: L2 REDs then win
+     * (16-leaf composite: 9.1 vs 6.1 G samples/s) */
+    if (base + hist_bytes <= (nwarp >= 16 ? SMEM_MAX : SMEM_MAX / 2)) return (int)HIST_SMEM_ATOMIC;
     return (int)HIST_GLOBAL_RED;
   };
   auto hist_smem = [&](int mode, int nwarp) -> size_t {

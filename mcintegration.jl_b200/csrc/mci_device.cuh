@@ -85,9 +85,11 @@ struct DevProblem {
 namespace mci {
 using Problem = JitProblem;
 #define MCI_VIEW(P, Pp) const ::mci::JitProblem P(Pp)
+#define MCI_UNROLL_LAYOUT _Pragma("unroll") /* loops over the layout have constant bounds: unroll them completely */
 #else
 using Problem = DevProblem;
 #define MCI_VIEW(P, Pp) const ::mci::DevProblem &P = Pp
+#define MCI_UNROLL_LAYOUT
 #endif
 
 /* ---------------------------------------------------------------------------------------- */

@@ -283,9 +283,12 @@ __device__ __forceinline__ void vegas_sample_generic(const Problem &P, const dou
   jac = 1.0;
   int k = 0;
   uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  MCI_UNROLL_LAYOUT
   for (int v = 0; v < P.nv; ++v) {
+    MCI_UNROLL_LAYOUT
     for (int p = 0; p < P.maxdof[v]; ++p) {
       double tp = 1.0;
+      MCI_UNROLL_LAYOUT
       for (int l = 0; l < P.top_nleaf[v]; ++l, ++k) {
         const DevLeaf &L = P.leaf[P.top_first[v] + l];
         double u;
@@ -317,11 +320,16 @@ __device__ __forceinline__ void vegas_sample_generic(const Problem &P, const dou
   }
   FlatX X{x, &P};
   F::template eval<0>(X, P, w);
+  MCI_UNROLL_LAYOUT
   for (int i = 0; i < P.ni; ++i) {
     double pd = 1.0;
-    if (P.need_pad && !P.same_dof[i])
-      for (int v = 0; v < P.nv; ++v)
+    if (P.need_pad && !P.same_dof[i]) {
+      MCI_UNROLL_LAYOUT
+      for (int v = 0; v < P.nv; ++v) {
+        MCI_UNROLL_LAYOUT
         for (int p = P.dof[i * P.nv + v]; p < P.maxdof[v]; ++p) pd *= tprob[P.top_tslot[v] + p];
+      }
+    }
     pad[i] = pd;
   }
 }
@@ -385,11 +393,15 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
         cnt++;
       }
       if (hmode != HIST_NONE) {
+        MCI_UNROLL_LAYOUT
         for (int v = 0; v < P.nv; ++v)
+          MCI_UNROLL_LAYOUT
           for (int i = 0; i < NI; ++i) {
             const double a = fabs(w[i]) * jac;
             const double w2 = a * a;
+            MCI_UNROLL_LAYOUT
             for (int p = 0; p < P.dof[i * P.nv + v]; ++p)
+              MCI_UNROLL_LAYOUT
               for (int l = 0; l < P.top_nleaf[v]; ++l) {
                 const DevLeaf &L = P.leaf[P.top_first[v] + l];
                 if (L.adapt) hist_add_rt(hmode, myhist + L.hist_off, bin[L.base + p * L.stride], w2, active);

@@ -27,6 +27,9 @@ def case(name):
         "genz6_comp": dict(f=I.genz_corner_peak(6, "comp"),
                            cfg=lambda: dict(var=mci.Continuous([(0.0, 1.0)] * 6), dof=[[1]]),
                            expect=[I.genz_corner_peak_exact(I.genz_corner_peak(6, "comp").userdata)]),
+        "genz16_comp": dict(f=I.genz_corner_peak(16, "comp"),
+                            cfg=lambda: dict(var=mci.Continuous([(0.0, 1.0)] * 16), dof=[[1]]),
+                            expect=[4.17984992413838e-05]),
         # test/montecarlo.jl:4-9 (Sphere1), :19-49 (Sphere2/3)
         "sphere1": dict(f=I.sphere1, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[2]]), expect=[PI / 4]),
         "sphere2": dict(f=I.sphere2, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[2], [3]]),
