@@ -155,6 +155,10 @@ typedef struct mci_problem_t {
                               else the ahead-of-time kernel; MCI_F_USER always jits                                */
   int32_t reserved_;
   const char *user_source; /* MCI_F_USER: NUL-terminated CUDA C++ source, copied by mci_create; else NULL         */
+  uint64_t chain_burnin;   /* chain solvers: extra update steps every walker makes BEFORE the reference's loop starts,
+                              touching no statistic (0 = the reference).  A GPU cuts a block into many short chains
+                              and each starts from a draw of the VEGAS map, not of the target density: chains of
+                              ~10^3 steps carry a visible start bias, which this burns away          */
 } mci_problem_t;
 
 enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };

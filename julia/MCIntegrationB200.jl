@@ -27,6 +27,7 @@ struct MciProblem
     n_userdata::Int32; n_block::Int32; neval_per_block::UInt64; seed::UInt64
     measurefreq::Int32; walkers_per_block::Int32; thermal_ratio::Float64; device::Int32; hist_policy::Int32
     jit::Int32; reserved_::Int32; user_source::Cstring       # ABI v2: NVRTC specialisation / user integrand source
+    chain_burnin::UInt64                                       # extra unmeasured steps per chain (0 = reference)
 end
 
 struct MciIterationOut
@@ -56,7 +57,7 @@ closure.
 """
 function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
     gamma=1.0, adapt=true, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
-    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, jit=0, kwargs...)
+    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, jit=0, chain_burnin=0, kwargs...)
     # `integrand` is a built-in id (enum mci_integrand_id) or a String holding CUDA C++ source that defines
     # `template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w)`
     # (MCI_F_USER = 100, compiled by NVRTC inside mci_create) — the device-side equivalent of the closure f(x, c).
@@ -87,7 +88,7 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
         prob = MciProblem(SOLVER[solver], integrand_id, measure_kind, N, Nv, length(lv), pointer(topn), pointer(topoff),
             pointer(desc), pointer(dof), pointer(obslen), pointer(nbptr), pointer(nbidx), pointer(ud), length(ud), block,
             nevalperblock, seed, measurefreq, W, thermal_ratio, device, hist_policy, jit, 0,
-            isempty(source) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, source))
+            isempty(source) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, source), UInt64(chain_burnin))
         rc = ccall((:mci_create, LIB), Cint, (Ref{MciProblem}, Ref{Ptr{Cvoid}}), prob, h)
         rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
     end

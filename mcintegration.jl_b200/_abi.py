@@ -91,6 +91,7 @@ class Problem(C.Structure):
         ("jit", C.c_int32),
         ("reserved_", C.c_int32),
         ("user_source", C.c_char_p),
+        ("chain_burnin", C.c_uint64),
     ]
 
 

@@ -149,6 +149,7 @@ class ProblemSpec:
     hist_policy: int = 0
     jit: int = 0
     user_source: str | None = None
+    chain_burnin: int = 0
 
     def to_ctypes(self):
         keep = []
@@ -191,6 +192,7 @@ class ProblemSpec:
         p.device = self.device
         p.hist_policy = self.hist_policy
         p.jit = self.jit
+        p.chain_burnin = int(self.chain_burnin)
         if self.user_source is not None:
             src = self.user_source.encode()
             keep.append(src)
@@ -201,7 +203,7 @@ class ProblemSpec:
 def problem_from_config(config: Configuration, integrand, *, solver: int, measure_kind: int, n_block: int,
                         neval_per_block: int, measurefreq: int = 1, walkers_per_block: int = 1,
                         thermal_ratio: float = 0.1, device: int = 0, hist_policy: int = 0,
-                        default_neighbor: bool = False, jit: int = 0) -> ProblemSpec:
+                        default_neighbor: bool = False, jit: int = 0, chain_burnin: int = 0) -> ProblemSpec:
     leaves = []
     for L in config.leaves():
         if isinstance(L, Continuous):
@@ -218,7 +220,7 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
         neighbor=None if default_neighbor else config.neighbor, userdata=list(integrand.userdata),
         n_block=n_block, neval_per_block=neval_per_block, seed=config.seed, measurefreq=measurefreq,
         walkers_per_block=walkers_per_block, thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit,
-        user_source=getattr(integrand, "source", None))
+        user_source=getattr(integrand, "source", None), chain_burnin=chain_burnin)
 
 
 def maps_from_config(config: Configuration):

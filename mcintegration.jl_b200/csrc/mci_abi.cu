@@ -708,7 +708,7 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, p.walkers_per_block);
     CA.ctas_per_block = h->ctas_per_block; CA.n_local_blocks = n_local; CA.rank = h->rank; CA.world = h->world;
     CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;
-    CA.rows = h->chain_rows; CA.coop_ci = h->coop_ci;
+    CA.rows = h->chain_rows; CA.coop_ci = h->coop_ci; CA.burnin = (long long)p.chain_burnin;
     args[0] = &h->dp; args[1] = &CA;
   }
   const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);

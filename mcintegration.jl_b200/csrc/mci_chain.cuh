@@ -44,6 +44,7 @@ struct ChainArgs {
   int n_local_blocks, rank, world;
   int hist_mode, n_hist_copies, maps_in_smem;
   int rows;               /* walker rows in shared memory = n_draw + max leaves of one variable  */
+  long long burnin;       /* extra unmeasured steps before the reference's loop (mci_problem_t.chain_burnin) */
   int coop_ci;            /* mcmc: changeIntegrand creates/removes enough slots for the warp-cooperative path */
 };
 
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   }
   const double meas_from = (double)A.steps / 100; /* ne >= neval/100 (montecarlo.jl:213) */
 
-  for (uint64_t ne = 1; ne <= A.steps; ++ne) {
+  for (long long ne = 1 - A.burnin; ne <= (long long)A.steps; ++ne) { /* ne <= 0: burn-in, no statistics */
     /* changeVariable: updates.jl:45-106 */
     if (active) {
       const int vi = C.rng.randint(K, P.nv) - 1;
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
     __syncwarp();
     /* histogram of every step: montecarlo.jl:198-211.  hist[bin of (v, pos)] += wf2_i for every integrand i with
      * pos <= dof[i][v]: the contributions of the integrands to one slot are summed first, one update per slot */
-    if (hmode != HIST_NONE && active) {
+    if (hmode != HIST_NONE && active && ne >= 1) {
       double wf2[NI];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
     }
     __syncwarp();
     /* measurement: montecarlo.jl:213-232 */
-    if (active && (P.measurefreq == 1 || (ne % (uint64_t)P.measurefreq) == 0) && (double)ne >= meas_from) {
+    if (active && ne >= 1 && (P.measurefreq == 1 || ((uint64_t)ne % (uint64_t)P.measurefreq) == 0) && (double)ne >= meas_from) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         visited[i] += __ddiv_rn(fabs(__dmul_rn(__dmul_rn(weights[i], pad[i]), rw[i])), prob_cur);
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   const uint64_t nburnin = (uint64_t)floor(__dmul_rn((double)A.steps, P.thermal_ratio));
   const uint64_t total = A.steps + nburnin;
 
-  for (uint64_t it = 1; it <= total; ++it) {
+  for (long long it = 1 - A.burnin; it <= (long long)total; ++it) { /* it <= 0: burn-in, no statistics */
     /* ---- propose (divergent, cheap) ---- */
     int kind = 0;   /* 0 none, 1 changeIntegrand, 2 changeVariable, 3 swapVariable (= first index of propose/accept + 1) */
     int tgt = curr; /* integrand to evaluate */
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
     bool ci = false, ci_dof = false; /* changeIntegrand proposed (to tgt); it changes some dof */
     if (active) {
 #pragma unroll
-      for (int i = 0; i <= N; ++i) visited[i] += (i == curr);
+      for (int i = 0; i <= N; ++i) visited[i] += (i == curr && it >= 1);
       const int u = C.rng.randint(K, nupdates);
       if (u == 1) {
         /* changeIntegrand: updates.jl:1-70.  The create!/remove! of the dof difference is done by the whole warp below */
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
     }
     __syncwarp();
     /* measurement: montecarlo.jl:145-170 */
-    if (active && (P.measurefreq == 1 || (it % (uint64_t)P.measurefreq) == 0) && it >= nburnin) {
+    if (active && it >= 1 && (P.measurefreq == 1 || ((uint64_t)it % (uint64_t)P.measurefreq) == 0) && (uint64_t)it >= nburnin) {
       if (curr == N) {
         normalization += __ddiv_rn(1.0, rw[N]);
       } else {

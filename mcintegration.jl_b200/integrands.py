@@ -114,6 +114,29 @@ class BubblePara:
         return -Pi * density * spin / 2
 
 
+def lindhard_finite_temperature(para: "BubblePara", q: float) -> float:
+    """Static polarisation of example/bubble.jl at ITS temperature: the Maldague average
+    Pi_T(q; mu) = int_0^inf dmu' Pi_0(q; mu') / (4T cosh^2((mu - mu') / 2T)) of the T=0 Lindhard function
+    (example/bubble.jl:24-38) with mu = kF^2/2m fixed, as the integrand's dispersion has it (bubble.jl:62,68).
+    The reference compares with the T=0 value under loose sigma ratios; this is the exact target (needs scipy)."""
+    from scipy.integrate import quad
+
+    me, kF, spin = para.me, para.kF, para.spin
+    EF, T = kF ** 2 / (2 * me), 1.0 / para.β
+
+    def pi0(kf):
+        if kf <= 0:
+            return 0.0
+        qq = max(q, 1e-6)
+        x = qq / 2 / kf
+        Pi = 1 + (1 - x ** 2) * math.log(abs((1 + x) / (1 - x))) / 2 / x if abs(qq - 2 * kf) > 1e-9 else 1.0
+        return -Pi * (me * kf / (2 * math.pi ** 2)) * spin / 2
+
+    f = lambda mu: pi0(math.sqrt(2 * me * mu)) / (4 * T * math.cosh((mu - EF) / (2 * T)) ** 2)
+    v, _ = quad(f, 0.0, EF + 40 * T, points=[EF, (max(q, 1e-6) / 2) ** 2 / (2 * me)], limit=400, epsabs=1e-13, epsrel=1e-12)
+    return v
+
+
 def bubble(para: BubblePara | None = None) -> Integrand:
     """example/bubble.jl:50-75; variables (R, θ, φ, T, Ext); userdata = [kF, β, me, spin, dim, Qsize, extQx…]."""
     para = para or BubblePara()

@@ -19,6 +19,17 @@ _MEASURES = {None: _abi.MEASURE_DEFAULT, "default": _abi.MEASURE_DEFAULT,
 # density, so chains much shorter than the equilibration time bias the estimate
 DEFAULT_WALKERS = 4096
 MIN_CHAIN_STEPS = 512
+# unmeasured steps every chain makes first when a block is cut into several chains and the caller does not say:
+# measured on C4 (tools/c4_bias_probe.py, against the finite-temperature Lindhard function) 1000 burn-in steps take
+# 1525-step chains from 3-8 sigma off to < 1 sigma, and 4000 do the same for 190-step chains
+DEFAULT_CHAIN_BURNIN = 1024
+
+
+def default_chain_burnin(walkers, chain_burnin):
+    """None -> 0 for the reference's decomposition (one chain per block), DEFAULT_CHAIN_BURNIN otherwise"""
+    if chain_burnin is not None:
+        return int(chain_burnin)
+    return 0 if walkers <= 1 else DEFAULT_CHAIN_BURNIN
 
 
 def _standardize_block(neval, nblock, nworker=1):
@@ -79,12 +90,14 @@ def drive(engine, config, *, solver, niter, block, gamma=1.0, adapt=True, reweig
 def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, block=16, verbose=-1, gamma=1.0,
               adapt=True, debug=False, reweight_goal=None, ignore=None, measure=None, measurefreq=1,
               thermal_ratio=0.1, inplace=False, parallel="nothread", print=-1, walkers=None, device=0,
-              hist_policy=0, comm=None, jit=0, **kwargs):
+              hist_policy=0, comm=None, jit=0, chain_burnin=None, **kwargs):
     """Drop-in for MCIntegration.integrate (main.jl:71-90) on one B200.
 
     `integrand` is a built-in device integrand (mcintegration_jl_b200.integrands) or CUDA C++ source
     (integrands.user_integrand, compiled by NVRTC into a kernel specialised to the problem) instead of a closure;
     `jit` = 0 auto / 1 always specialise with NVRTC / 2 ahead-of-time kernels only;
+    `chain_burnin` = extra unmeasured steps at the start of every chain (0 = the reference; default 1024 when a
+    block is cut into several chains; see DESIGN.md 5.3);
     `measure` is None or "bin_by_discrete".  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
     `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU).
     Everything else keeps the reference's meaning; `neval` is per iteration.
@@ -110,7 +123,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
         nevalperblock = (nevalperblock // W) * W
     spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
-                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit)
+                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W, chain_burnin))
     engine = CudaEngine(spec)
     try:
         engine.set_maps(*maps_from_config(config))  # warm restart: config=result.config (main.jl:95-97)

@@ -967,8 +967,9 @@ static void vegasmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker
   for (int i = 0; i < N + 1; ++i) pad[i] = padding_probability(c, i); /* :161 */
   double probability_ = c->reweight[N] * pad[N];                    /* :162 */
   for (int i = 0; i < N; ++i) { weights[i] = _weights[i]; probability_ += fabs(_weights[i]) * c->reweight[i] * pad[i]; }
-  for (uint64_t ne = 1; ne <= neval; ++ne) {                        /* :184 */
+  for (int64_t ne = 1 - (int64_t)h->p.chain_burnin; ne <= (int64_t)neval; ++ne) { /* :184; ne <= 0: extra burn-in (mcib200.h) */
     probability_ = vegasmc_change_variable(c, probability_, weights, _weights, pad, _pad); /* :186-188; single update */
+    if (ne < 1) continue;
     for (int i = 0; i < N; ++i) {                                   /* :198-211 */
       double f2 = fabs(weights[i]) * fabs(weights[i]) / probability(c, i);
       double wf2 = f2 * pad[i] / probability_;
@@ -977,7 +978,7 @@ static void vegasmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker
         for (int pos = 1; pos <= c->dof[i * c->nv + vi]; ++pos) var_accumulate(c, vi, pos + offset, wf2);
       }
     }
-    if (ne % (uint64_t)h->p.measurefreq == 0 && (double)ne >= (double)neval / 100) { /* :213 */
+    if ((uint64_t)ne % (uint64_t)h->p.measurefreq == 0 && (double)ne >= (double)neval / 100) { /* :213 */
       for (int i = 0; i < N; ++i) {
         c->visited[i] += fabs(weights[i] * pad[i] * c->reweight[i]) / probability_;
         relw[i] = weights[i] * pad[i] / probability_;
@@ -1078,13 +1079,13 @@ static int mcmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker, ui
   if (s.curr != c->ni && s.probability == 0.0) return MCI_ERR_MCMC_START;
   int nupdates = 2 * c->nv + 2;                              /* :117-120 */
   uint64_t nburnin = (uint64_t)floor((double)neval * h->p.thermal_ratio); /* :133 */
-  for (uint64_t i = 1; i <= neval + nburnin; ++i) {          /* :134 */
-    c->visited[s.curr] += 1;
+  for (int64_t i = 1 - (int64_t)h->p.chain_burnin; i <= (int64_t)(neval + nburnin); ++i) { /* :134; i <= 0: extra burn-in */
+    if (i >= 1) c->visited[s.curr] += 1;
     int u = orng_int(&c->rng, nupdates);                     /* :138 */
     if (u == 1) mcmc_change_integrand(c, &s);
     else if (u == 2) mcmc_swap_variable(c, &s);
     else mcmc_change_variable(c, &s);
-    if (i % (uint64_t)h->p.measurefreq == 0 && i >= nburnin) { /* :145 */
+    if (i >= 1 && (uint64_t)i % (uint64_t)h->p.measurefreq == 0 && (uint64_t)i >= nburnin) { /* :145 */
       if (s.curr != c->ni)
         for (int vi = 0; vi < c->nv; ++vi) {
           int offset = c->top[vi].offset;

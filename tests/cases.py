@@ -77,10 +77,11 @@ MEASURE_ID = {None: _abi.MEASURE_DEFAULT, "bin_by_discrete": _abi.MEASURE_BIN_BY
 
 
 def make_spec(name, solver, *, n_block=16, neval_per_block=4096, seed=1234, walkers=1, measurefreq=1,
-              thermal_ratio=0.1, hist_policy=0):
+              thermal_ratio=0.1, hist_policy=0, chain_burnin=0):
     c = case(name)
     cfg = mci.Configuration(seed=seed, **c["cfg"]())
     spec = mci.problem_from_config(cfg, c["f"], solver=SOLVER_ID[solver], measure_kind=MEASURE_ID[c.get("measure")],
                                    n_block=n_block, neval_per_block=neval_per_block, measurefreq=measurefreq,
-                                   walkers_per_block=walkers, thermal_ratio=thermal_ratio, hist_policy=hist_policy)
+                                   walkers_per_block=walkers, thermal_ratio=thermal_ratio, hist_policy=hist_policy,
+                                   chain_burnin=chain_burnin)
     return spec, cfg

@@ -165,6 +165,25 @@ def test_L1_chain_iteration(name, solver):
         gpu.close(); cpu.close()
 
 
+@pytest.mark.parametrize("name,solver", [("bubble", "vegasmc"), ("sphere2", "vegasmc"), ("bubble", "mcmc"), ("product4_d6", "mcmc")])
+def test_chain_burnin_parity(name, solver):
+    """mci_problem_t.chain_burnin: extra unmeasured steps before the reference's loop, same on the oracle"""
+    gpu, cpu, _ = _pair(name, solver, n_block=4, neval_per_block=96 * 100, walkers=96, chain_burnin=37)
+    try:
+        a, b = gpu.run_iteration(0), cpu.run_iteration(0)
+        _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
+        np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
+        assert np.array_equal(np.round(a.propose - b.propose, 6), np.zeros_like(a.propose))
+        # the measured part is unchanged in length: same normalisation count scale as without burn-in, more evaluations
+        g0, c0, _ = _pair(name, solver, n_block=4, neval_per_block=96 * 100, walkers=96)
+        try:
+            assert g0.run_iteration(0).neval < a.neval
+        finally:
+            g0.close(); c0.close()
+    finally:
+        gpu.close(); cpu.close()
+
+
 @pytest.mark.parametrize("name,solver", [("gauss10", "vegas"), ("sphere2", "vegas"), ("bubble", "vegas"),
                                           ("sphere2", "vegasmc"), ("sphere2", "mcmc")])
 def test_partition_is_invisible(name, solver):
@@ -245,6 +264,22 @@ def test_bubble_vegasmc_vs_lindhard():
     avg, std = res.mean[0], res.stdev[0]
     for i, q in enumerate(para.extQ):
         assert abs(avg[i] - para.lindhard(q)) < 10.0 * std[i] + 2e-4, (i, avg[i], std[i], para.lindhard(q))
+
+
+@pytest.mark.parametrize("solver,kw", [("vegas", {}), ("vegasmc", dict(walkers=4096)), ("mcmc", dict(walkers=4096))])
+def test_bubble_against_finite_temperature_exact(solver, kw):
+    """BASELINE C4 at size: example/bubble.jl against the EXACT finite-temperature polarisation (Maldague average of the
+    bubble.jl Lindhard function), 5 sigma at sigma ~ 1e-4 — a far sharper pin than the reference's own 10 sigma against
+    the T=0 value.  The chain solvers run the GPU decomposition (4096 chains per block, default burn-in)."""
+    from mcintegration_jl_b200.integrands import lindhard_finite_temperature
+    c = case("bubble")
+    para = c["para"]
+    res = mci.integrate(c["f"], solver=solver, measure="bin_by_discrete", neval=2e7, niter=10, seed=99, **kw, **c["cfg"]())
+    avg, std = res.mean[0], res.stdev[0]
+    for i, q in enumerate(para.extQ):
+        ex = lindhard_finite_temperature(para, q)
+        assert abs(avg[i] - ex) < 5.0 * std[i], (solver, i, avg[i], std[i], ex)
+        assert std[i] < 5e-4
 
 
 def test_error_paths():

@@ -50,6 +50,23 @@ def test_mcmc_known_answers(name):
     check(res, c["expect"])
 
 
+@pytest.mark.parametrize("solver", ["vegasmc", "mcmc"])
+def test_many_short_chains_with_burnin(solver):
+    """The GPU decomposition — many short chains per block — on the oracle: 64 chains x 97 measured steps each with
+    200 extra burn-in steps (chain_burnin) still reproduces the known answer (sphere volumes)."""
+    from mcintegration_jl_b200 import _abi
+    from mcintegration_jl_b200.main import drive
+    from cases import make_spec
+    from oracle_lib import OracleEngine
+    spec, cfg = make_spec("sphere2", solver, n_block=16, neval_per_block=64 * 97, walkers=64, chain_burnin=200, seed=77)
+    eng = OracleEngine(spec)
+    try:
+        res = drive(eng, cfg, solver=solver, niter=10, block=16)
+    finally:
+        eng.close()
+    check(res, case("sphere2")["expect"])
+
+
 def test_stateful_shift_form_agrees():
     """The reference's VEGAS loop updates prob by the ratio form of shift! (sampler.jl:383-384); the device
     evaluates the equivalent create! form 1/(N*dx).  Both oracle modes must agree to rounding."""
