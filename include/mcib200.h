@@ -102,8 +102,14 @@ enum mci_integrand_id {
 /* `measure` kwarg (main.jl:35-37, 83).  Default = obs[i] += relw[i]. */
 enum mci_measure_kind {
   MCI_MEASURE_DEFAULT = 0,
-  MCI_MEASURE_BIN_BY_DISCRETE = 1 /* obs[0][Ext-lower] += relw[0]; example/bubble.jl:81-84.
+  MCI_MEASURE_BIN_BY_DISCRETE = 1, /* obs[0][Ext-lower] += relw[0]; example/bubble.jl:81-84.
                                      The binning leaf is the LAST leaf of the problem.      */
+  MCI_MEASURE_USER = 2 /* the caller's measure(x, obs, relw, config) / measure(idx, x, obs, relw, config) as CUDA C++
+                          source in user_source (compiled by NVRTC, like MCI_F_USER):
+                            template <class XA> __device__ void mci_user_measure(const XA &X, double *obs,
+                                                               const double *relw, const double *userdata);
+                          obs = the flattened config.observable (integrand i at the running offset of obs_len);
+                          relw[i] = relative weight of integrand i (mcmc: zero except the current integrand)      */
 };
 
 /* one leaf map (Continuous ctor kwargs variable.jl:137, Discrete ctor :299) */

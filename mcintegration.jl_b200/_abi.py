@@ -28,7 +28,7 @@ ERR_MCMC_START = -7
 
 SOLVER_VEGAS, SOLVER_VEGASMC, SOLVER_MCMC = 0, 1, 2
 LEAF_CONTINUOUS, LEAF_DISCRETE = 0, 1
-MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE = 0, 1
+MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE, MEASURE_USER = 0, 1, 2
 JIT_AUTO, JIT_ON, JIT_OFF = 0, 1, 2
 HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
 

@@ -203,7 +203,8 @@ class ProblemSpec:
 def problem_from_config(config: Configuration, integrand, *, solver: int, measure_kind: int, n_block: int,
                         neval_per_block: int, measurefreq: int = 1, walkers_per_block: int = 1,
                         thermal_ratio: float = 0.1, device: int = 0, hist_policy: int = 0,
-                        default_neighbor: bool = False, jit: int = 0, chain_burnin: int = 0) -> ProblemSpec:
+                        default_neighbor: bool = False, jit: int = 0, chain_burnin: int = 0,
+                        measure_source: str | None = None) -> ProblemSpec:
     leaves = []
     for L in config.leaves():
         if isinstance(L, Continuous):
@@ -211,6 +212,7 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
                                alpha=L.alpha))
         else:
             leaves.append(dict(kind=_abi.LEAF_DISCRETE, nbins=L.nbins, adapt=L.adapt, lower_i=L.lower, alpha=L.alpha))
+    sources = [x for x in (getattr(integrand, "source", None), measure_source) if x]
     assert integrand.n_integrand == config.N, (
         f"integrand {integrand.name} returns {integrand.n_integrand} values but dof has {config.N} rows")
     return ProblemSpec(
@@ -220,7 +222,7 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
         neighbor=None if default_neighbor else config.neighbor, userdata=list(integrand.userdata),
         n_block=n_block, neval_per_block=neval_per_block, seed=config.seed, measurefreq=measurefreq,
         walkers_per_block=walkers_per_block, thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit,
-        user_source=getattr(integrand, "source", None), chain_burnin=chain_burnin)
+        user_source="\n".join(sources) if sources else None, chain_burnin=chain_burnin)
 
 
 def maps_from_config(config: Configuration):

@@ -202,7 +202,7 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   int rc = jit_compile(P, h->user_source.c_str(), exprs, ks, err);
   h->chain_maxt = 1024;
   if (rc != 0) {
-    if (h->jit_mode == MCI_JIT_AUTO && P.fid != MCI_F_USER) { /* auto: the ahead-of-time kernel serves as well */
+    if (h->jit_mode == MCI_JIT_AUTO && P.fid != MCI_F_USER && P.measure_kind != MCI_MEASURE_USER) { /* auto: the ahead-of-time kernel serves as well */
       h->use_jit = false;
       return resolve_kernel(h, kind, mode, threads, exact);
     }
@@ -514,6 +514,8 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
         BAIL(MCI_ERR_INVALID, "bin-by-discrete measure needs a Discrete last leaf and obs_len[0] >= its size");
       if (p->solver != MCI_SOLVER_VEGAS && E.nbins > CHAIN_MAX_BINNED_OBS)
         BAIL(MCI_ERR_UNSUPPORTED, "bin-by-discrete measure of the chain solvers keeps at most %d bins", CHAIN_MAX_BINNED_OBS);
+    } else if (p->measure_kind == MCI_MEASURE_USER) {
+      if (!p->user_source || !*p->user_source) BAIL(MCI_ERR_INVALID, "measure_kind = MCI_MEASURE_USER needs user_source defining mci_user_measure");
     } else if (p->measure_kind != MCI_MEASURE_DEFAULT) BAIL(MCI_ERR_INVALID, "unknown measure kind %d", p->measure_kind);
   }
   /* neighbor graph: configuration.jl:201-209 default, or the caller's CSR */
@@ -560,7 +562,7 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
    * what the JIT would build */
   h->jit_mode = p->jit;
   if (const char *e = getenv("MCIB200_JIT")) h->jit_mode = atoi(e) == 0 ? MCI_JIT_OFF : MCI_JIT_ON;
-  h->use_jit = p->integrand_id == MCI_F_USER || h->jit_mode == MCI_JIT_ON ||
+  h->use_jit = p->integrand_id == MCI_F_USER || p->measure_kind == MCI_MEASURE_USER || h->jit_mode == MCI_JIT_ON ||
                (h->jit_mode == MCI_JIT_AUTO && (double)p->n_block * (double)p->neval_per_block >= 16777216.0);
 #undef BAIL
 

@@ -300,6 +300,16 @@ __device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainAr
 #endif
 /* bin-by-Discrete observables of the chain kernels are kept in this many per-thread accumulators (mci_create checks) */
 constexpr int CHAIN_MAX_BINNED_OBS = 8;
+/* per-thread observable accumulators: one per integrand (default measure), CHAIN_MAX_BINNED_OBS for the single binned
+ * integrand, the whole flattened observable for a user measure (JIT builds only: its length is a compile-time constant) */
+template <int NI>
+struct ChainNobs {
+#ifdef MCI_JIT
+  static constexpr int value = JitProblem::measure_kind == MCI_MEASURE_USER ? JitProblem::obs_total : (NI > 1 ? NI : CHAIN_MAX_BINNED_OBS);
+#else
+  static constexpr int value = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+#endif
+};
 #define PA_IDX(P, u, i, j) (((u) * (P).nd + (i)) * (P).pa_dim + (j))
 
 /* ------------------------------------------------------------------------------------------ */
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
 
   /* per-thread statistics.  Default measure: one accumulator per integrand; bin-by-Discrete: one per bin, selected
    * with a short compare chain so that the accumulators stay in registers */
-  constexpr int NOBS = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+  constexpr int NOBS = ChainNobs<NI>::value;
   double obs[NOBS];
 #pragma unroll
   for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
@@ -424,17 +434,20 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
     __syncwarp();
     /* measurement: montecarlo.jl:213-232 */
     if (active && ne >= 1 && (P.measurefreq == 1 || ((uint64_t)ne % (uint64_t)P.measurefreq) == 0) && (double)ne >= meas_from) {
+      double relw_all[NI];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         visited[i] += __ddiv_rn(fabs(__dmul_rn(__dmul_rn(weights[i], pad[i]), rw[i])), prob_cur);
         const double relw = __ddiv_rn(__dmul_rn(weights[i], pad[i]), prob_cur);
-        if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[i] += relw;
-        else if (i == 0) {
+        relw_all[i] = relw;
+        if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[i < NOBS ? i : 0] += relw;
+        else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE && i == 0) {
           const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
 #pragma unroll
           for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
         }
       }
+      if (P.measure_kind == MCI_MEASURE_USER) UserMeasureT<0>::call(X, obs, relw_all, P.userdata);
       normalization += __ddiv_rn(pad[N], prob_cur);
       visited[N] += __ddiv_rn(__dmul_rn(rw[N], pad[N]), prob_cur);
     }
@@ -448,11 +461,15 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   __syncthreads();
   if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
-  } else {
+    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+  } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
 #pragma unroll
     for (int o = 0; o < NOBS; ++o)
       if (o < P.obs_len[0]) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[P.obs_off[0] + o] = t; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o)
+      if (o < P.obs_total) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[o] = t; }
   }
   { double t = cta_sum(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
 #pragma unroll
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
 #pragma unroll
   for (int i = 0; i <= N; ++i) rw[i] = A.reweight[i];
 
-  constexpr int NOBS = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+  constexpr int NOBS = ChainNobs<NI>::value;
   double obs[NOBS];
 #pragma unroll
   for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
@@ -724,11 +741,16 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
         const double relw = __ddiv_rn(weight, prob_cur);
         if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) obs[i] += (i == curr) ? relw : 0.0;
-        } else {
+          for (int i = 0; i < N; ++i) obs[i < NOBS ? i : 0] += (i == curr) ? relw : 0.0;
+        } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
           const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
 #pragma unroll
           for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
+        } else { /* measure(idx, x, obs, relw, config): a measure is linear in relw, so pass zero for the other integrands */
+          double relw_all[NI];
+#pragma unroll
+          for (int i = 0; i < N; ++i) relw_all[i] = (i == curr) ? relw : 0.0;
+          UserMeasureT<0>::call(X, obs, relw_all, P.userdata);
         }
       }
     }
@@ -741,11 +763,15 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   __syncthreads();
   if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
-  } else {
+    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+  } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
 #pragma unroll
     for (int o = 0; o < NOBS; ++o)
       if (o < P.obs_len[0]) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[P.obs_off[0] + o] = t; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o)
+      if (o < P.obs_total) { double t = cta_sum(obs[o], S.sred); if (tid == 0) out[o] = t; }
   }
   { double t = cta_sum(normalization, S.sred); if (tid == 0) out[P.obs_total] = t; }
 #pragma unroll

@@ -92,6 +92,18 @@ using Problem = DevProblem;
 #define MCI_UNROLL_LAYOUT
 #endif
 
+/* MCI_MEASURE_USER: the `measure` callback of integrate (main.jl:35-37) as CUDA C++ source.  The primary template does
+ * nothing; a JIT program whose user_source defines
+ *   template <class XA> __device__ void mci_user_measure(const XA &X, double *obs, const double *relw, const double *userdata);
+ * specialises UserMeasureT<0> to forward to it (mci_jit.cu).  obs = this thread's accumulators, laid out like
+ * config.observable flattened (integrand i at obs_off[i], obs_len[i] entries); relw[i] = relative weight of integrand i
+ * (mcmc: zero except for the current integrand — a measure is linear in relw). */
+template <int K>
+struct UserMeasureT {
+  template <class XA>
+  __device__ __forceinline__ static void call(const XA &, double *, const double *, const double *) {}
+};
+
 /* ---------------------------------------------------------------------------------------- */
 /* Philox4x32-10 (Salmon et al. 2011).  Stream layout (DESIGN.md "RNG"):                     */
 /*   key = (seed_lo, seed_hi ^ iter*0x9E3779B1), counter = (idx_lo, idx_hi, pair, block)     */

@@ -146,11 +146,19 @@ int jit_compile(const DevProblem &P, const char *user_source, const std::vector<
   std::string top;
   top += defines; /* e.g. "#define MCI_CHAIN_MAXT 512\n" */
   top += "#define MCI_JIT 1\n#include \"mci_vegas.cuh\"\n#include \"mci_chain.cuh\"\n";
-  if (P.fid == MCI_F_USER) {
-    if (!user_source || !*user_source) { err = "integrand_id = MCI_F_USER needs mci_problem_t.user_source"; return -1; }
+  const bool user_f = P.fid == MCI_F_USER, user_m = P.measure_kind == MCI_MEASURE_USER;
+  if (user_f || user_m) {
+    if (!user_source || !*user_source) { err = "a user integrand / user measure needs mci_problem_t.user_source"; return -1; }
     top += "#line 1 \"user_source\"\n";
     top += user_source;
-    top += "\n#line 1 \"mci_jit_glue\"\nnamespace mci {\ntemplate <> struct Integrand<MCI_F_USER> {\n"
+    top += "\n#line 1 \"mci_jit_glue\"\n";
+  }
+  if (user_m)
+    top += "namespace mci {\ntemplate <> struct UserMeasureT<0> {\n  template <class XA>\n"
+           "  __device__ __forceinline__ static void call(const XA &X, double *obs, const double *relw, const double *userdata) "
+           "{ ::mci_user_measure(X, obs, relw, userdata); }\n};\n}\n";
+  if (user_f) {
+    top += "namespace mci {\ntemplate <> struct Integrand<MCI_F_USER> {\n"
            "  static constexpr int NI = JitProblem::ni;\n"
            "  template <int MAXD, class XA, bool EXACT = false>\n"
            "  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) { ::mci_user_integrand(X, P.userdata, w); }\n"

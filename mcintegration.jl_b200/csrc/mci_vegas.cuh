@@ -387,8 +387,15 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
         if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
           for (int i = 0; i < NI; ++i) acc[P.obs_off[i]] += w[i] * pad[i] * jac;
-        } else { /* obs[0][Ext - lower] += relw[0]; the binning leaf is the last leaf, slot 1 (example/bubble.jl:81-84) */
+        } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
+          /* obs[0][Ext - lower] += relw[0]; the binning leaf is the last leaf, slot 1 (example/bubble.jl:81-84) */
           acc[P.obs_off[0] + bin[P.leaf[P.nleaf - 1].base]] += w[0] * pad[0] * jac;
+        } else { /* the caller's measure(x, obs, relw, config) (main.jl:35-37), compiled from source */
+          double relw[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) relw[i] = w[i] * pad[i] * jac;
+          FlatX X{x, &P};
+          UserMeasureT<0>::call(X, acc, relw, P.userdata);
         }
         cnt++;
       }

@@ -37,6 +37,21 @@ def user_integrand(source: str, n_integrand: int = 1, userdata: Sequence[float] 
     return Integrand(name, _abi.F_USER, int(n_integrand), tuple(float(x) for x in userdata), "user source (NVRTC)", source)
 
 
+@dataclass(frozen=True)
+class UserMeasure:
+    """The `measure` kwarg of integrate (main.jl:35-37) as CUDA C++ source defining
+
+        template <class XA> __device__ void mci_user_measure(const XA &X, double *obs, const double *relw, const double *userdata);
+
+    obs = the flattened config.observable (integrand i at the running offset of the observable lengths);
+    relw[i] = relative weight of integrand i (under :mcmc zero except for the current integrand)."""
+    source: str
+
+
+def user_measure(source: str) -> UserMeasure:
+    return UserMeasure(source)
+
+
 gauss_nd = Integrand("gauss_nd", _abi.F_GAUSS_ND, 1, doc="(2π)^(-d/2) exp(-|x|²/2); one Continuous pool, dof=[[d]]")
 log_over_sqrt = Integrand("log_over_sqrt", _abi.F_LOG_OVER_SQRT, 1, doc="log(x)/√x (test/montecarlo.jl:129-134)")
 sphere1 = Integrand("sphere1", _abi.F_SPHERE1, 1, doc="x₁²+x₂²<1 (test/montecarlo.jl:4-9)")

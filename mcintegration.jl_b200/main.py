@@ -12,7 +12,7 @@ from .statistics import Result, mean_std, report
 
 _SOLVERS = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC, "mcmc": _abi.SOLVER_MCMC}
 _MEASURES = {None: _abi.MEASURE_DEFAULT, "default": _abi.MEASURE_DEFAULT,
-             "bin_by_discrete": _abi.MEASURE_BIN_BY_DISCRETE}
+             "bin_by_discrete": _abi.MEASURE_BIN_BY_DISCRETE, "user": _abi.MEASURE_USER}
 
 # concurrent chains per block for the chain solvers when the caller does not say (SURVEY §7 hard part 3), and the
 # shortest chain the default will cut a block into: a chain starts from a draw of the VEGAS map, not of the target
@@ -98,7 +98,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
     `jit` = 0 auto / 1 always specialise with NVRTC / 2 ahead-of-time kernels only;
     `chain_burnin` = extra unmeasured steps at the start of every chain (0 = the reference; default 1024 when a
     block is cut into several chains; see DESIGN.md 5.3);
-    `measure` is None or "bin_by_discrete".  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
+    `measure` is None, "bin_by_discrete" or integrands.user_measure(source).  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
     `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU).
     Everything else keeps the reference's meaning; `neval` is per iteration.
     """
@@ -109,6 +109,10 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
         raise ValueError(f"Solver {solver} is not supported!")  # main.jl:263
     print_level = max(print, verbose)
     f = resolve(integrand)
+    from .integrands import UserMeasure
+    measure_source = None
+    if isinstance(measure, UserMeasure):  # measure(x, obs, relw, config) as CUDA C++ source
+        measure_source, measure = measure.source, "user"
     if config is None:
         config = Configuration(**kwargs)
     for i, m in enumerate(config.maxdof):
@@ -123,7 +127,8 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
         nevalperblock = (nevalperblock // W) * W
     spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
-                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W, chain_burnin))
+                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W, chain_burnin),
+                               measure_source=measure_source)
     engine = CudaEngine(spec)
     try:
         engine.set_maps(*maps_from_config(config))  # warm restart: config=result.config (main.jl:95-97)

@@ -104,8 +104,8 @@ def test_L1_hist_policies(name, policy):
     gpu, cpu, _ = _pair(name, "vegas", neval_per_block=3000, hist_policy=policy)
     try:
         # a policy that does not fit in shared memory (bubble: 8 warps x 32 KB) or that the kernel of this layout does not
-        # implement (striped copies: pool kernel only) falls back to the shared CTA copy
-        assert gpu.launch_info()["hist_mode"] in (policy, _abi.HIST_SMEM_ATOMIC)
+        # implement (striped copies: pool kernel only) falls back to the automatic choice (shared CTA copy or L2 REDs)
+        assert gpu.launch_info()["hist_mode"] in (policy, _abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED)
         cpu.run_iteration(0); cpu.refine(); _sync_maps(cpu, gpu)
         _assert_stats(gpu.run_iteration(1), cpu.run_iteration(1))
     finally:

@@ -29,6 +29,36 @@ template <class XA> __device__ void mci_user_integrand(const XA &X, const double
 """
 
 
+# test/montecarlo.jl:52-92 (Sphere3): two integrands, obs = [0.0, [0.0, 0.0]], measure doubles the second entry
+SPHERE3_F = """
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  const double r2 = X(0, 1) * X(0, 1) + X(0, 2) * X(0, 2);
+  w[0] = r2 < 1.0 ? 1.0 : 0.0;
+  w[1] = r2 + X(0, 3) * X(0, 3) < 1.0 ? 1.0 : 0.0;
+}
+"""
+SPHERE3_M = """
+template <class XA> __device__ void mci_user_measure(const XA &X, double *obs, const double *relw, const double *userdata) {
+  obs[0] += relw[0];
+  obs[1] += relw[1];
+  obs[2] += relw[1] * 2.0;
+}
+"""
+# test/montecarlo.jl:173-185 (TestComplex2): (x, i x^2) as two real integrands + a measure that files re / im parts
+COMPLEX2_F = """
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  w[0] = X(0, 1);
+  w[1] = X(0, 1) * X(0, 1);
+}
+"""
+COMPLEX2_M = """
+template <class XA> __device__ void mci_user_measure(const XA &X, double *obs, const double *relw, const double *userdata) {
+  obs[0] += relw[0];   /* Re obs1 */
+  obs[3] += relw[1];   /* Im obs2; obs = [re1, im1, re2, im2] */
+}
+"""
+
+
 def _check(spec):
     lib = _abi.load_library()
     p, keep = spec.to_ctypes()
@@ -105,6 +135,45 @@ def test_user_integrand_end_to_end(solver):
                         var=(mci.Continuous(0.0, 1.0), mci.Continuous(0.0, 2.0), mci.Discrete(1, 4)), dof=[[1, 1, 0], [0, 0, 1]])
     for k, ex in enumerate((1.0, 10.0)):
         assert abs(res.mean[k] - ex) < 7 * res.stdev[k] + 1e-12, (k, res.mean[k], res.stdev[k])
+
+
+def test_user_measure_compiles():
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[2], [3]], obs=[0.0, [0.0, 0.0]], neighbor=[(1, 3), (1, 2)], seed=3)
+    f = I.user_integrand(SPHERE3_F, 2)
+    for solver in (_abi.SOLVER_VEGAS, _abi.SOLVER_VEGASMC, _abi.SOLVER_MCMC):
+        spec = mci.problem_from_config(cfg, f, solver=solver, measure_kind=_abi.MEASURE_USER, n_block=16, neval_per_block=640,
+                                       walkers_per_block=64 if solver else 1, measure_source=SPHERE3_M)
+        rc, log = _check(spec)
+        assert rc == 0, log
+    spec = mci.problem_from_config(cfg, f, solver=0, measure_kind=_abi.MEASURE_USER, n_block=16, neval_per_block=640)
+    rc, log = _check(spec)  # user measure requested but the source does not define it
+    assert rc == _abi.ERR_UNSUPPORTED and "mci_user_measure" in log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+def test_sphere3_with_user_measure(solver):
+    """test/montecarlo.jl:52-92,272,307,350: check_vector(Sphere3(...), [pi/4, [4pi/3/8, 4pi/3/4]])"""
+    res = mci.integrate(I.user_integrand(SPHERE3_F, 2), measure=I.user_measure(SPHERE3_M), solver=solver, neval=4e5, niter=10,
+                        seed=8, walkers=64, var=mci.Continuous(0.0, 1.0), dof=[[2], [3]], obs=[0.0, [0.0, 0.0]],
+                        neighbor=[(1, 3), (1, 2)])
+    want = [[math.pi / 4], [4 * math.pi / 3 / 8, 4 * math.pi / 3 / 4]]
+    for k in range(2):
+        m, s = np.ravel(res.mean[k]), np.ravel(res.stdev[k])
+        for mm, ss, ee in zip(m, s, want[k]):
+            assert abs(mm - ee) < 7 * ss, (solver, k, mm, ss, ee)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+def test_complex2_as_real_pairs(solver):
+    """test/montecarlo.jl:173-185,296,329,377: check_complex(TestComplex2, [0.5, i/3]) with complex numbers carried as
+    (re, im) pairs: observables [[re1, im1], [re2, im2]]"""
+    res = mci.integrate(I.user_integrand(COMPLEX2_F, 2), measure=I.user_measure(COMPLEX2_M), solver=solver, neval=2e5, niter=10,
+                        seed=9, walkers=64, var=mci.Continuous(0.0, 1.0), dof=[[1], [1]], obs=[[0.0, 0.0], [0.0, 0.0]])
+    (re1, im1), (re2, im2) = res.mean[0], res.mean[1]
+    assert abs(re1 - 0.5) < 7 * res.stdev[0][0] and im1 == 0.0
+    assert abs(im2 - 1.0 / 3) < 7 * res.stdev[1][1] and re2 == 0.0
 
 
 @pytest.mark.gpu
