@@ -323,6 +323,10 @@ int plan(mci_handle_t *h) {
       if (extra > SMEM_MAX) continue;
       int policy_mode = pick_hist(nwarp, extra, false);
       if (policy_mode == HIST_WARP_PRIVATE) policy_mode = HIST_SMEM_ATOMIC;
+      /* mcmc keeps its shared histogram as u32 counters: a bin can receive at most T * steps * slots increments */
+      if (p.solver == MCI_SOLVER_MCMC && policy_mode == HIST_SMEM_ATOMIC &&
+          (double)T * ((double)(p.neval_per_block / W) * (1.0 + P.thermal_ratio) + 1.0) * (double)P.n_draw >= 4.0e9)
+        policy_mode = HIST_GLOBAL_RED;
       const int mis = h->maps_in_smem;
       const size_t smem = (mis ? map_bytes : 0) + hist_smem(policy_mode, nwarp) + extra;
       int occ = 0;

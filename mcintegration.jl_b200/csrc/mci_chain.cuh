@@ -284,11 +284,16 @@ __device__ __forceinline__ ChainSmem chain_setup(const Problem &P, const ChainAr
   return S;
 }
 
+/* COUNTS: the shared histogram holds u32 counters (MCMC: every contribution is exactly 1.0, variable.jl:196-200 with
+ * weight = 1.0 from mcmc/montecarlo.jl:148-155, so a native ATOMS.ADD counter is the same number as the fp64 sum, bit
+ * for bit, without the LDS/DADD/CAS loop and its ~21 shared-memory wavefronts per update) */
+template <bool COUNTS>
 __device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainArgs &A, const ChainSmem &S) {
   if (A.hist_mode == HIST_SMEM_ATOMIC) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
-    for (int i = threadIdx.x; i < P.hist_len; i += blockDim.x) out[i] = S.shist[i];
+    const unsigned int *cnt = reinterpret_cast<const unsigned int *>(S.shist);
+    for (int i = threadIdx.x; i < P.hist_len; i += blockDim.x) out[i] = COUNTS ? (double)cnt[i] : S.shist[i];
   }
 }
 
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   double *prop_o = out + P.obs_total + 1 + P.nd, *acc_o = prop_o + pa_len;
   for (int i = tid; i < pa_len; i += blockDim.x) { prop_o[i] = (double)s_prop[i]; acc_o[i] = (double)s_acc[i]; }
   { double t = cta_sum((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
-  chain_flush_hist(P, A, S);
+  chain_flush_hist<false>(P, A, S);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -735,7 +740,11 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
             for (int pos = 1; pos <= cd; ++pos)
               for (int k = 0; k < P.top_nleaf[v]; ++k) {
                 const DevLeaf &L = P.leaf[P.top_first[v] + k];
-                if (L.adapt) chain_hist_add(hmode, S.hist_saddr + 8u * (uint32_t)L.hist_off, S.ghist + L.hist_off, W.gidx[frow(L, pos) * W.T], 1.0);
+                if (L.adapt) {
+                  const int bin = W.gidx[frow(L, pos) * W.T];
+                  if (hmode == HIST_SMEM_ATOMIC) atomicAdd(reinterpret_cast<unsigned int *>(S.shist) + L.hist_off + bin, 1u); /* ATOMS.ADD */
+                  else atomicAdd(S.ghist + L.hist_off + bin, 1.0);
+                }
               }
           }
         const double relw = __ddiv_rn(weight, prob_cur);
@@ -780,7 +789,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   double *prop_o = out + P.obs_total + 1 + P.nd, *acc_o = prop_o + pa_len;
   for (int i = tid; i < pa_len; i += blockDim.x) { prop_o[i] = (double)s_prop[i]; acc_o[i] = (double)s_acc[i]; }
   { double t = cta_sum((double)neval, S.sred); if (tid == 0) out[stat_len - 1] = t; }
-  chain_flush_hist(P, A, S);
+  chain_flush_hist<true>(P, A, S);
 }
 
 }  // namespace mci
