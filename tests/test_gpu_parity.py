@@ -303,3 +303,65 @@ def test_error_paths():
     with pytest.raises(MCIError):
         eng.refine()  # nothing to refine yet
     eng.close()
+
+
+# ---- edge cases of the layout / sizes (GPU against the oracle) -------------------------------------------------------
+def _edge_spec(solver, var, dof, f, *, obs=None, neighbor=None, n_block=4, npb=3000, walkers=1, measurefreq=1, measure=None):
+    cfg = mci.Configuration(var=var, dof=dof, seed=321, obs=obs, neighbor=neighbor)
+    from cases import SOLVER_ID, MEASURE_ID
+    return mci.problem_from_config(cfg, f, solver=SOLVER_ID[solver], measure_kind=MEASURE_ID[measure], n_block=n_block,
+                                   neval_per_block=npb, walkers_per_block=walkers, measurefreq=measurefreq)
+
+
+EDGE = {
+    # Discrete variable with a single value: changeVariable skips it (vegas_mc/updates.jl:52-55, mcmc/updates.jl:80-83)
+    "single_value_discrete": lambda s: _edge_spec(s, (mci.Continuous(0.0, 1.0), mci.Discrete(3, 3)), [[2, 1]],
+                                                  mci.integrands.x2_plus_y2, walkers=32, npb=32 * 60),
+    # a coarse hand grid (3 increments) and a learning rate far from the default
+    "coarse_grid": lambda s: _edge_spec(s, mci.Continuous(0.0, 1.0, grid=[0.0, 0.1, 0.4, 1.0], alpha=0.5), [[2]],
+                                        mci.integrands.sphere1, walkers=32, npb=32 * 60),
+    # the largest pool the device supports (24 slots) with padding between integrands of different dof
+    "pool24_padding": lambda s: _edge_spec(s, mci.Continuous(0.0, 1.0), [[24]] * 4, mci.integrands.product4(), walkers=32, npb=32 * 40),
+    # non-adaptive variables: no histogram at all
+    "no_adapt": lambda s: _edge_spec(s, mci.Continuous(0.0, 1.0, adapt=False), [[2], [3]], mci.integrands.sphere2, walkers=32,
+                                     npb=32 * 60),
+    # measure every 7th step only
+    "measurefreq7": lambda s: _edge_spec(s, mci.Continuous(-1.0, 1.0), [[2], [3], [4]], mci.integrands.hypersphere3, walkers=32,
+                                         npb=32 * 70, measurefreq=7),
+}
+
+
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+@pytest.mark.parametrize("name", sorted(EDGE))
+def test_edge_layouts(name, solver):
+    if name == "pool24_padding" and solver == "vegas":
+        pytest.skip("covered by product4 in VEGAS_CASES")
+    spec = EDGE[name](solver)
+    gpu, cpu = mci.CudaEngine(spec), OracleEngine(spec)
+    try:
+        for it in range(2):
+            a, b = gpu.run_iteration(it), cpu.run_iteration(it)
+            _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
+            np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
+            assert np.array_equal(np.round(a.propose - b.propose, 6), np.zeros_like(a.propose))
+            if spec.solver != _abi.SOLVER_VEGAS:
+                gpu.reweight(1.0); cpu.reweight(1.0)
+            cpu.refine(); _sync_maps(cpu, gpu)
+    finally:
+        gpu.close(); cpu.close()
+
+
+def test_warm_restart_like_the_reference():
+    """test/bubble.jl:104-113: integrate, then integrate again with config=result.config (trained maps), niter=1, block=64"""
+    c = case("bubble")
+    cfg = mci.Configuration(seed=3, **c["cfg"]())
+    r1 = mci.integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8, config=cfg)
+    g1 = r1.config.var[0].grid.copy()
+    assert not np.allclose(np.diff(g1), np.diff(g1)[0])  # the map was trained
+    r2 = mci.integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e6, block=64, niter=1, config=r1.config)
+    from mcintegration_jl_b200.integrands import lindhard_finite_temperature
+    for i, q in enumerate(c["para"].extQ):
+        assert abs(r2.mean[0][i] - lindhard_finite_temperature(c["para"], q)) < 7 * r2.stdev[0][i]
+    o1 = oracle_integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8,
+                          config=mci.Configuration(seed=3, **c["cfg"]()))
+    np.testing.assert_allclose(g1, o1.config.var[0].grid, rtol=1e-7, atol=1e-12)  # g1: before the restart trained it further
