@@ -147,10 +147,20 @@ __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K
     cnt++;
   }
   if (HMODE != HIST_NONE && (!GUARD || active)) {
+    /* hist[bin_p] += (|w_i| jac)^2 for every integrand i with p < dof_i.  When every integrand uses every slot (EXACT)
+     * the contributions to a slot are summed first: one update per slot instead of one per (integrand, slot) */
+    constexpr int NPASS = EXACT ? 1 : NI;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const double a = fabs(w[i]) * jac;
-      const double w2 = a * a;
+    for (int i = 0; i < NPASS; ++i) {
+      double w2;
+      if (EXACT) {
+        w2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NI; ++k) { const double a = fabs(w[k]) * jac; w2 += a * a; }
+      } else {
+        const double a = fabs(w[i]) * jac;
+        w2 = a * a;
+      }
       const int di = EXACT ? MAXD : P.dof[i * P.nv];
       if constexpr (HMODE == HIST_SMEM_STRIPED && MCI_HIST_BATCH > 1) {
 #pragma unroll
@@ -168,8 +178,6 @@ __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K
   }
 }
 
-/* resident CTAs per SM the register allocation aims at: 64 registers per thread up to 12 slots (and always for the
- * 1024-thread striped variant), 80 up to 16 slots, 128 beyond — x[] and bin[] of a sample live in registers */
 template <int MAXD, int THREADS>
 struct PoolMinBlocks {
   static constexpr int value = THREADS >= 1024 ? 1 : (MAXD <= 12 ? 1024 / THREADS : (MAXD <= 16 ? 768 / THREADS : 512 / THREADS));
