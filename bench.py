@@ -250,9 +250,11 @@ def run_ours(args):
         # algorithmic HBM bytes per launch (DESIGN.md "Roofline"): read the staged map image once per CTA (L2 hits after
         # the first), write one histogram partial per CTA and (obs, count) per tile
         alg_bytes = 8.0 * (2 * eng.hist_len + eng.hist_len * info["grid"] + info["tiles_per_block"] * BLOCKS_PER_GPU * 2)
-        traffic = None
+        traffic, ncu = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_fill_ncu.json")))["dram_bytes_per_launch"]
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_fill_ncu.json")))
+            traffic = ncu["dram_bytes_per_launch"]
+            ncu = {k: ncu[k] for k in ("issue_active_pct", "smem_pipe_busy_frac", "warp_instructions_per_sample_warp", "source") if k in ncu}
         except Exception:
             pass
         cb = None
@@ -275,6 +277,7 @@ def run_ours(args):
                                     f"samples per launch / {fill_ms:.3f} ms fill kernel (CUDA events, library stream); peak = "
                                     "DFMA probe measured in this run (mci_fp64_peak; MEASURED_PEAKS.json has no fp64 figure)",
                             "fill_ms": fill_ms, "fill_samples_per_s": fill_rate,
+                            "limiters_ncu": ncu,  # what actually binds (offline ncu capture of the same launch): issue slots + shared-memory wavefronts
                             "hbm": {"achieved_gbs": alg_bytes / (fill_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                     "frac": alg_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured" if peaks else "fallback",
                                     "algorithmic_bytes_per_launch": alg_bytes}},
