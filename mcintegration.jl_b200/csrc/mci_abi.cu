@@ -262,10 +262,10 @@ int plan(mci_handle_t *h) {
       size_t hs = hist_smem(mode, nwarp);
       /* 16 bank-striped copies of the histogram, one 1024-thread CTA per SM, when they fit */
       const size_t red_s = (size_t)(POOL_THREADS_STRIPED / 32) * (P.ni + 1) * 8;
-      const bool striped_fits = map_bytes + (size_t)STRIPE * hist_bytes + red_s <= SMEM_MAX;
+      const bool striped_fits = (size_t)POOL_MAP_REP * map_bytes + (size_t)STRIPE * hist_bytes + red_s <= SMEM_MAX;
       if (P.any_adapt && striped_fits && (p.hist_policy == MCI_HIST_SMEM_STRIPED || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_STRIPED))) {
         mode = HIST_SMEM_STRIPED; threads = POOL_THREADS_STRIPED; nwarp = threads / 32; red = red_s;
-        hs = (size_t)STRIPE * hist_bytes; h->maps_in_smem = 1;
+        hs = (size_t)STRIPE * hist_bytes + (size_t)(POOL_MAP_REP - 1) * map_bytes; h->maps_in_smem = 1;
       }
       if (h->maps_in_smem) {
         const void *k = resolve_kernel(h, 0, mode, threads, !P.need_pad);

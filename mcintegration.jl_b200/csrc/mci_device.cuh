@@ -37,6 +37,10 @@ constexpr int HIST_SMEM_STRIPED = 4; /* CTA-shared fp64 histogram in 16 bank-str
                                         ever has a bank conflict (2 wavefronts per instruction instead of ~10)           */
 constexpr int STRIPE_LOG2 = 4;
 constexpr int STRIPE = 1 << STRIPE_LOG2;
+#ifndef MCI_POOL_MAP_REP
+#define MCI_POOL_MAP_REP 1
+#endif
+constexpr int POOL_MAP_REP = MCI_POOL_MAP_REP; /* copies of the pool's map in the striped variant (1 or 4), see PoolMap: 4 measured -0.8 % on C2, +3 % on C3-A, so 1 */
 
 struct DevLeaf {
   int kind, nbins, adapt, lower_i;
@@ -200,6 +204,17 @@ __device__ __forceinline__ double map_continuous(const double2 *__restrict__ pai
   iy = i;
   dx = g.y;
   return __dadd_rn(g.x, __dmul_rn(dy, g.y));
+}
+
+/* the same draw with the table lookup left to the caller: increment iy (0-based) and the offset dy inside it */
+__device__ __forceinline__ void map_index(int nbins, double nbins_d, double u, int &iy, double &dy) {
+  const double MAGIC = 4503599627370496.0;
+  double t = __dmul_rn(u, nbins_d);
+  double f = __dadd_rd(t, MAGIC);
+  int i = __double2loint(f);
+  double fl = __dsub_rn(f, MAGIC);
+  dy = __dsub_rn(t, fl);
+  iy = min(i, nbins - 1);
 }
 
 /* locate (common.jl:8-36) clamped into the table instead of throwing; returns 0-based index g

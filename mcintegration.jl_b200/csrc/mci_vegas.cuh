@@ -92,8 +92,33 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
 #define MCI_HIST_BATCH 5
 #endif
 
-template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD>
-__device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const double2 *__restrict__ pair,
+/* The pool's map in shared memory.
+ *   REP == 1: one table of (edge, width) pairs, one LDS.128 per draw.  32 lanes at random increments conflict on the 8
+ *             16-byte bank groups: ~10 wavefronts per instruction — with the histogram the shared-memory pipe was 80 %
+ *             busy (ncu, profiles/r1_fill_ncu.json), THE limiter of the kernel.
+ *   REP == 4: edges and widths as two arrays, each in 4 copies interleaved [increment][copy]; lane l reads copy l % 4,
+ *             which lives in bank pairs (l % 4) + 4 k.  The 4 lanes of a half-warp that share a copy collide only when
+ *             their increments agree mod 4: ~3.2 wavefronts per LDS.64, 6.4 per draw instead of 10, for 48 KB more
+ *             shared memory (affordable in the striped variant, which owns the SM).  MEASURED (B200, A/B in one job):
+ *             C2 38.5 vs 38.8 G samples/s with one table, C3-A 25.6 vs 24.8 — the saved wavefronts are paid back by the
+ *             second LDS per draw, so the kernel is not purely wavefront-bound and REP = 1 stays the default. */
+template <int REP>
+struct PoolMap {
+  const double2 *pair;      /* REP == 1 */
+  uint32_t g_saddr, d_saddr; /* REP == 4: shared addresses of this lane's copy of edge[0] / width[0] */
+  __device__ __forceinline__ void lookup(int iy, double &g, double &dx) const {
+    if (REP == 1) {
+      const double2 v = pair[iy];
+      g = v.x; dx = v.y;
+    } else {
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(g) : "r"(g_saddr + (uint32_t)iy * (8u * REP)));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(d_saddr + (uint32_t)iy * (8u * REP)));
+    }
+  }
+};
+
+template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD, int REP>
+__device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M,
                                             uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
                                             bool active, double *acc, int &cnt, unsigned long long &bad) {
   using F = Integrand<FID>;
@@ -111,13 +136,17 @@ __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K
     if (2 * j < d) {
       uint32_t o0, o1, o2, o3;
       philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
-      double dx;
-      X.v[2 * j] = map_continuous(pair, nbins, nbins_d, u52(o0, o1), bin[2 * j], dx);
+      double dx, dy, g;
+      map_index(nbins, nbins_d, u52(o0, o1), bin[2 * j], dy);
+      M.lookup(bin[2 * j], g, dx);
+      X.v[2 * j] = __dadd_rn(g, __dmul_rn(dy, dx));
       double ndx = __dmul_rn(nbins_d, dx);
       jac *= ndx;
       if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / ndx;
       if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
-        X.v[2 * j + 1] = map_continuous(pair, nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dx);
+        map_index(nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dy);
+        M.lookup(bin[2 * j + 1], g, dx);
+        X.v[2 * j + 1] = __dadd_rn(g, __dmul_rn(dy, dx));
         ndx = __dmul_rn(nbins_d, dx);
         jac *= ndx;
         if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / ndx;
@@ -192,18 +221,34 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED,
                 "pool kernel histogram modes");
   constexpr int NCOPY = HMODE == HIST_SMEM_STRIPED ? STRIPE : (HMODE == HIST_SMEM_ATOMIC ? 1 : 0);
+  constexpr int REP = HMODE == HIST_SMEM_STRIPED ? POOL_MAP_REP : 1; /* the striped variant owns the SM: room for map copies */
   extern __shared__ __align__(16) double smem[];
-  double *smaps = smem;                                 /* P.map_doubles                          */
-  double *shist = smem + P.map_doubles;                 /* the CTA's histogram: [bin][copy]       */
+  double *smaps = smem;                                 /* REP * P.map_doubles                    */
+  double *shist = smem + REP * P.map_doubles;           /* the CTA's histogram: [bin][copy]       */
   double *sred = shist + NCOPY * P.hist_len;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool adapt = P.leaf[0].adapt != 0;
 
-  stage_maps(P, smaps, A.gmaps);
+  PoolMap<REP> M;
+  if (REP == 1) {
+    stage_maps(P, smaps, A.gmaps);
+    M.pair = reinterpret_cast<const double2 *>(smaps);
+    M.g_saddr = M.d_saddr = 0;
+  } else { /* edges [nbins][REP] | widths [nbins][REP] */
+    const int nb = P.leaf[0].nbins;
+    const double2 *src = reinterpret_cast<const double2 *>(A.gmaps);
+    for (int i = tid; i < nb * REP; i += THREADS) {
+      const double2 v = __ldg(src + i / REP);
+      smaps[i] = v.x;
+      smaps[nb * REP + i] = v.y;
+    }
+    M.pair = nullptr;
+    M.g_saddr = (uint32_t)__cvta_generic_to_shared(smaps) + 8u * (lane & (REP - 1));
+    M.d_saddr = M.g_saddr + 8u * REP * (uint32_t)nb;
+  }
   for (int i = tid; i < NCOPY * P.hist_len; i += THREADS) shist[i] = 0.0;
   __syncthreads();
-  const double2 *pair = reinterpret_cast<const double2 *>(smaps);
   const uint32_t hist_saddr = (uint32_t)__cvta_generic_to_shared(shist) + (HMODE == HIST_SMEM_STRIPED ? 8u * (lane & (STRIPE - 1)) : 0u);
   double *ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
 
@@ -225,19 +270,19 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
     if (s0 + tile_samples <= A.neval_per_block) { /* full tile: no per-lane guards anywhere */
       if (adapt) {
         for (int k = 0; k < A.spt; ++k)
-          pool_sample<FID, MAXD, HMODE, EXACT, false>(P, K, pair, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
+          pool_sample<FID, MAXD, HMODE, EXACT, false, REP>(P, K, M, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
                                                        true, acc, cnt, bad);
       } else {
         for (int k = 0; k < A.spt; ++k)
-          pool_sample<FID, MAXD, HIST_NONE, EXACT, false>(P, K, pair, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
+          pool_sample<FID, MAXD, HIST_NONE, EXACT, false, REP>(P, K, M, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
                                                            block, true, acc, cnt, bad);
       }
     } else { /* ragged last tile of a block */
       for (int k = 0; k < A.spt; ++k) {
         const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
         const bool active = s < A.neval_per_block;
-        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true>(P, K, pair, hist_saddr, ghist, s, block, active, acc, cnt, bad);
-        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true>(P, K, pair, hist_saddr, ghist, s, block, active, acc, cnt, bad);
+        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true, REP>(P, K, M, hist_saddr, ghist, s, block, active, acc, cnt, bad);
+        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true, REP>(P, K, M, hist_saddr, ghist, s, block, active, acc, cnt, bad);
       }
     }
     /* tile flush: warp shuffle -> shared -> one thread sums the warps in order */
