@@ -58,12 +58,13 @@ struct Walker {
   int bk0;      /* first backup row */
 };
 
-struct ChainCtx {
+template <class RNG>
+struct ChainCtxT {
   const Problem &P;
   const double *maps;
   const PhiloxKey &K;
-  Rng rng;
-  __device__ __forceinline__ ChainCtx(const Problem &p, const double *m, const PhiloxKey &k) : P(p), maps(m), K(k) {}
+  RNG rng;
+  __device__ __forceinline__ ChainCtxT(const Problem &p, const double *m, const PhiloxKey &k) : P(p), maps(m), K(k) {}
 };
 
 /* integrand accessor on the shared walker rows: X(leaf, pos), pos 1-based like the reference's x[pos] */
@@ -79,8 +80,8 @@ struct ChainX {
 __device__ __forceinline__ int frow(const DevLeaf &L, int pos) { return L.base + (pos - 1) * L.stride; }
 
 /* create! : sampler.jl:293-305 (Continuous), :13-22 (Discrete).  Returns 1/prob. */
-template <bool HP>
-__device__ __forceinline__ double leaf_create(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double leaf_create(CTX &C, Walker<HP> &W, const DevLeaf &L, int pos) {
   const int f = frow(L, pos) * W.T;
   const double u = C.rng.rand(C.K);
   if (L.kind == MCI_LEAF_CONTINUOUS) {
@@ -103,8 +104,8 @@ __device__ __forceinline__ double leaf_create(ChainCtx &C, Walker<HP> &W, const 
 }
 
 /* remove! : sampler.jl:317-322, :37-41 */
-template <bool HP>
-__device__ __forceinline__ double leaf_remove(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double leaf_remove(CTX &C, Walker<HP> &W, const DevLeaf &L, int pos) {
   const int f = frow(L, pos) * W.T;
   if (L.kind == MCI_LEAF_CONTINUOUS) {
     const double2 g = reinterpret_cast<const double2 *>(C.maps + L.smem_off)[W.gidx[f]];
@@ -115,8 +116,8 @@ __device__ __forceinline__ double leaf_remove(ChainCtx &C, Walker<HP> &W, const 
 }
 
 /* shift! : sampler.jl:336-386, :57-71.  k = leaf number inside its variable (backup row). */
-template <bool HP>
-__device__ __forceinline__ double leaf_shift(ChainCtx &C, Walker<HP> &W, const DevLeaf &L, int pos, int k) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double leaf_shift(CTX &C, Walker<HP> &W, const DevLeaf &L, int pos, int k) {
   const int f = frow(L, pos) * W.T;
   const int b = (W.bk0 + k) * W.T;
   W.data[b] = W.data[f];
@@ -154,8 +155,8 @@ __device__ __forceinline__ double top_prob(const Problem &P, const Walker<true> 
 }
 
 /* top-level dispatch incl. CompositeVar: sampler.jl:410-462 */
-template <bool HP>
-__device__ __forceinline__ double var_create(ChainCtx &C, Walker<HP> &W, int v, int pos) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double var_create(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_create(C, W, P.leaf[P.top_first[v]], pos);
@@ -163,8 +164,8 @@ __device__ __forceinline__ double var_create(ChainCtx &C, Walker<HP> &W, int v, 
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_create(C, W, P.leaf[P.top_first[v] + k], pos));
   return prop;
 }
-template <bool HP>
-__device__ __forceinline__ double var_remove(ChainCtx &C, Walker<HP> &W, int v, int pos) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double var_remove(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_remove(C, W, P.leaf[P.top_first[v]], pos);
@@ -172,8 +173,8 @@ __device__ __forceinline__ double var_remove(ChainCtx &C, Walker<HP> &W, int v, 
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_remove(C, W, P.leaf[P.top_first[v] + k], pos));
   return prop;
 }
-template <bool HP>
-__device__ __forceinline__ double var_shift(ChainCtx &C, Walker<HP> &W, int v, int pos) {
+template <bool HP, class CTX>
+__device__ __forceinline__ double var_shift(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   if (nl == 1) return leaf_shift(C, W, P.leaf[P.top_first[v]], pos, 0);
@@ -206,8 +207,8 @@ __device__ __forceinline__ void var_swap(const Problem &P, Walker<HP> &W, int v,
 }
 
 /* initialize!: variable.jl:576-580 / :497-507 — leaf-major, slots 1..maxdof */
-template <bool HP>
-__device__ __forceinline__ void var_initialize(ChainCtx &C, Walker<HP> &W, int v) {
+template <bool HP, class CTX>
+__device__ __forceinline__ void var_initialize(CTX &C, Walker<HP> &W, int v) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
   for (int k = 0; k < nl; ++k)
@@ -303,6 +304,8 @@ __device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainAr
 #ifndef MCI_CHAIN_MAXT
 #define MCI_CHAIN_MAXT 1024
 #endif
+/* uniforms the MCMC kernel generates ahead per step (RngAhead): update type, variable, slot(s), shift, accept */
+constexpr int MCMC_DRAWS_AHEAD = 6;
 /* bin-by-Discrete observables of the chain kernels are kept in this many per-thread accumulators (mci_create checks) */
 constexpr int CHAIN_MAX_BINNED_OBS = 8;
 /* per-thread observable accumulators: one per integrand (default measure), CHAIN_MAX_BINNED_OBS for the single binned
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
-  ChainCtx C(P, S.maps, K);
+  ChainCtxT<Rng> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
   ChainX X{W.data, &P, W.T};
 
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
-  ChainCtx C(P, S.maps, K);
+  ChainCtxT<RngAhead<MCMC_DRAWS_AHEAD>> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
   ChainX X{W.data, &P, W.T};
   double rw[NI + 1];
@@ -634,6 +637,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   const uint64_t total = A.steps + nburnin;
 
   for (long long it = 1 - A.burnin; it <= (long long)total; ++it) { /* it <= 0: burn-in, no statistics */
+    C.rng.fill(K); /* convergent: the divergent code below only pops registers */
     /* ---- propose (divergent, cheap) ---- */
     int kind = 0;   /* 0 none, 1 changeIntegrand, 2 changeVariable, 3 swapVariable (= first index of propose/accept + 1) */
     int tgt = curr; /* integrand to evaluate */
@@ -698,8 +702,9 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
                                          C.rng.c3, &s_q, &s_b);
         if ((tid & 31) == src) {
           prop = __dmul_rn(prop, f);
-          if (s_q != C.rng.q) { C.rng.q = s_q; if (s_q & 1u) C.rng.b = s_b; }
+          if (s_q != C.rng.q) C.rng.jump_to(s_q);
         }
+        (void)s_b;
       }
       if (ci) { if (prop > EPS0) kind = 1; else tgt = curr; }
     }
