@@ -309,7 +309,9 @@ int plan(mci_handle_t *h) {
           for (int v = 0; v < P.nv; ++v) items += std::abs(P.dof[a * P.nv + v] - P.dof[P.nb_idx[k] * P.nv + v]) * P.top_nleaf[v];
           worst = std::max(worst, items);
         }
-      h->coop_ci = worst >= 8; /* measured: 20 items 1.8x faster cooperatively, 2-4 items 1.6x slower */
+      int coop_min = 5; /* measured: 20 items 1.8x and 5 items 1.2x faster cooperatively, 2-3 items 2x slower */
+      if (const char *e = getenv("MCIB200_COOP_MIN")) coop_min = atoi(e);
+      h->coop_ci = worst >= coop_min;
     }
     const size_t row_bytes = (size_t)h->chain_rows * (8 + 4 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0));
     const size_t fixed = 32 * 8 + (((size_t)2 * h->pa_len + 1) / 2) * 8;
