@@ -63,9 +63,12 @@ class Result:
         return (len(self.iterations) - (self.ignore + 1) + 1) - 1
 
 
-def report(result: Result, pick=None, name=None, verbose=0, io=None):
-    """statistics.jl:137-172: per-iteration table + final estimate."""
+def report(result, pick=None, name=None, verbose=0, io=None):
+    """statistics.jl:137-172: per-iteration table + final estimate; report(config) -> report_config."""
     import sys
+
+    if not isinstance(result, Result):
+        return report_config(result, io=io)
 
     io = io or sys.stdout
     N = len(result.mean)
@@ -90,6 +93,45 @@ def report(result: Result, pick=None, name=None, verbose=0, io=None):
         m, s, c2 = result.mean[o], result.stdev[o], result.chi2[o]
         print(f"{label} = {np.asarray(m).ravel()} ± {np.asarray(s).ravel()}   (reduced chi2 = {np.asarray(c2).ravel()})", file=io)
     return None
+
+
+def report_config(config, io=None):
+    """report(config::Configuration) (configuration.jl:345-464): proposal / acceptance tables of the three updates,
+    visit counts and reweight factors, from the counters the kernels hand back (propose/accept[3, Nd, max(Nd, Nv)])."""
+    import sys
+
+    io = io or sys.stdout
+    neval = max(float(config.neval), 1.0)
+    propose, accept = np.asarray(config.propose), np.asarray(config.accept)
+    Nd = len(config.visited)
+    bar = "-" * 85
+    print("\n===========================  Configuration  =========================================", file=io)
+    print(bar, file=io)
+    print(f"Integral num = {config.N}, dof = {config.dof}, with variables:", file=io)
+    for vi, v in enumerate(config.var):
+        print(f"{vi + 1}. {v}", file=io)
+    print(bar, file=io)
+    row = lambda label, p, a: print(f"{label:<22s} {p / neval * 100.0:11.6f}% {a / neval * 100.0:11.6f}% {a / p if p else float('nan'):12.6f}", file=io)
+    print(f"{'ChangeIntegrand':<20s} {'Proposed':>12s} {'Accepted':>12s} {'Ratio  ':>12s}", file=io)
+    for n in config.neighbor[Nd - 1]:
+        row(f"Norm -> {n:2d}:", propose[0, Nd - 1, n - 1], accept[0, Nd - 1, n - 1])
+    for idx in range(1, Nd):
+        for n in config.neighbor[idx - 1]:
+            row(f"  {idx} ->Norm:" if n == Nd else f"  {idx} -> {n:2d}:", propose[0, idx - 1, n - 1], accept[0, idx - 1, n - 1])
+    print(bar, file=io)
+    kinds = {"Continuous": "Continuous", "Discrete": "Discrete", "CompositeVar": "Composite"}
+    for title, u in (("ChangeVariable", 1), ("SwapVariable", 2)):
+        print(f"{title:<20s} {'Proposed':>12s} {'Accepted':>12s} {'Ratio  ':>12s}", file=io)
+        for idx in range(1, Nd):
+            for vi, v in enumerate(config.var):
+                row(f"  {idx:2d} / {kinds.get(type(v).__name__, type(v).__name__):<11s}:", propose[u, idx - 1, vi], accept[u, idx - 1, vi])
+        print(bar, file=io)
+    print("Integrand            Visited      ReWeight", file=io)
+    print(f"  Norm   :     {int(config.visited[-1]):12d} {config.reweight[-1]:12.6f}", file=io)
+    for idx in range(1, Nd):
+        print(f"  Order{idx:2d}:     {int(config.visited[idx - 1]):12d} {config.reweight[idx - 1]:12.6f}", file=io)
+    print(bar, file=io)
+    print(f"Integrand evaluation = {int(config.neval)}\n", file=io)
 
 
 def do_reweight(reweight, visited, gamma, goal=None):

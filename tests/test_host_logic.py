@@ -167,3 +167,18 @@ def test_result_average_and_report():
     with redirect_stdout(buf):
         mci.report(res)
     assert "Integral 1" in buf.getvalue() or "integral" in buf.getvalue().lower()
+
+
+def test_report_config_tables():
+    """report(config) (configuration.jl:345-464) on counters shaped like the kernels' output"""
+    cfg = mci.Configuration(var=(mci.Continuous(0.0, 1.0), mci.Discrete(1, 4)), dof=[[1, 1], [2, 0]])
+    cfg.neval = 1000
+    cfg.propose = np.full((3, 3, 3), 10.0)
+    cfg.accept = np.full((3, 3, 3), 4.0)
+    cfg.visited = np.array([300.0, 300.0, 400.0])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        mci.report(cfg)
+    out = buf.getvalue()
+    assert "ChangeIntegrand" in out and "SwapVariable" in out and "Norm ->" in out and "0.400000" in out
+    assert "Integrand evaluation = 1000" in out and "Discrete" in out
