@@ -168,6 +168,12 @@ typedef struct mci_problem_t {
 } mci_problem_t;
 
 enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };
+/* where the per-bin variance histogram (accumulate!, variable.jl:196-200) is kept during a launch; every policy
+ * produces the same sums up to floating-point order (DESIGN.md 5.1 has the measurements behind AUTO):
+ *   SMEM_ATOMIC  one fp64 copy per CTA in shared memory, red.shared.add.f64
+ *   GLOBAL_RED   RED.E.ADD.F64 into a few L2-resident copies (layouts whose histograms do not fit in shared memory)
+ *   WARP_PRIVATE one copy per warp, MATCH.ANY conflict ranking, no atomics (generic VEGAS kernel only; kept for study)
+ *   SMEM_STRIPED 16 bank-striped copies per CTA, one 1024-thread CTA per SM (single-pool VEGAS kernel; AUTO picks it) */
 enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4 };
 
 /*
