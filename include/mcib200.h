@@ -152,7 +152,9 @@ typedef struct mci_problem_t {
                               solvers = walkers_per_block * steps per walker            */
   uint64_t seed;           /* Philox key                                                 */
   int32_t measurefreq;     /* main.jl:84                                                 */
-  int32_t walkers_per_block; /* chain solvers: concurrent chains per block (>=1)         */
+  int32_t walkers_per_block; /* chain solvers: concurrent chains per block; 0 = as many whole CTAs
+                                as fill the GPU with chains of >= 512 steps (depends on the
+                                number of local blocks: read it back with mci_chain_info)   */
   double thermal_ratio;    /* mcmc burn-in (mcmc/montecarlo.jl:77,133)                   */
   int32_t device;          /* CUDA device ordinal                                        */
   int32_t hist_policy;     /* 0 = auto; see MCI_HIST_* (performance knob, not semantics) */
@@ -323,6 +325,9 @@ int mci_fp64_peak(int32_t device, double *tflops);
  * tiles per block and samples per thread (VEGAS; 0 for the chain solvers) */
 int mci_launch_info(const mci_handle_t *h, int32_t *grid, int32_t *threads, int64_t *smem_bytes, int32_t *hist_mode,
                     int32_t *tiles_per_block, int32_t *samples_per_thread);
+/* chain solvers: the decomposition in use — chains per block (as given, or as chosen for walkers_per_block = 0),
+ * steps per chain, CTAs per block */
+int mci_chain_info(const mci_handle_t *h, int32_t *walkers_per_block, uint64_t *steps_per_walker, int32_t *ctas_per_block);
 /* name of the fill kernel variant chosen for this handle (static string) */
 const char *mci_kernel_name(const mci_handle_t *h);
 

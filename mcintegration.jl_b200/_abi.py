@@ -137,6 +137,7 @@ EXPORTS = [
     "mci_timer_stop",
     "mci_fill_history",
     "mci_jit_check",
+    "mci_chain_info",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -193,6 +194,7 @@ def declare(lib, prefix="mci_"):
         f("stats_sync_host", C.c_int, [H])
         f("fill_history", C.c_int, [H, C.POINTER(C.c_float), C.c_int32, ip])
         f("jit_check", C.c_int, [C.POINTER(Problem), C.c_char_p, C.c_int32])
+        f("chain_info", C.c_int, [H, ip, C.POINTER(C.c_uint64), ip])
         f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
     return lib
 

@@ -100,7 +100,7 @@ struct mci_handle_t {
   bool is_pool = false;
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
   size_t smem = 0;
-  int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0, chain_rows = 0, coop_ci = 0;
+  int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0, chain_rows = 0, coop_ci = 0, walkers = 1;
   uint64_t steps = 0;
   bool maps_dirty = true, have_iteration = false, async_mode = false;
   nccl_comm_t comm = nullptr;
@@ -315,26 +315,44 @@ int plan(mci_handle_t *h) {
     }
     const size_t row_bytes = (size_t)h->chain_rows * (8 + 4 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0));
     const size_t fixed = 32 * 8 + (((size_t)2 * h->pa_len + 1) / 2) * 8;
-    const int W = std::max(1, p.walkers_per_block);
     CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    int best_score = -1;
-    for (int T = h->use_jit ? h->chain_maxt : 1024; T >= 128; T >>= 1) {
-      if (T > 128 && T / 2 >= W) continue; /* more than half of the CTA would idle */
-      const int nwarp = T / 32;
-      const size_t extra = fixed + row_bytes * T;
-      if (extra > SMEM_MAX) continue;
-      int policy_mode = pick_hist(nwarp, extra, false);
-      if (policy_mode == HIST_WARP_PRIVATE) policy_mode = HIST_SMEM_ATOMIC;
-      /* mcmc keeps its shared histogram as u32 counters: a bin can receive at most T * steps * slots increments */
-      if (p.solver == MCI_SOLVER_MCMC && policy_mode == HIST_SMEM_ATOMIC &&
-          (double)T * ((double)(p.neval_per_block / W) * (1.0 + P.thermal_ratio) + 1.0) * (double)P.n_draw >= 4.0e9)
-        policy_mode = HIST_GLOBAL_RED;
-      const int mis = h->maps_in_smem;
-      const size_t smem = (mis ? map_bytes : 0) + hist_smem(policy_mode, nwarp) + extra;
-      int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, T, smem) != cudaSuccess) { cudaGetLastError(); continue; }
-      const int score = occ * T * 4 + (mis ? 2 : 0) + (policy_mode == HIST_SMEM_ATOMIC ? 1 : 0);
-      if (score > best_score) { best_score = score; h->threads = T; h->hist_mode = policy_mode; h->smem = smem; best_mis = mis; }
+    int best_score = -1, best_occ = 1;
+    /* CTA size that keeps most walkers resident for W walkers per block (W <= 0: as many as wanted) */
+    auto choose_T = [&](int W) {
+      best_score = -1;
+      for (int T = h->use_jit ? h->chain_maxt : 1024; T >= 128; T >>= 1) {
+        if (W > 0 && T > 128 && T / 2 >= W) continue; /* more than half of the CTA would idle */
+        const int nwarp = T / 32;
+        const size_t extra = fixed + row_bytes * T;
+        if (extra > SMEM_MAX) continue;
+        int policy_mode = pick_hist(nwarp, extra, false);
+        if (policy_mode == HIST_WARP_PRIVATE) policy_mode = HIST_SMEM_ATOMIC;
+        /* mcmc keeps its shared histogram as u32 counters: a bin can receive at most T * steps * slots increments */
+        if (p.solver == MCI_SOLVER_MCMC && policy_mode == HIST_SMEM_ATOMIC &&
+            (double)T * ((double)(p.neval_per_block / (W > 0 ? W : T)) * (1.0 + P.thermal_ratio) + 1.0) * (double)P.n_draw >= 4.0e9)
+          policy_mode = HIST_GLOBAL_RED;
+        const int mis = h->maps_in_smem;
+        const size_t smem = (mis ? map_bytes : 0) + hist_smem(policy_mode, nwarp) + extra;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, T, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        const int score = occ * T * 4 + (mis ? 2 : 0) + (policy_mode == HIST_SMEM_ATOMIC ? 1 : 0);
+        if (score > best_score) { best_score = score; best_occ = occ; h->threads = T; h->hist_mode = policy_mode; h->smem = smem; best_mis = mis; }
+      }
+    };
+    if (p.walkers_per_block > 0) {
+      h->walkers = p.walkers_per_block;
+      choose_T(h->walkers);
+    } else {
+      /* walkers_per_block = 0: fill the GPU with whole CTAs — every block gets floor(resident CTAs / local blocks) of
+       * them — unless that would cut the chains below 512 steps (start bias) */
+      choose_T(0);
+      if (best_score >= 0) {
+        const int ctas = std::max(1, h->n_sm * best_occ / std::max(1, n_local));
+        long long W = (long long)ctas * h->threads;
+        const long long wmax = std::max<long long>(1, (long long)(p.neval_per_block / 512));
+        if (W > wmax) { W = wmax >= 32 ? wmax / 32 * 32 : wmax; choose_T((int)W); }
+        h->walkers = (int)W;
+      }
     }
     if (best_score < 0) return fail(h, MCI_ERR_UNSUPPORTED, "walker state of %d rows does not fit in shared memory", h->chain_rows);
     h->maps_in_smem = best_mis;
@@ -358,7 +376,7 @@ int plan(mci_handle_t *h) {
     h->grid = (int)std::min<uint64_t>((uint64_t)resident, tpb * n_local);
     h->ctas_per_block = 0;
   } else {
-    const int W = std::max(1, p.walkers_per_block);
+    const int W = std::max(1, h->walkers);
     h->steps = p.neval_per_block / W;
     h->ctas_per_block = (W + h->threads - 1) / h->threads;
     h->grid = h->ctas_per_block * n_local;
@@ -713,7 +731,7 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     args[0] = &h->dp; args[1] = &FA;
   } else {
     CA.gmaps = h->d_gmaps; CA.reweight = h->d_reweight; CA.cta_stats = h->d_cta_stats; CA.cta_hist = h->d_cta_hist;
-    CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, p.walkers_per_block);
+    CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, h->walkers);
     CA.ctas_per_block = h->ctas_per_block; CA.n_local_blocks = n_local; CA.rank = h->rank; CA.world = h->world;
     CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;
     CA.rows = h->chain_rows; CA.coop_ci = h->coop_ci; CA.burnin = (long long)p.chain_burnin;
@@ -979,6 +997,14 @@ int mci_fill_history(mci_handle_t *h, float *ms, int32_t cap, int32_t *n) {
     CU(h, cudaEventElapsedTime(&ms[k], h->ev_fill0[slot], h->ev_fill1[slot]));
   }
   *n = m;
+  return MCI_OK;
+}
+
+int mci_chain_info(const mci_handle_t *h, int32_t *walkers_per_block, uint64_t *steps_per_walker, int32_t *ctas_per_block) {
+  if (!h) return MCI_ERR_INVALID;
+  if (walkers_per_block) *walkers_per_block = h->p.solver == MCI_SOLVER_VEGAS ? 0 : h->walkers;
+  if (steps_per_walker) *steps_per_walker = h->p.solver == MCI_SOLVER_VEGAS ? 0 : h->steps;
+  if (ctas_per_block) *ctas_per_block = h->ctas_per_block;
   return MCI_OK;
 }
 

@@ -200,6 +200,13 @@ class CudaEngine(HandleEngine):
         self._check(self.lib.mci_fill_history(self.h, buf, n, C.byref(got)))
         return [buf[i] for i in range(got.value)]
 
+    def chain_info(self) -> dict:
+        """chain solvers: chains per block (as given or auto-chosen), steps per chain, CTAs per block"""
+        w, c = C.c_int32(), C.c_int32()
+        st = C.c_uint64()
+        self._check(self.lib.mci_chain_info(self.h, C.byref(w), C.byref(st), C.byref(c)))
+        return dict(walkers_per_block=w.value, steps_per_walker=st.value, ctas_per_block=c.value)
+
     def stats_sync_host(self):
         self._check(self.lib.mci_stats_sync_host(self.h))
 

@@ -98,7 +98,8 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
     `jit` = 0 auto / 1 always specialise with NVRTC / 2 ahead-of-time kernels only;
     `chain_burnin` = extra unmeasured steps at the start of every chain (0 = the reference; default 1024 when a
     block is cut into several chains; see DESIGN.md 5.3);
-    `measure` is None, "bin_by_discrete" or integrands.user_measure(source).  `walkers` = concurrent chains per block for :vegasmc/:mcmc.
+    `measure` is None, "bin_by_discrete" or integrands.user_measure(source).  `walkers` = concurrent chains per block for :vegasmc/:mcmc (default: chosen by the library to fill the GPU; the
+    choice depends on the number of GPUs, so pass it explicitly for results that are identical across GPU counts).
     `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU).
     Everything else keeps the reference's meaning; `neval` is per iteration.
     """
@@ -122,12 +123,14 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
     assert block % world == 0  # main.jl:122
     if solver == "vegas":
         W = 1
-    else:
-        W = int(walkers) if walkers else min(DEFAULT_WALKERS, max(1, nevalperblock // MIN_CHAIN_STEPS))
+    elif walkers:
+        W = int(walkers)
         nevalperblock = (nevalperblock // W) * W
+    else:
+        W = 0  # the library fills the GPU with whole CTAs of chains of >= MIN_CHAIN_STEPS steps (engine.chain_info())
     spec = problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
-                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W, chain_burnin),
+                               thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W if W else DEFAULT_WALKERS, chain_burnin),
                                measure_source=measure_source)
     engine = CudaEngine(spec)
     try:

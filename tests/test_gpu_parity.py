@@ -367,3 +367,36 @@ def test_warm_restart_like_the_reference():
     # g1: before the restart trained it further.  Ten refinements compound the 1e-12 histogram differences (each
     # iteration's samples are drawn through the previous grid): grids agree to ~5e-6
     np.testing.assert_allclose(g1, o1.config.var[0].grid, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,solver", [("bubble", "vegasmc"), ("product4", "mcmc"), ("sphere2", "mcmc")])
+def test_auto_walkers_fill_the_gpu_and_match_the_oracle(name, solver):
+    """walkers_per_block = 0: the library picks whole CTAs of chains (>= 512 steps each); the oracle run with the
+    decomposition it reports (mci_chain_info) reproduces the statistics."""
+    import copy
+    spec, _ = make_spec(name, solver, n_block=4, neval_per_block=1 << 16, walkers=0, chain_burnin=16)
+    gpu = mci.CudaEngine(spec)
+    try:
+        info, launch = gpu.chain_info(), gpu.launch_info()
+        W = info["walkers_per_block"]
+        assert W >= 32 and info["steps_per_walker"] >= 512 and info["steps_per_walker"] == (1 << 16) // W
+        assert W <= (1 << 16) // 512 and launch["grid"] == info["ctas_per_block"] * 4
+        a = gpu.run_iteration(0)
+        spec2 = copy.copy(spec)
+        spec2.walkers_per_block = W
+        cpu = OracleEngine(spec2)
+        try:
+            b = cpu.run_iteration(0)
+            _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
+        finally:
+            cpu.close()
+    finally:
+        gpu.close()
+    big, _ = make_spec(name, solver, n_block=16, neval_per_block=1 << 26, walkers=0)
+    eng = mci.CudaEngine(big)
+    try:  # plenty of steps: every SM gets whole CTAs, at most one wave
+        info, launch = eng.chain_info(), eng.launch_info()
+        assert info["walkers_per_block"] == info["ctas_per_block"] * launch["threads"]
+        assert 148 * 0.8 <= launch["grid"] <= 148 * 2
+    finally:
+        eng.close()

@@ -46,8 +46,8 @@ run("C3-A 16-D Genz corner peak, pool", I.genz_corner_peak(16, "pool"), [[4.1798
 run("C3-B 16-D Genz corner peak, 16-leaf composite", I.genz_corner_peak(16, "comp"), [[4.17984992413838e-05]], solver="vegas",
     neval=2 ** 28, niter=20, var=mci.Continuous([(0.0, 1.0)] * 16), dof=[[1]])
 run("C4 example/bubble.jl (exact = finite-temperature Lindhard)", b["f"], [[I.lindhard_finite_temperature(para, q) for q in para.extQ]],
-    solver="vegasmc", neval=1e8, niter=10, measure="bin_by_discrete", walkers=4096, **b["cfg"]())
-run("C5 20-D 4-component product", I.product4(), [[1.0]] * 4, solver="mcmc", neval=1e9, niter=10, walkers=16384,
+    solver="vegasmc", neval=1e8, niter=10, measure="bin_by_discrete", **b["cfg"]())
+run("C5 20-D 4-component product", I.product4(), [[1.0]] * 4, solver="mcmc", neval=1e9, niter=10,
     var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4)
 run("C5 integrand under vegas", I.product4(), [[1.0]] * 4, solver="vegas", neval=2 ** 28, niter=10,
     var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4)
