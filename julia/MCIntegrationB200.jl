@@ -57,7 +57,7 @@ closure.
 """
 function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
     gamma=1.0, adapt=true, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
-    userdata=Float64[], measure_kind=0, walkers=4096, device=0, hist_policy=0, jit=0, chain_burnin=0, kwargs...)
+    userdata=Float64[], measure_kind=0, walkers=0, device=0, hist_policy=0, jit=0, chain_burnin=1024, kwargs...)
     # `integrand` is a built-in id (enum mci_integrand_id) or a String holding CUDA C++ source that defines
     # `template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w)`
     # (MCI_F_USER = 100, compiled by NVRTC inside mci_create) — the device-side equivalent of the closure f(x, c).
@@ -66,8 +66,10 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
     haskey(SOLVER, solver) || error("Solver $solver is not supported!")            # main.jl:263
     config = isnothing(config) ? Configuration(; kwargs...) : config                # main.jl:95-97
     nevalperblock, block = MCIntegration._standardize_block(neval, block)          # main.jl:121
-    W = solver == :vegas ? 1 : min(walkers, max(1, nevalperblock ÷ 512))   # chains of >= 512 steps (DESIGN.md 5.3)
-    nevalperblock = (nevalperblock ÷ W) * W
+    # walkers = 0: the library fills the GPU with whole CTAs of chains of >= 512 steps (mci_chain_info); walkers = 1 and
+    # chain_burnin = 0 reproduce the reference's one-chain-per-block decomposition (DESIGN.md 5.3)
+    W = solver == :vegas ? 1 : walkers
+    W > 0 && (nevalperblock = (nevalperblock ÷ W) * W)
 
     lv = vcat((leaves(v) for v in config.var)...)
     topn = Int32[length(leaves(v)) for v in config.var]
