@@ -39,12 +39,26 @@ UNIT = "samples/s"
 WORKLOAD = "C2: 10-D unit Gaussian, Continuous(-5,5), dof=[[10]], solver=vegas, 16 blocks/GPU x 2^26 samples"
 FLOP_PER_SAMPLE = 157.0  # 8*10 (map) + 5 + 10 (hist) + 62 (integrand)
 BLOCKS_PER_GPU = 16
+BUBBLE = False  # --workload bubble: the second workload the north star names (example/bubble.jl, solver=vegasmc)
+# algorithmic flop per VegasMC step on bubble.jl (SURVEY 8d convention: FMA 2, add/mul 1, div/sqrt 8, exp/sincos 40 per
+# value): integrand ~400 (2 sincos, 4 exp, 6 div, ~60 mul/add) + shift 8 + padding products 10 + ratio 4 + histogram
+# weights of 4 adaptive leaves 22 + measurement 20
+BUBBLE_FLOP_PER_STEP = 464.0
 
 
-def _spec(n_gpus, neval_per_block, device=0, seed=1234):
+def _spec(n_gpus, neval_per_block, device=0, seed=1234, cpu=False):
     import mcintegration_jl_b200 as mci
     from mcintegration_jl_b200 import _abi, integrands
 
+    if BUBBLE:
+        from cases import case
+        b = case("bubble")
+        cfg = mci.Configuration(seed=seed, **b["cfg"]())
+        # the CPU port runs the reference's decomposition (one chain per block); the GPU lets the library fill the SMs
+        spec = mci.problem_from_config(cfg, b["f"], solver=_abi.SOLVER_VEGASMC, measure_kind=_abi.MEASURE_BIN_BY_DISCRETE,
+                                       n_block=BLOCKS_PER_GPU * n_gpus, neval_per_block=neval_per_block, device=device,
+                                       walkers_per_block=1 if cpu else 0, chain_burnin=0 if cpu else 1024)
+        return spec, cfg
     cfg = mci.Configuration(var=mci.Continuous(-5.0, 5.0), dof=[[10]], seed=seed)
     spec = mci.problem_from_config(cfg, integrands.gauss_nd, solver=_abi.SOLVER_VEGAS, measure_kind=0,
                                    n_block=BLOCKS_PER_GPU * n_gpus, neval_per_block=neval_per_block, device=device)
@@ -101,7 +115,7 @@ def cpu_reference_rate(n_blocks=BLOCKS_PER_GPU, target_s=12.0, iters_after=1):
     from oracle_lib import OracleEngine
 
     cores = os.cpu_count() or 1
-    spec, _ = _spec(1, 1 << 14)
+    spec, _ = _spec(1, 1 << 14, cpu=True)
     spec.n_block = max(n_blocks, cores)  # blocks are the parallel unit (parallel=:thread, main.jl:153-158)
     eng = OracleEngine(spec, nthreads=cores)
     t0 = time.perf_counter(); eng.run_iteration(0); dt = time.perf_counter() - t0
@@ -109,7 +123,7 @@ def cpu_reference_rate(n_blocks=BLOCKS_PER_GPU, target_s=12.0, iters_after=1):
     eng.refine()
     eng.close()
     npb = max(1 << 14, int(rate * target_s / spec.n_block))
-    spec2, _ = _spec(1, npb)
+    spec2, _ = _spec(1, npb, cpu=True)
     spec2.n_block = spec.n_block
     eng = OracleEngine(spec2, nthreads=cores)
     eng.run_iteration(0); eng.refine()  # adapt once so the timed pass runs on a trained map, like the GPU steps
@@ -152,6 +166,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever native libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
@@ -185,6 +203,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if BUBBLE:  # chain solver: doReweight! belongs to the iteration (main.jl:183)
+        _refine = eng.refine
+        eng.refine = lambda: (eng.reweight(1.0), _refine())
     # ---------------- device-resident leg ("value") ----------------
     eng.set_async(True)
     it = 0
@@ -257,6 +278,12 @@ def run_ours(args):
             ncu = {k: ncu[k] for k in ("issue_active_pct", "smem_pipe_busy_frac", "warp_instructions_per_sample_warp", "source") if k in ncu}
         except Exception:
             pass
+        if BUBBLE:
+            from mcintegration_jl_b200 import integrands as _I
+            exact_value = _I.lindhard_finite_temperature(_I.BubblePara(), 0.0)  # first momentum bin, exact finite-T value
+            traffic, ncu = None, None  # the ncu capture in profiles/r1_fill_ncu.json is of the C2 kernel
+        else:
+            exact_value = math.erf(5 / math.sqrt(2)) ** 10
         cb = None
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_reference_rate()
@@ -270,7 +297,7 @@ def run_ours(args):
                           "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
                           "smem_bytes": info["smem_bytes"], "hist_mode": info["hist_mode"]},
                "result": {"integral": float(np.ravel(mean[0])[0]), "sigma": float(np.ravel(std[0])[0]),
-                          "exact": math.erf(5 / math.sqrt(2)) ** 10},
+                          "exact": exact_value},
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": traffic,
                             "note": f"{FLOP_PER_SAMPLE:.0f} algorithmic flop/sample (SURVEY 8d) x {BLOCKS_PER_GPU * npb} "
@@ -288,8 +315,10 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 def main():
@@ -300,7 +329,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--neval-per-block", type=int, default=1 << 26)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="gauss10", choices=["gauss10", "bubble"],
+                    help="gauss10 = BASELINE C2 (the metric); bubble = example/bubble.jl under vegasmc (C4), steps/s")
     args = ap.parse_args()
+    if args.workload == "bubble":
+        global BUBBLE, WORKLOAD, FLOP_PER_SAMPLE, METRIC, UNIT
+        BUBBLE = True
+        if args.neval_per_block == 1 << 26:
+            args.neval_per_block = 1 << 25  # ~3600 measured steps per chain on top of the 1024 burn-in steps
+        WORKLOAD = (f"C4: example/bubble.jl, (R,theta,phi,T) Continuous alpha=3 x Ext Discrete(1,4), 4-bin observable, solver=vegasmc, "
+                    f"16 blocks/GPU x {args.neval_per_block} steps")
+        FLOP_PER_SAMPLE = BUBBLE_FLOP_PER_STEP
+        METRIC = "MC steps/sec (fp64) for example/bubble.jl under vegasmc"
+        UNIT = "steps/s"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
