@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -128,3 +129,17 @@ def test_product_never_references_the_oracle():
                     assert bad not in txt, (fn, bad)
     needed = subprocess.run(["ldd", _abi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in needed
+
+
+def test_missing_library_fails_loudly():
+    """no CUDA extension -> an error that says so, never a silent CPU path"""
+    code = ("import sys; sys.path.insert(0, %r); import mcintegration_jl_b200 as mci\n"
+            "from mcintegration_jl_b200 import integrands\n"
+            "try:\n"
+            "    mci.integrate(integrands.gauss_nd, var=mci.Continuous(-5.0, 5.0), dof=[[10]], solver='vegas', neval=1e4)\n"
+            "except Exception as e:\n"
+            "    print(type(e).__name__, str(e)); sys.exit(3)\n" % ROOT)
+    env = dict(os.environ, MCIB200_LIB="/nonexistent/libmcib200.so")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 3, r.stdout + r.stderr
+    assert "LibraryMissing" in r.stdout and "no CPU fallback" in r.stdout
