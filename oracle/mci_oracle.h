@@ -23,8 +23,11 @@
  *     (test/mpi_test.jl:148-168), reduce/add algebra of histograms;
  *   - the reference's statistical known answers with its own 7-sigma rule
  *     (test/montecarlo.jl:262-387, test/bubble.jl) for all three solvers;
- *   - golden vectors for the map, train! and rescale produced by an
- *     independent pure-Python restatement (tests/golden/make_golden.py);
+ *   - golden vectors for the map, train! and rescale AND for the three whole
+ *     solver loops (vegas, vegasmc, mcmc on a two-integrand pool problem:
+ *     observables, normalisation, histograms, visited / propose / accept
+ *     counters) produced by an independent pure-Python restatement of the
+ *     Julia sources (tests/golden/make_golden.py);
  *   - Philox4x32-10 against the Random123 known-answer vectors.
  */
 #ifndef MCI_ORACLE_H

@@ -171,6 +171,247 @@ def average(means, stds, init):
     return mea, err, chi2 / ((mx - init + 1) - 1)
 
 
+# ---- whole solver loops on one Continuous pool (restated from the Julia sources; the two documented deviations of the
+# ---- oracle are followed so that the streams line up: initialize! creates the slots 1..maxdof only, and a chain
+# ---- consumes one uniform for every rand(rng, 1:n), also when n == 1) ----------------------------------------------
+class Stream:
+    def __init__(self, seed, it, block, idx):
+        self.a = (seed, it, block, idx)
+        self.buf = []
+        self.n = 0
+
+    def rand(self):
+        if self.n >= len(self.buf):
+            self.buf = uniforms(*self.a, len(self.buf) + 64)
+        u = self.buf[self.n]
+        self.n += 1
+        return u
+
+    def randint(self, n):
+        return min(int(math.floor(self.rand() * n)) + 1, n)
+
+
+class Pool:
+    """Continuous pool: create!/remove!/shift!/swap! of src/distribution/sampler.jl:293-408 (1-based slots)"""
+
+    def __init__(self, grid, nslot):
+        self.g, self.N = grid, len(grid) - 1
+        self.data, self.gidx, self.prob = [0.0] * (nslot + 2), [0] * (nslot + 2), [0.0] * (nslot + 2)
+
+    def _draw(self, rng):
+        y = rng.rand()
+        iy = min(int(math.floor(y * self.N)) + 1, self.N)
+        dy = y * self.N - (iy - 1)
+        return iy, self.g[iy - 1] + dy * (self.g[iy] - self.g[iy - 1])
+
+    def create(self, pos, rng):
+        iy, x = self._draw(rng)
+        self.data[pos], self.gidx[pos] = x, iy
+        self.prob[pos] = 1.0 / (self.N * (self.g[iy] - self.g[iy - 1]))
+        return 1.0 / self.prob[pos]
+
+    def remove(self, pos):
+        iy = self.gidx[pos]
+        return 1 / ((self.g[iy] - self.g[iy - 1]) * self.N)
+
+    def shift(self, pos, rng):
+        self.bk = (self.data[pos], self.gidx[pos], self.prob[pos])
+        curr = self.gidx[pos]
+        iy, x = self._draw(rng)
+        self.data[pos], self.gidx[pos] = x, iy
+        ratio = (self.g[curr] - self.g[curr - 1]) / (self.g[iy] - self.g[iy - 1])
+        self.prob[pos] *= ratio
+        return 1.0 / ratio
+
+    def rollback(self, pos):
+        self.data[pos], self.gidx[pos], self.prob[pos] = self.bk
+
+    def swap(self, a, b):
+        for arr in (self.data, self.gidx, self.prob):
+            arr[a], arr[b] = arr[b], arr[a]
+
+    def probability(self, d):  # variable.jl:606-619
+        p = 1.0
+        for pos in range(1, d + 1):
+            p *= self.prob[pos]
+        return p
+
+    def padding(self, d, maxdof):  # variable.jl:628-641
+        p = 1.0
+        for pos in range(d + 1, maxdof + 1):
+            p *= self.prob[pos]
+        return p
+
+
+def sphere2(x):  # test/montecarlo.jl:19-24
+    r2 = x[1] * x[1] + x[2] * x[2]
+    return [1.0 if r2 < 1.0 else 0.0, 1.0 if r2 + x[3] * x[3] < 1.0 else 0.0]
+
+
+DOF, MAXDOF, NBRS = [2, 3, 0], 3, [[3, 2], [1], [1]]  # dof incl. the normalisation row; configuration.jl:201-209 for Nd = 3
+EPS0, TINY_ = 5e-324, 5e-324 * 1e50
+
+
+def loop_vegas(grid, seed, it, nblock, npb, mf):
+    """vegas/montecarlo.jl:117-187"""
+    hist = [0.0] * (len(grid) - 1)
+    obs, norm = [], []
+    for b in range(nblock):
+        o, n = [0.0, 0.0], 0.0
+        for ne in range(1, npb + 1):
+            rng, P = Stream(seed, it, b, ne - 1), Pool(grid, MAXDOF)
+            jac = 1.0
+            for pos in range(1, MAXDOF + 1):
+                P.create(pos, rng)
+                jac /= P.prob[pos]
+            pad = [P.padding(DOF[i], MAXDOF) if DOF[i] != MAXDOF else 1.0 for i in range(2)]
+            w = sphere2(P.data)
+            if ne % mf == 0:
+                for i in range(2):
+                    o[i] += w[i] * pad[i] * jac
+                n += 1.0
+            for i in range(2):
+                for pos in range(1, DOF[i] + 1):
+                    hist[P.gidx[pos] - 1] += (abs(w[i]) * jac) * (abs(w[i]) * jac)
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist)
+
+
+def loop_vegasmc(grid, rw, seed, it, nblock, steps, mf):
+    """vegas_mc/montecarlo.jl:151-232 + updates.jl:45-106, one chain per block"""
+    hist = [0.0] * (len(grid) - 1)
+    obs, norm, visited, prop_c, acc_c, neval = [], [], [0.0] * 3, 0.0, 0.0, 0
+    for b in range(nblock):
+        rng, P = Stream(seed, it, b, 0), Pool(grid, MAXDOF)
+        for pos in range(1, MAXDOF + 1):
+            P.create(pos, rng)
+        w = sphere2(P.data)
+        pad = [P.padding(DOF[i], MAXDOF) for i in range(3)]
+        cur = rw[2] * pad[2]
+        for i in range(2):
+            cur += abs(w[i]) * rw[i] * pad[i]
+        o, n = [0.0, 0.0], 0.0
+        for ne in range(1, steps + 1):
+            rng.randint(1)  # vi = rand(rng, 1:length(var))
+            pos = rng.randint(MAXDOF)
+            prop = P.shift(pos, rng)
+            if prop > EPS0:
+                nw = sphere2(P.data)
+                neval += 1
+                npad = [P.padding(DOF[i], MAXDOF) for i in range(3)]
+                new = rw[2] * npad[2]
+                for i in range(2):
+                    new += abs(nw[i]) * rw[i] * npad[i]
+                R = prop * new / cur
+                prop_c += 1.0
+                if rng.rand() < R:
+                    acc_c += 1.0
+                    w, pad, cur = nw, npad, new
+                else:
+                    P.rollback(pos)
+            for i in range(2):
+                f2 = abs(w[i]) * abs(w[i]) / P.probability(DOF[i])
+                wf2 = f2 * pad[i] / cur
+                for p in range(1, DOF[i] + 1):
+                    hist[P.gidx[p] - 1] += wf2
+            if ne % mf == 0 and ne >= steps / 100:
+                for i in range(2):
+                    visited[i] += abs(w[i] * pad[i] * rw[i]) / cur
+                    o[i] += w[i] * pad[i] / cur
+                n += 1.0 * pad[2] / cur
+                visited[2] += rw[2] * pad[2] / cur
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose_cv=prop_c, accept_cv=acc_c, neval=neval)
+
+
+def loop_mcmc(grid, rw, seed, it, nblock, steps, mf, thermal):
+    """mcmc/montecarlo.jl:99-177 + updates.jl:1-147, one chain per block; counters [update][curr][new or vi] (0-based)"""
+    hist = [0.0] * (len(grid) - 1)
+    obs, norm, visited, neval = [], [], [0.0] * 3, 0
+    prop_c = [[[0.0] * 3 for _ in range(3)] for _ in range(3)]
+    acc_c = [[[0.0] * 3 for _ in range(3)] for _ in range(3)]
+    NORM = 2
+    for b in range(nblock):
+        rng, P = Stream(seed, it, b, 0), Pool(grid, MAXDOF)
+        curr = 0
+        for _ in range(10000):
+            for pos in range(1, MAXDOF + 1):
+                P.create(pos, rng)
+            weight = sphere2(P.data)[curr]
+            prob = abs(weight) * rw[curr]
+            if prob > TINY_:
+                break
+        o, n = [0.0, 0.0], 0.0
+        nburn = int(math.floor(steps * thermal))
+        for i in range(1, steps + nburn + 1):
+            visited[curr] += 1
+            u = rng.randint(4)
+            if u == 1:  # changeIntegrand
+                nb = NBRS[curr]
+                new = nb[rng.randint(len(nb)) - 1] - 1
+                if new != curr:
+                    prop = len(nb) / len(NBRS[new])
+                    cd, nd = DOF[curr], DOF[new]
+                    if cd < nd:
+                        for pos in range(cd + 1, nd + 1):
+                            prop *= P.create(pos, rng)
+                    elif cd > nd:
+                        for pos in range(nd + 1, cd + 1):
+                            prop *= P.remove(pos)
+                    if prop > EPS0:
+                        nw = 0.0 if new == NORM else sphere2(P.data)[new]
+                        neval += 1
+                        nprob = rw[new] if new == NORM else abs(nw) * rw[new]
+                        R = prop * nprob / prob
+                        prop_c[0][curr][new] += 1.0
+                        if rng.rand() < R:
+                            acc_c[0][curr][new] += 1.0
+                            curr, weight, prob = new, nw, nprob
+            elif curr != NORM:
+                rng.randint(1)  # vi
+                cd = DOF[curr]
+                if u == 2:  # swapVariable
+                    i1, i2 = rng.randint(cd), rng.randint(cd)
+                    if i1 != i2:
+                        P.swap(i1, i2)
+                        nw = sphere2(P.data)[curr]
+                        neval += 1
+                        nprob = abs(nw) * rw[curr]
+                        R = 1.0 * nprob / prob
+                        prop_c[2][curr][0] += 1.0
+                        if rng.rand() < R:
+                            acc_c[2][curr][0] += 1.0
+                            weight, prob = nw, nprob
+                        else:
+                            P.swap(i1, i2)
+                else:  # changeVariable
+                    pos = rng.randint(cd)
+                    prop = P.shift(pos, rng)
+                    if prop > EPS0:
+                        nw = sphere2(P.data)[curr]
+                        neval += 1
+                        nprob = abs(nw) * rw[curr]
+                        R = prop * nprob / prob
+                        prop_c[1][curr][0] += 1.0
+                        if rng.rand() < R:
+                            acc_c[1][curr][0] += 1.0
+                            weight, prob = nw, nprob
+                        else:
+                            P.rollback(pos)
+            if i % mf == 0 and i >= nburn:
+                if curr == NORM:
+                    n += 1.0 / rw[NORM]
+                else:
+                    for pos in range(1, DOF[curr] + 1):
+                        hist[P.gidx[pos] - 1] += 1.0
+                    o[curr] += weight / prob
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose=prop_c, accept=acc_c, neval=neval)
+
+
 def main():
     rnd = random.Random(20261017)
     G = {}
@@ -258,6 +499,14 @@ def main():
     means = [rnd.gauss(2.0, 0.01) for _ in range(10)]
     stds = [abs(rnd.gauss(0.01, 0.002)) for _ in range(10)]
     G["average"] = [dict(means=means, stds=stds, init=i, out=list(average(means, stds, i))) for i in (1, 2, 10)]
+
+    # whole solver loops: sphere2 (dof [[2],[3]]) on a hand-made non-uniform 8-increment grid
+    lgrid = [0.0, 0.07, 0.19, 0.3, 0.46, 0.6, 0.71, 0.88, 1.0]
+    lrw = [0.5, 0.3, 0.2]
+    G["loops"] = dict(grid=lgrid, reweight=lrw, seed=4242, iter=3, n_block=2,
+                      vegas=dict(npb=60, measurefreq=2, out=loop_vegas(lgrid, 4242, 3, 2, 60, 2)),
+                      vegasmc=dict(steps=300, measurefreq=1, out=loop_vegasmc(lgrid, lrw, 4242, 3, 2, 300, 1)),
+                      mcmc=dict(steps=300, measurefreq=2, thermal_ratio=0.1, out=loop_mcmc(lgrid, lrw, 4242, 3, 2, 300, 2, 0.1)))
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:

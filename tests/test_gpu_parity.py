@@ -400,3 +400,34 @@ def test_auto_walkers_fill_the_gpu_and_match_the_oracle(name, solver):
         assert 148 * 0.8 <= launch["grid"] <= 148 * 2
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+def test_gpu_against_independent_loop_fixtures(solver):
+    """The CUDA path held directly to tests/golden/golden.json["loops"]: whole solver loops restated in pure Python from
+    the Julia sources (tests/golden/make_golden.py), no C oracle in between."""
+    import json, os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))["loops"]
+    L0 = G[solver]
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0, grid=G["grid"]), dof=[[2], [3]], seed=G["seed"])
+    from cases import SOLVER_ID
+    spec = mci.problem_from_config(cfg, mci.integrands.sphere2, solver=SOLVER_ID[solver], measure_kind=0, n_block=G["n_block"],
+                                   neval_per_block=L0.get("npb", L0.get("steps")), measurefreq=L0["measurefreq"],
+                                   walkers_per_block=1, thermal_ratio=L0.get("thermal_ratio", 0.1))
+    gpu = mci.CudaEngine(spec)
+    try:
+        gpu.set_maps(grids=np.array(G["grid"]), reweight=np.array(G["reweight"]))
+        st = gpu.run_iteration(G["iter"])
+        want = L0["out"]
+        B1 = G["n_block"] + 1
+        np.testing.assert_allclose(st.block_obs, want["obs"], rtol=1e-12)
+        np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=1e-12)
+        np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"], rtol=1e-9, atol=1e-9)
+        if solver != "vegas":
+            np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+            assert st.neval == want["neval"]
+        if solver == "mcmc":
+            assert np.array_equal(np.round(st.propose - B1 * 1e-8, 3), np.array(want["propose"]))
+            assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
+    finally:
+        gpu.close()

@@ -201,3 +201,77 @@ def test_host_statistics_match_oracle():
         lib.orc_average(dptr(arr(means)), dptr(arr(stds)), 10, init, C.byref(a), C.byref(e), C.byref(c))
         pa, pe, pc = average(means, stds, init=init)
         np.testing.assert_allclose([pa, pe, pc], [a.value, e.value, c.value], rtol=1e-12)
+
+
+# ---- whole solver loops against the independent pure-Python restatement (tests/golden/make_golden.py) -------------------
+def _loop_engine(solver, npb, measurefreq, thermal=0.1):
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import _abi, integrands
+    from oracle_lib import OracleEngine
+    L = GOLD["loops"]
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0, grid=L["grid"]), dof=[[2], [3]], seed=L["seed"])
+    spec = mci.problem_from_config(cfg, integrands.sphere2, solver=solver, measure_kind=0, n_block=L["n_block"],
+                                   neval_per_block=npb, measurefreq=measurefreq, walkers_per_block=1, thermal_ratio=thermal)
+    eng = OracleEngine(spec, nthreads=1)
+    eng.set_maps(grids=arr(L["grid"]), reweight=arr(L["reweight"]))
+    return eng, L
+
+
+def _unpack(eng, raw):
+    """[hist | block_obs | block_cnt | visited | propose | accept | neval] (csrc/mci_aux.cuh PackedLayout)"""
+    nb, ot, hl, nd, pa = eng.n_block, eng.obs_total, eng.hist_len, eng.nd, eng.pa_len
+    o = 0
+    out = {}
+    for name, n in (("hist", hl), ("obs", nb * ot), ("cnt", nb), ("visited", nd), ("propose", pa), ("accept", pa), ("neval", 1)):
+        out[name] = np.array(raw[o:o + n]); o += n
+    out["obs"] = out["obs"].reshape(nb, ot)
+    out["propose"] = out["propose"].reshape(3, nd, pa // (3 * nd)); out["accept"] = out["accept"].reshape(3, nd, pa // (3 * nd))
+    return out
+
+
+def test_vegas_loop_against_independent_restatement():
+    from mcintegration_jl_b200 import _abi
+    L0 = GOLD["loops"]["vegas"]
+    eng, L = _loop_engine(_abi.SOLVER_VEGAS, L0["npb"], L0["measurefreq"])
+    try:
+        eng.run_local(L["iter"])
+        got, want = _unpack(eng, eng.packed()), L0["out"]
+        np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-14)
+        assert got["cnt"].tolist() == want["norm"]
+        np.testing.assert_allclose(got["hist"], want["hist"], rtol=1e-14)
+    finally:
+        eng.close()
+
+
+def test_vegasmc_loop_against_independent_restatement():
+    from mcintegration_jl_b200 import _abi
+    L0 = GOLD["loops"]["vegasmc"]
+    eng, L = _loop_engine(_abi.SOLVER_VEGASMC, L0["steps"], L0["measurefreq"])
+    try:
+        eng.run_local(L["iter"])
+        got, want = _unpack(eng, eng.packed()), L0["out"]
+        np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-13)
+        np.testing.assert_allclose(got["cnt"], want["norm"], rtol=1e-13)
+        np.testing.assert_allclose(got["hist"], want["hist"], rtol=1e-13)
+        np.testing.assert_allclose(got["visited"], want["visited"], rtol=1e-13)
+        assert got["propose"][1, 0, 0] == want["propose_cv"] and got["accept"][1, 0, 0] == want["accept_cv"]
+        assert int(got["neval"][0]) == want["neval"]
+    finally:
+        eng.close()
+
+
+def test_mcmc_loop_against_independent_restatement():
+    from mcintegration_jl_b200 import _abi
+    L0 = GOLD["loops"]["mcmc"]
+    eng, L = _loop_engine(_abi.SOLVER_MCMC, L0["steps"], L0["measurefreq"], L0["thermal_ratio"])
+    try:
+        eng.run_local(L["iter"])
+        got, want = _unpack(eng, eng.packed()), L0["out"]
+        np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-13)
+        np.testing.assert_allclose(got["cnt"], want["norm"], rtol=1e-13)
+        assert got["hist"].tolist() == want["hist"]          # integer visit counts: exact
+        assert got["visited"].tolist() == want["visited"]
+        assert got["propose"].tolist() == want["propose"] and got["accept"].tolist() == want["accept"]
+        assert int(got["neval"][0]) == want["neval"]
+    finally:
+        eng.close()
