@@ -230,6 +230,12 @@ class Pool:
         for arr in (self.data, self.gidx, self.prob):
             arr[a], arr[b] = arr[b], arr[a]
 
+    def hist_len(self):
+        return self.N
+
+    def accumulate(self, pos, w, hist):  # variable.jl:196-200
+        hist[self.gidx[pos] - 1] += w
+
     def probability(self, d):  # variable.jl:606-619
         p = 1.0
         for pos in range(1, d + 1):
@@ -243,55 +249,141 @@ class Pool:
         return p
 
 
+class DiscretePair:
+    """CompositeVar of two Discrete leaves (variable.jl:272-325, 397-507; sampler.jl:13-22, 37-41, 57-97, 410-462):
+    every operation acts on both leaves at the same slot, leaf 0 first; prob = 1.0 * p_leaf0 * p_leaf1."""
+
+    def __init__(self, dists, lowers, nslot):
+        self.dist = dists
+        self.acc = []
+        for d in dists:  # accumulation = [0, sum(d[1:1]), sum(d[1:2]), ...] each prefix recomputed (variable.jl:314-315)
+            self.acc.append([0.0] + [seqsum(d[: i + 1]) for i in range(len(d))])
+        self.lower = lowers
+        self.val = [[0] * (nslot + 2) for _ in dists]
+        self.lprob = [[0.0] * (nslot + 2) for _ in dists]
+        self.prob = [0.0] * (nslot + 2)
+        self.data = self.val  # integrand view: data[leaf][pos]
+
+    def _locate(self, k, u):  # clamped into the table (DESIGN.md: quirk 15)
+        acc = self.acc[k]
+        if u < acc[0]:
+            return 1
+        jl, ju = 1, len(acc) + 1
+        while ju - jl > 1:
+            jm = (jl + ju) // 2
+            if u < acc[jm - 1]:
+                ju = jm
+            else:
+                jl = jm
+        return min(jl, len(self.dist[k]))
+
+    def create(self, pos, rng):
+        prop, self.prob[pos] = 1.0, 1.0
+        for k in range(len(self.dist)):
+            g = self._locate(k, rng.rand())
+            self.val[k][pos] = self.lower[k] + g - 1
+            self.lprob[k][pos] = self.dist[k][g - 1]
+            prop *= 1.0 / self.dist[k][g - 1]
+            self.prob[pos] *= self.lprob[k][pos]
+        return prop
+
+    def remove(self, pos):
+        prop = 1.0
+        for k in range(len(self.dist)):
+            prop *= self.dist[k][self.val[k][pos] - self.lower[k]]
+        return prop
+
+    def shift(self, pos, rng):
+        self.bk = ([v[pos] for v in self.val], [p[pos] for p in self.lprob], self.prob[pos])
+        prop, self.prob[pos] = 1.0, 1.0
+        for k in range(len(self.dist)):
+            curr = self.val[k][pos] - self.lower[k] + 1
+            g = self._locate(k, rng.rand())
+            self.val[k][pos] = self.lower[k] + g - 1
+            ratio = self.dist[k][g - 1] / self.dist[k][curr - 1]
+            self.lprob[k][pos] *= ratio
+            prop *= 1.0 / ratio
+            self.prob[pos] *= self.lprob[k][pos]
+        return prop
+
+    def rollback(self, pos):
+        for k in range(len(self.dist)):
+            self.val[k][pos], self.lprob[k][pos] = self.bk[0][k], self.bk[1][k]
+        self.prob[pos] = self.bk[2]
+
+    def swap(self, a, b):
+        for arr in self.val + self.lprob + [self.prob]:
+            arr[a], arr[b] = arr[b], arr[a]
+
+    def hist_len(self):
+        return sum(len(d) for d in self.dist)
+
+    def accumulate(self, pos, w, hist):  # variable.jl:362-367, 474-478
+        off = 0
+        for k in range(len(self.dist)):
+            hist[off + self.val[k][pos] - self.lower[k]] += w
+            off += len(self.dist[k])
+
+    probability = Pool.probability
+    padding = Pool.padding
+
+
+class Prob:
+    def __init__(self, make_pool, f, dof, nbrs):
+        self.make_pool, self.f, self.DOF, self.NBRS = make_pool, f, dof, nbrs
+        self.MAXDOF, self.NI = max(dof), len(dof) - 1
+
+
 def sphere2(x):  # test/montecarlo.jl:19-24
     r2 = x[1] * x[1] + x[2] * x[2]
     return [1.0 if r2 < 1.0 else 0.0, 1.0 if r2 + x[3] * x[3] < 1.0 else 0.0]
 
 
-DOF, MAXDOF, NBRS = [2, 3, 0], 3, [[3, 2], [1], [1]]  # dof incl. the normalisation row; configuration.jl:201-209 for Nd = 3
 EPS0, TINY_ = 5e-324, 5e-324 * 1e50
 
 
-def loop_vegas(grid, seed, it, nblock, npb, mf):
+def loop_vegas(Q, seed, it, nblock, npb, mf):
     """vegas/montecarlo.jl:117-187"""
-    hist = [0.0] * (len(grid) - 1)
+    DOF, MAXDOF, NI, sphere2 = Q.DOF, Q.MAXDOF, Q.NI, Q.f
+    hist = [0.0] * Q.make_pool().hist_len()
     obs, norm = [], []
     for b in range(nblock):
-        o, n = [0.0, 0.0], 0.0
+        o, n = [0.0] * NI, 0.0
         for ne in range(1, npb + 1):
-            rng, P = Stream(seed, it, b, ne - 1), Pool(grid, MAXDOF)
+            rng, P = Stream(seed, it, b, ne - 1), Q.make_pool()
             jac = 1.0
             for pos in range(1, MAXDOF + 1):
                 P.create(pos, rng)
                 jac /= P.prob[pos]
-            pad = [P.padding(DOF[i], MAXDOF) if DOF[i] != MAXDOF else 1.0 for i in range(2)]
+            pad = [P.padding(DOF[i], MAXDOF) if DOF[i] != MAXDOF else 1.0 for i in range(NI)]
             w = sphere2(P.data)
             if ne % mf == 0:
-                for i in range(2):
+                for i in range(NI):
                     o[i] += w[i] * pad[i] * jac
                 n += 1.0
-            for i in range(2):
+            for i in range(NI):
                 for pos in range(1, DOF[i] + 1):
-                    hist[P.gidx[pos] - 1] += (abs(w[i]) * jac) * (abs(w[i]) * jac)
+                    P.accumulate(pos, (abs(w[i]) * jac) * (abs(w[i]) * jac), hist)
         obs.append(o)
         norm.append(n)
     return dict(obs=obs, norm=norm, hist=hist)
 
 
-def loop_vegasmc(grid, rw, seed, it, nblock, steps, mf):
+def loop_vegasmc(Q, rw, seed, it, nblock, steps, mf):
     """vegas_mc/montecarlo.jl:151-232 + updates.jl:45-106, one chain per block"""
-    hist = [0.0] * (len(grid) - 1)
-    obs, norm, visited, prop_c, acc_c, neval = [], [], [0.0] * 3, 0.0, 0.0, 0
+    DOF, MAXDOF, NI, sphere2 = Q.DOF, Q.MAXDOF, Q.NI, Q.f
+    hist = [0.0] * Q.make_pool().hist_len()
+    obs, norm, visited, prop_c, acc_c, neval = [], [], [0.0] * (NI + 1), 0.0, 0.0, 0
     for b in range(nblock):
-        rng, P = Stream(seed, it, b, 0), Pool(grid, MAXDOF)
+        rng, P = Stream(seed, it, b, 0), Q.make_pool()
         for pos in range(1, MAXDOF + 1):
             P.create(pos, rng)
         w = sphere2(P.data)
-        pad = [P.padding(DOF[i], MAXDOF) for i in range(3)]
-        cur = rw[2] * pad[2]
-        for i in range(2):
+        pad = [P.padding(DOF[i], MAXDOF) for i in range(NI + 1)]
+        cur = rw[NI] * pad[NI]
+        for i in range(NI):
             cur += abs(w[i]) * rw[i] * pad[i]
-        o, n = [0.0, 0.0], 0.0
+        o, n = [0.0] * NI, 0.0
         for ne in range(1, steps + 1):
             rng.randint(1)  # vi = rand(rng, 1:length(var))
             pos = rng.randint(MAXDOF)
@@ -299,9 +391,9 @@ def loop_vegasmc(grid, rw, seed, it, nblock, steps, mf):
             if prop > EPS0:
                 nw = sphere2(P.data)
                 neval += 1
-                npad = [P.padding(DOF[i], MAXDOF) for i in range(3)]
-                new = rw[2] * npad[2]
-                for i in range(2):
+                npad = [P.padding(DOF[i], MAXDOF) for i in range(NI + 1)]
+                new = rw[NI] * npad[NI]
+                for i in range(NI):
                     new += abs(nw[i]) * rw[i] * npad[i]
                 R = prop * new / cur
                 prop_c += 1.0
@@ -310,31 +402,33 @@ def loop_vegasmc(grid, rw, seed, it, nblock, steps, mf):
                     w, pad, cur = nw, npad, new
                 else:
                     P.rollback(pos)
-            for i in range(2):
+            for i in range(NI):
                 f2 = abs(w[i]) * abs(w[i]) / P.probability(DOF[i])
                 wf2 = f2 * pad[i] / cur
                 for p in range(1, DOF[i] + 1):
-                    hist[P.gidx[p] - 1] += wf2
+                    P.accumulate(p, wf2, hist)
             if ne % mf == 0 and ne >= steps / 100:
-                for i in range(2):
+                for i in range(NI):
                     visited[i] += abs(w[i] * pad[i] * rw[i]) / cur
                     o[i] += w[i] * pad[i] / cur
-                n += 1.0 * pad[2] / cur
-                visited[2] += rw[2] * pad[2] / cur
+                n += 1.0 * pad[NI] / cur
+                visited[NI] += rw[NI] * pad[NI] / cur
         obs.append(o)
         norm.append(n)
     return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose_cv=prop_c, accept_cv=acc_c, neval=neval)
 
 
-def loop_mcmc(grid, rw, seed, it, nblock, steps, mf, thermal):
+def loop_mcmc(Q, rw, seed, it, nblock, steps, mf, thermal):
     """mcmc/montecarlo.jl:99-177 + updates.jl:1-147, one chain per block; counters [update][curr][new or vi] (0-based)"""
-    hist = [0.0] * (len(grid) - 1)
-    obs, norm, visited, neval = [], [], [0.0] * 3, 0
-    prop_c = [[[0.0] * 3 for _ in range(3)] for _ in range(3)]
-    acc_c = [[[0.0] * 3 for _ in range(3)] for _ in range(3)]
-    NORM = 2
+    DOF, MAXDOF, NI, sphere2, NBRS = Q.DOF, Q.MAXDOF, Q.NI, Q.f, Q.NBRS
+    Nd = NI + 1
+    hist = [0.0] * Q.make_pool().hist_len()
+    obs, norm, visited, neval = [], [], [0.0] * Nd, 0
+    prop_c = [[[0.0] * Nd for _ in range(Nd)] for _ in range(3)]
+    acc_c = [[[0.0] * Nd for _ in range(Nd)] for _ in range(3)]
+    NORM = NI
     for b in range(nblock):
-        rng, P = Stream(seed, it, b, 0), Pool(grid, MAXDOF)
+        rng, P = Stream(seed, it, b, 0), Q.make_pool()
         curr = 0
         for _ in range(10000):
             for pos in range(1, MAXDOF + 1):
@@ -343,7 +437,7 @@ def loop_mcmc(grid, rw, seed, it, nblock, steps, mf, thermal):
             prob = abs(weight) * rw[curr]
             if prob > TINY_:
                 break
-        o, n = [0.0, 0.0], 0.0
+        o, n = [0.0] * NI, 0.0
         nburn = int(math.floor(steps * thermal))
         for i in range(1, steps + nburn + 1):
             visited[curr] += 1
@@ -405,7 +499,7 @@ def loop_mcmc(grid, rw, seed, it, nblock, steps, mf, thermal):
                     n += 1.0 / rw[NORM]
                 else:
                     for pos in range(1, DOF[curr] + 1):
-                        hist[P.gidx[pos] - 1] += 1.0
+                        P.accumulate(pos, 1.0, hist)
                     o[curr] += weight / prob
         obs.append(o)
         norm.append(n)
@@ -503,10 +597,20 @@ def main():
     # whole solver loops: sphere2 (dof [[2],[3]]) on a hand-made non-uniform 8-increment grid
     lgrid = [0.0, 0.07, 0.19, 0.3, 0.46, 0.6, 0.71, 0.88, 1.0]
     lrw = [0.5, 0.3, 0.2]
+    Q = Prob(lambda: Pool(lgrid, 3), sphere2, [2, 3, 0], [[3, 2], [1], [1]])  # neighbours: configuration.jl:201-209, Nd = 3
     G["loops"] = dict(grid=lgrid, reweight=lrw, seed=4242, iter=3, n_block=2,
-                      vegas=dict(npb=60, measurefreq=2, out=loop_vegas(lgrid, 4242, 3, 2, 60, 2)),
-                      vegasmc=dict(steps=300, measurefreq=1, out=loop_vegasmc(lgrid, lrw, 4242, 3, 2, 300, 1)),
-                      mcmc=dict(steps=300, measurefreq=2, thermal_ratio=0.1, out=loop_mcmc(lgrid, lrw, 4242, 3, 2, 300, 2, 0.1)))
+                      vegas=dict(npb=60, measurefreq=2, out=loop_vegas(Q, 4242, 3, 2, 60, 2)),
+                      vegasmc=dict(steps=300, measurefreq=1, out=loop_vegasmc(Q, lrw, 4242, 3, 2, 300, 1)),
+                      mcmc=dict(steps=300, measurefreq=2, thermal_ratio=0.1, out=loop_mcmc(Q, lrw, 4242, 3, 2, 300, 2, 0.1)))
+    # the same loops on Discrete([(1,3),(1,4)]) (a CompositeVar of two Discrete leaves), f = 1 (test/montecarlo.jl:113-120)
+    # with non-uniform distributions: pins locate / the Discrete index draws / the composite probability product
+    d1, d2 = [0.2, 0.5, 0.3], [0.1, 0.4, 0.15, 0.35]
+    QD = Prob(lambda: DiscretePair([d1, d2], [1, 1], 1), lambda x: [1.0], [1, 0], [[2], [1]])
+    drw = [0.6, 0.4]
+    G["loops_discrete"] = dict(dist=[d1, d2], reweight=drw, seed=777, iter=1, n_block=2,
+                               vegas=dict(npb=80, measurefreq=1, out=loop_vegas(QD, 777, 1, 2, 80, 1)),
+                               vegasmc=dict(steps=250, measurefreq=1, out=loop_vegasmc(QD, drw, 777, 1, 2, 250, 1)),
+                               mcmc=dict(steps=250, measurefreq=1, thermal_ratio=0.2, out=loop_mcmc(QD, drw, 777, 1, 2, 250, 1, 0.2)))
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:

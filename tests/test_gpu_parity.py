@@ -431,3 +431,37 @@ def test_gpu_against_independent_loop_fixtures(solver):
             assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+def test_gpu_against_independent_discrete_loop_fixtures(solver):
+    """golden.json["loops_discrete"]: CompositeVar of two Discrete leaves with non-uniform distributions (locate, index
+    draws, composite probability product), whole loops restated in pure Python (tests/golden/make_golden.py)."""
+    import json, os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))["loops_discrete"]
+    L0 = G[solver]
+    cfg = mci.Configuration(var=mci.Discrete([(1, 3), (1, 4)]), dof=[[1]], seed=G["seed"])
+    from cases import SOLVER_ID
+    spec = mci.problem_from_config(cfg, mci.integrands.discrete2_const, solver=SOLVER_ID[solver], measure_kind=0,
+                                   n_block=G["n_block"], neval_per_block=L0.get("npb", L0.get("steps")),
+                                   measurefreq=L0["measurefreq"], walkers_per_block=1,
+                                   thermal_ratio=L0.get("thermal_ratio", 0.1))
+    gpu = mci.CudaEngine(spec)
+    try:
+        dist = np.concatenate([np.array(d, dtype=np.float64) for d in G["dist"]])
+        accum = np.concatenate([np.concatenate([[0.0], [sum(d[: i + 1], 0.0) for i in range(len(d))]]) for d in G["dist"]])
+        gpu.set_maps(dist=dist, accum=accum, reweight=np.array(G["reweight"]))
+        st = gpu.run_iteration(G["iter"])
+        want = L0["out"]
+        B1 = G["n_block"] + 1
+        np.testing.assert_allclose(st.block_obs, want["obs"], rtol=1e-12)
+        np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=1e-12)
+        np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"], rtol=1e-9, atol=1e-9)
+        if solver != "vegas":
+            np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+            assert st.neval == want["neval"]
+        if solver == "mcmc":
+            assert np.array_equal(np.round(st.propose - B1 * 1e-8, 3), np.array(want["propose"]))
+            assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
+    finally:
+        gpu.close()

@@ -275,3 +275,43 @@ def test_mcmc_loop_against_independent_restatement():
         assert int(got["neval"][0]) == want["neval"]
     finally:
         eng.close()
+
+
+def _discrete_loop_engine(engine_cls, solver, L0, **kw):
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import integrands
+    D = GOLD["loops_discrete"]
+    cfg = mci.Configuration(var=mci.Discrete([(1, 3), (1, 4)]), dof=[[1]], seed=D["seed"])
+    spec = mci.problem_from_config(cfg, integrands.discrete2_const, solver=solver, measure_kind=0, n_block=D["n_block"],
+                                   neval_per_block=L0.get("npb", L0.get("steps")), measurefreq=L0["measurefreq"],
+                                   walkers_per_block=1, thermal_ratio=L0.get("thermal_ratio", 0.1))
+    eng = engine_cls(spec, **kw)
+    dist = np.concatenate([arr(d) for d in D["dist"]])
+    # accumulation = [0, sum(d[1:1]), sum(d[1:2]), ...], every prefix summed left to right (variable.jl:314-315)
+    accum = np.concatenate([np.concatenate([[0.0], [sum(d[: i + 1], 0.0) for i in range(len(d))]]) for d in D["dist"]])
+    eng.set_maps(dist=dist, accum=accum, reweight=arr(D["reweight"]))
+    return eng, D
+
+
+@pytest.mark.parametrize("solver_name", ["vegas", "vegasmc", "mcmc"])
+def test_discrete_composite_loops_against_independent_restatement(solver_name):
+    """CompositeVar of two Discrete leaves with non-uniform distributions: locate, the index draws and the composite
+    probability product, whole loops, against tests/golden/make_golden.py"""
+    from mcintegration_jl_b200 import _abi
+    from oracle_lib import OracleEngine
+    solver = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC, "mcmc": _abi.SOLVER_MCMC}[solver_name]
+    L0 = GOLD["loops_discrete"][solver_name]
+    eng, D = _discrete_loop_engine(OracleEngine, solver, L0, nthreads=1)
+    try:
+        eng.run_local(D["iter"])
+        got, want = _unpack(eng, eng.packed()), L0["out"]
+        np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-13)
+        np.testing.assert_allclose(got["cnt"], want["norm"], rtol=1e-13)
+        np.testing.assert_allclose(got["hist"], want["hist"], rtol=1e-13)
+        if solver_name != "vegas":
+            np.testing.assert_allclose(got["visited"], want["visited"], rtol=1e-13)
+            assert int(got["neval"][0]) == want["neval"]
+        if solver_name == "mcmc":
+            assert got["propose"].tolist() == want["propose"] and got["accept"].tolist() == want["accept"]
+    finally:
+        eng.close()
