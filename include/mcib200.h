@@ -64,8 +64,11 @@ enum {
 /* solver: `solver::Symbol` kwarg of integrate (main.jl:72, dispatch main.jl:253-264) */
 enum { MCI_SOLVER_VEGAS = 0, MCI_SOLVER_VEGASMC = 1, MCI_SOLVER_MCMC = 2 };
 
-/* leaf kinds: Continuous (variable.jl:87-153) / Discrete (variable.jl:272-325) */
-enum { MCI_LEAF_CONTINUOUS = 0, MCI_LEAF_DISCRETE = 1 };
+/* leaf kinds: Continuous (variable.jl:87-153) / Discrete (variable.jl:272-325) / one Cartesian component of a
+ * FermiK{D} momentum (variable.jl:1-21, sampler.jl:109-281).  A FermiK{D} variable is a top-level variable of D = 2
+ * or 3 FERMIK leaves (k_x, k_y[, k_z]: X(leaf0 + c, pos) is component c of K[pos]); it has no map and no histogram
+ * (nbins = 0, adapt = 0) and, like in the reference (test/bubble_FermiK.jl:2,139-140), works under :mcmc only. */
+enum { MCI_LEAF_CONTINUOUS = 0, MCI_LEAF_DISCRETE = 1, MCI_LEAF_FERMIK = 2 };
 
 /*
  * Built-in integrands.  A Julia closure cannot run on the device, so the
@@ -89,6 +92,7 @@ enum mci_integrand_id {
   MCI_F_HYPERSPHERE3 = 13,  /* 3 nested unit balls, dof=[[2],[3],[4]] test/montecarlo.jl:200-216         */
   MCI_F_POLY3 = 14,         /* (x, x^2, x^3), dof=[[1],[1],[1]]       test/thread.jl                       */
   MCI_F_X2_PLUS_Y2 = 15,    /* x1^2+x2^2, pool dof=[[2]]              main.jl:64, vegas/montecarlo.jl:69   */
+  MCI_F_BUBBLE_FERMIK = 16, /* the same polarization bubble on vars (T, K::FermiK{3}, Ext), mcmc  test/bubble_FermiK.jl:54-75 */
   MCI_F_USER = 100          /* the caller's own integrand: CUDA C++ source in mci_problem_t.user_source, compiled with
                                NVRTC at mci_create into a kernel specialised to the problem — the equivalent of the
                                reference taking any closure f(x, c) (main.jl:25-33).  The source defines
@@ -119,9 +123,9 @@ typedef struct mci_leaf_t {
                       variable.jl:147); Discrete: upper-lower+1                     */
   int32_t adapt;   /* 0/1                                                           */
   int32_t lower_i; /* Discrete: `lower`                                             */
-  double lower;    /* Continuous bounds                                             */
-  double upper;
-  double alpha;    /* learning rate of train! (variable.jl:206-239, :369-382)       */
+  double lower;    /* Continuous bounds; FermiK: kF                                 */
+  double upper;    /*                    FermiK: dk (half width of the radial shell) */
+  double alpha;    /* learning rate of train! (variable.jl:206-239, :369-382); FermiK: maxK (stored, never read: sampler.jl) */
 } mci_leaf_t;
 
 /*

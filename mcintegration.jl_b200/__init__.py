@@ -10,9 +10,9 @@ from .configuration import Configuration, ProblemSpec, problem_from_config, maps
 from .engine import CudaEngine, IterationStats, MCIError, fp64_peak_tflops
 from .main import integrate, drive, block_statistics
 from .statistics import Result, average, mean_std, report
-from .variables import CompositeVar, Continuous, Discrete
+from .variables import CompositeVar, Continuous, Discrete, FermiK
 
 __all__ = [
-    "integrate", "report", "Result", "Configuration", "Continuous", "Discrete", "CompositeVar", "integrands",
+    "integrate", "report", "Result", "Configuration", "Continuous", "Discrete", "CompositeVar", "FermiK", "integrands",
     "CudaEngine", "IterationStats", "MCIError", "ProblemSpec", "average", "mean_std", "drive",
 ]

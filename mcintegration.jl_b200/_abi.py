@@ -27,7 +27,7 @@ ERR_COMM = -6
 ERR_MCMC_START = -7
 
 SOLVER_VEGAS, SOLVER_VEGASMC, SOLVER_MCMC = 0, 1, 2
-LEAF_CONTINUOUS, LEAF_DISCRETE = 0, 1
+LEAF_CONTINUOUS, LEAF_DISCRETE, LEAF_FERMIK = 0, 1, 2
 MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE, MEASURE_USER = 0, 1, 2
 JIT_AUTO, JIT_ON, JIT_OFF = 0, 1, 2
 HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
@@ -48,6 +48,7 @@ F_LATTICE_COMP = 12
 F_HYPERSPHERE3 = 13
 F_POLY3 = 14
 F_X2_PLUS_Y2 = 15
+F_BUBBLE_FERMIK = 16
 F_USER = 100
 
 

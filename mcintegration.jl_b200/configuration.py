@@ -9,7 +9,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _abi
-from .variables import CompositeVar, Continuous, Discrete, is_variable
+from .variables import CompositeVar, Continuous, Discrete, FermiK, is_variable
 
 
 def _maxdof(dof):
@@ -210,6 +210,8 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
         if isinstance(L, Continuous):
             leaves.append(dict(kind=_abi.LEAF_CONTINUOUS, nbins=L.nbins, adapt=L.adapt, lower=L.lower, upper=L.upper,
                                alpha=L.alpha))
+        elif isinstance(L, FermiK):  # one leaf per Cartesian component: (kF, δk, maxK) ride in (lower, upper, alpha)
+            leaves.append(dict(kind=_abi.LEAF_FERMIK, nbins=0, adapt=False, lower=L.kF, upper=L.δk, alpha=L.maxK))
         else:
             leaves.append(dict(kind=_abi.LEAF_DISCRETE, nbins=L.nbins, adapt=L.adapt, lower_i=L.lower, alpha=L.alpha))
     sources = [x for x in (getattr(integrand, "source", None), measure_source) if x]
@@ -231,7 +233,7 @@ def maps_from_config(config: Configuration):
     for L in config.leaves():
         if isinstance(L, Continuous):
             grids.append(L.grid)
-        else:
+        elif isinstance(L, Discrete):
             dist.append(L.distribution)
             accum.append(L.accumulation)
     cat = lambda xs: np.concatenate(xs).astype(np.float64) if xs else np.zeros(0)
@@ -245,7 +247,7 @@ def maps_to_config(config: Configuration, grids, dist, accum, reweight):
             n = L.nbins + 1
             L.grid = np.array(grids[go:go + n])
             go += n
-        else:
+        elif isinstance(L, Discrete):
             n = L.nbins
             L.distribution = np.array(dist[do:do + n])
             L.accumulation = np.array(accum[ao:ao + n + 1])

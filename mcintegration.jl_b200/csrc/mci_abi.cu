@@ -101,6 +101,7 @@ struct mci_handle_t {
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
   size_t smem = 0;
   int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0, chain_rows = 0, coop_ci = 0, walkers = 1;
+  bool has_fermik = false; /* some variable is a FermiK (mcmc only; no cooperative create!) */
   uint64_t steps = 0;
   bool maps_dirty = true, have_iteration = false, async_mode = false;
   nccl_comm_t comm = nullptr;
@@ -140,6 +141,7 @@ bool fid_info(int fid, FidInfo &I) {
     case MCI_F_GENZ_CORNER_POOL: I = {1, 1, -1}; return true;
     case MCI_F_GENZ_CORNER_COMP: I = {1, 1, 1}; return true;
     case MCI_F_BUBBLE: I = {1, 5, 1}; return true;
+    case MCI_F_BUBBLE_FERMIK: I = {1, 4, 1}; return true;
     case MCI_F_PRODUCT_4: I = {4, 1, -1}; return true;
     case MCI_F_SPHERE1: I = {1, 1, 2}; return true;
     case MCI_F_SPHERE2: I = {2, 1, 3}; return true;
@@ -311,7 +313,7 @@ int plan(mci_handle_t *h) {
         }
       int coop_min = 5; /* measured: 20 items 1.8x and 5 items 1.2x faster cooperatively, 2-3 items 2x slower */
       if (const char *e = getenv("MCIB200_COOP_MIN")) coop_min = atoi(e);
-      h->coop_ci = worst >= coop_min;
+      h->coop_ci = worst >= coop_min && !h->has_fermik;
     }
     const size_t row_bytes = (size_t)h->chain_rows * (8 + 4 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0));
     const size_t fixed = 32 * 8 + (((size_t)2 * h->pa_len + 1) / 2) * 8;
@@ -502,11 +504,31 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
   h->leaf_grid_off.assign(nleaf, 0); h->leaf_dist_off.assign(nleaf, 0); h->leaf_acc_off.assign(nleaf, 0);
   h->alpha.assign(nleaf, 2.0);
   int go = 0, dd = 0, da = 0, ho = 0, mo = 0;
+  bool has_fermik = false;
   for (int v = 0; v < nv; ++v)
     for (int k = 0; k < P.top_nleaf[v]; ++k) {
       const int l = P.top_first[v] + k;
       const mci_leaf_t &S = p->leaf[l];
       DevLeaf &L = P.leaf[l];
+      if (S.kind == MCI_LEAF_FERMIK) {
+        /* FermiK{D}: D component leaves, no map, no histogram (variable.jl:1-21; accumulate!/train! fall through to
+         * the no-op methods, variable.jl:551,558) */
+        const int D = P.top_nleaf[v];
+        if (D != 2 && D != 3) BAIL(MCI_ERR_INVALID, "a FermiK variable has 2 or 3 component leaves, not %d", D);
+        for (int kk = 0; kk < D; ++kk)
+          if (p->leaf[P.top_first[v] + kk].kind != MCI_LEAF_FERMIK) BAIL(MCI_ERR_INVALID, "FermiK components cannot be bundled with other leaves");
+        if (p->solver != MCI_SOLVER_MCMC)
+          BAIL(MCI_ERR_UNSUPPORTED, "FermiK variables work under :mcmc only (the reference's own restriction, test/bubble_FermiK.jl:2,139-140)");
+        if (p->integrand_id != MCI_F_USER && p->integrand_id != MCI_F_BUBBLE_FERMIK)
+          BAIL(MCI_ERR_INVALID, "integrand %d does not take a FermiK variable", p->integrand_id);
+        if (!(S.lower > 0.0) || !(S.upper > 0.0)) BAIL(MCI_ERR_INVALID, "FermiK needs kF > 0 and dk > 0");
+        L.kind = S.kind; L.nbins = 0; L.adapt = 0; L.lower_i = 0; L.nbins_d = 0.0;
+        L.top = v; L.base = P.top_base[v] + k; L.stride = D; L.hist_off = ho; L.smem_off = mo;
+        L.p0 = S.lower; L.p1 = S.upper;
+        h->alpha[l] = 0.0;
+        has_fermik = true;
+        continue;
+      }
       if (S.nbins < 1) BAIL(MCI_ERR_INVALID, "leaf %d has no bins", l);
       L.kind = S.kind; L.nbins = S.nbins; L.adapt = S.adapt ? 1 : 0; L.lower_i = S.lower_i; L.nbins_d = (double)S.nbins;
       L.top = v; L.base = P.top_base[v] + k; L.stride = P.top_nleaf[v];
@@ -522,6 +544,11 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
       } else BAIL(MCI_ERR_INVALID, "leaf %d: unknown kind %d", l, S.kind);
       if (L.adapt) P.any_adapt = 1;
     }
+  if (p->integrand_id == MCI_F_BUBBLE_FERMIK &&
+      !(nv == 3 && P.top_nleaf[0] == 1 && P.top_nleaf[2] == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS &&
+        P.leaf[1].kind == MCI_LEAF_FERMIK && P.leaf[nleaf - 1].kind == MCI_LEAF_DISCRETE))
+    BAIL(MCI_ERR_INVALID, "integrand %d reads vars (T::Continuous, K::FermiK, Ext::Discrete)", p->integrand_id);
+  h->has_fermik = has_fermik;
   P.map_doubles = mo; P.hist_len = ho;
   h->grid_len = go; h->disc_len = dd; h->accum_len = da; h->hist_len = ho;
   for (int v = 0; v < nv; ++v)
@@ -567,6 +594,7 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
     const double pi = 3.14159265358979323846;
     if (P.fid == MCI_F_GAUSS_ND) P.fconst[0] = pow(2 * pi, -0.5 * P.dof[0]);
     if (P.fid == MCI_F_BUBBLE) P.fconst[0] = 1.0 / pow(2 * pi, P.userdata[4]);
+    if (P.fid == MCI_F_BUBBLE_FERMIK) P.fconst[0] = 1.0 / pow(2 * pi, (double)P.top_nleaf[1]); /* phase = 1/(2pi)^dim, test/bubble_FermiK.jl:71 */
     if (P.fid == MCI_F_HYPERSPHERE3) for (int i = 1; i <= 3; ++i) P.fconst[i - 1] = volume_inverse(i + 1);
   }
   P.pa_dim = std::max(nd, nv);
@@ -645,7 +673,7 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
         double *q = g.data() + h->leaf_grid_off[l];
         for (int i = 0; i < npts; ++i) { double t = (double)i / (npts - 1); q[i] = (1 - t) * S.lower + t * S.upper; }
         q[0] = S.lower; q[npts - 1] = S.upper;
-      } else {
+      } else if (S.kind == MCI_LEAF_DISCRETE) {
         const int n = S.nbins;
         double *d = di.data() + h->leaf_dist_off[l], *a = ac.data() + h->leaf_acc_off[l];
         for (int i = 0; i < n; ++i) d[i] = 1.0 / n;

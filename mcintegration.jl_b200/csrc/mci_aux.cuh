@@ -34,7 +34,7 @@ __global__ void build_maps_kernel(const __grid_constant__ DevProblem P, const do
       out[2 * i] = g[i];
       out[2 * i + 1] = __dsub_rn(g[i + 1], g[i]);
     }
-  } else {
+  } else if (L.kind == MCI_LEAF_DISCRETE) { /* a FermiK component has no map */
     const double *d = dist + leaf_dist_off[l];
     const double *a = accum + leaf_acc_off[l];
     for (int i = threadIdx.x; i < L.nbins; i += blockDim.x) out[i] = d[i];

@@ -58,8 +58,9 @@ struct Walker {
   int bk0;      /* first backup row */
 };
 
-template <class RNG>
+template <class RNG, bool FK = false>
 struct ChainCtxT {
+  static constexpr bool fermik = FK; /* the problem may hold FermiK variables (mcmc only): compile their proposals in */
   const Problem &P;
   const double *maps;
   const PhiloxKey &K;
@@ -144,6 +145,113 @@ __device__ __forceinline__ double leaf_shift(CTX &C, Walker<HP> &W, const DevLea
   return __ddiv_rn(1.0, ratio);
 }
 
+/* ---- FermiK{D} (variable.jl:1-21, sampler.jl:109-281): a momentum kept near the Fermi surface.  The D = 2 or 3
+ * leaves of the variable are its Cartesian components, rows f0, f0 + T[, f0 + 2T] of the walker.  The reference keeps
+ * a `prob` per slot that only :vegas/:vegasmc would read (and shift! corrupts it, sampler.jl:209), so :mcmc — the one
+ * solver it works under — needs none.  Arithmetic in the reference's association order, never contracted. ---- */
+#define MCI_2PI 6.283185307179586476925286766559
+template <bool FK>
+__device__ __forceinline__ bool is_fermik(const Problem &P, int v) {
+  if constexpr (FK) return P.leaf[P.top_first[v]].kind == MCI_LEAF_FERMIK;
+  else return false;
+}
+__device__ __forceinline__ double fermik_shell(double dk) { return __dmul_rn(__dmul_rn(2.0, dk), MCI_2PI); } /* 2 dk 2pi */
+
+/* create!: sampler.jl:109-149.  |K| uniform in [kF - dk, kF + dk), direction uniform in (phi, theta); returns the
+ * proposal volume 2 dk 2pi pi sin(theta) |K|^2 (D = 3) or 2 dk 2pi |K| (D = 2); 0 when |K| <= 0 */
+template <class CTX>
+__device__ __forceinline__ double fermik_create(CTX &C, Walker<false> &W, int v, int pos) {
+  const Problem &P = C.P;
+  const DevLeaf &L = P.leaf[P.top_first[v]];
+  const int D = P.top_nleaf[v], T = W.T, f = frow(L, pos) * T;
+  const double Kamp = __dadd_rn(L.p0, __dmul_rn(__dmul_rn(__dsub_rn(C.rng.rand(C.K), 0.5), 2.0), L.p1));
+  if (Kamp <= 0.0) return 0.0;
+  double sp, cp;
+  sincos(__dmul_rn(MCI_2PI, C.rng.rand(C.K)), &sp, &cp);
+  if (D == 3) {
+    double st, ct;
+    sincos(__dmul_rn(MCI_PI, C.rng.rand(C.K)), &st, &ct);
+    W.data[f] = __dmul_rn(__dmul_rn(Kamp, cp), st);
+    W.data[f + T] = __dmul_rn(__dmul_rn(Kamp, sp), st);
+    W.data[f + 2 * T] = __dmul_rn(Kamp, ct);
+    return __dmul_rn(__dmul_rn(fermik_shell(L.p1), MCI_PI), __dmul_rn(st, __dmul_rn(Kamp, Kamp)));
+  }
+  W.data[f] = __dmul_rn(Kamp, cp);
+  W.data[f + T] = __dmul_rn(Kamp, sp);
+  return __dmul_rn(fermik_shell(L.p1), Kamp);
+}
+
+/* remove!: sampler.jl:160-189.  0 unless kF - dk < |K| < kF + dk (and sin(theta) >= 1e-15), else 1 / the volume */
+template <class CTX>
+__device__ __forceinline__ double fermik_remove(CTX &C, Walker<false> &W, int v, int pos) {
+  const Problem &P = C.P;
+  const DevLeaf &L = P.leaf[P.top_first[v]];
+  const int D = P.top_nleaf[v], T = W.T, f = frow(L, pos) * T;
+  const double k1 = W.data[f], k2 = W.data[f + T];
+  const double r2 = __dadd_rn(__dmul_rn(k1, k1), __dmul_rn(k2, k2));
+  if (D == 3) {
+    const double k3 = W.data[f + 2 * T];
+    const double Kamp = sqrt(__dadd_rn(r2, __dmul_rn(k3, k3)));
+    if (!(__dsub_rn(L.p0, L.p1) < Kamp && Kamp < __dadd_rn(L.p0, L.p1))) return 0.0;
+    const double st = __ddiv_rn(sqrt(r2), Kamp);
+    if (st < 1.0e-15) return 0.0;
+    return __ddiv_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(fermik_shell(L.p1), MCI_PI), st), __dmul_rn(Kamp, Kamp)));
+  }
+  const double Kamp = sqrt(r2);
+  if (!(__dsub_rn(L.p0, L.p1) < Kamp && Kamp < __dadd_rn(L.p0, L.p1))) return 0.0;
+  return __ddiv_rn(1.0, __dmul_rn(fermik_shell(L.p1), Kamp));
+}
+
+/* shift!: sampler.jl:199-251, one of three moves with probability 1/3 each — rescale |K| by a factor uniform in
+ * [1/1.5, 1.5) (returns the factor for D = 3, 1 for D = 2), redraw the direction uniformly on the sphere / circle, or
+ * displace every component by up to dk/2.  The old K goes to the backup rows (K[end] = K[idx]). */
+template <class CTX>
+__device__ __forceinline__ double fermik_shift(CTX &C, Walker<false> &W, int v, int pos) {
+  const Problem &P = C.P;
+  const DevLeaf &L = P.leaf[P.top_first[v]];
+  const int D = P.top_nleaf[v], T = W.T, f = frow(L, pos) * T, b = W.bk0 * T;
+  for (int c = 0; c < D; ++c) { W.data[b + c * T] = W.data[f + c * T]; W.gidx[b + c * T] = 0; }
+  const double x = C.rng.rand(C.K);
+  if (x < 1.0 / 3) {
+    const double lam = 1.5, inv = 1.0 / 1.5;
+    const double ratio = __dadd_rn(inv, __dmul_rn(C.rng.rand(C.K), __dsub_rn(lam, inv)));
+    for (int c = 0; c < D; ++c) W.data[f + c * T] = __dmul_rn(W.data[f + c * T], ratio);
+    return D == 2 ? 1.0 : ratio;
+  } else if (x < 2.0 / 3) {
+    double sp, cp;
+    sincos(__dmul_rn(C.rng.rand(C.K), MCI_2PI), &sp, &cp);
+    const double k1 = W.data[f], k2 = W.data[f + T];
+    const double r2 = __dadd_rn(__dmul_rn(k1, k1), __dmul_rn(k2, k2));
+    if (D == 3) {
+      double st, ct;
+      sincos(acos(__dsub_rn(1.0, __dmul_rn(2.0, C.rng.rand(C.K)))), &st, &ct);
+      const double k3 = W.data[f + 2 * T];
+      const double Kamp = sqrt(__dadd_rn(r2, __dmul_rn(k3, k3)));
+      W.data[f] = __dmul_rn(__dmul_rn(Kamp, cp), st);
+      W.data[f + T] = __dmul_rn(__dmul_rn(Kamp, sp), st);
+      W.data[f + 2 * T] = __dmul_rn(Kamp, ct);
+    } else {
+      const double Kamp = sqrt(r2);
+      W.data[f] = __dmul_rn(Kamp, cp);
+      W.data[f + T] = __dmul_rn(Kamp, sp);
+    }
+    return 1.0;
+  }
+  for (int c = 0; c < D; ++c)
+    W.data[f + c * T] = __dadd_rn(W.data[f + c * T], __dmul_rn(__dsub_rn(C.rng.rand(C.K), 0.5), L.p1));
+  return 1.0;
+}
+
+/* the constructor's fill (variable.jl:13): every component kF / sqrt(D) */
+__device__ __forceinline__ void fermik_reset(const Problem &P, Walker<false> &W) {
+  for (int v = 0; v < P.nv; ++v)
+    if (P.leaf[P.top_first[v]].kind == MCI_LEAF_FERMIK) {
+      const int D = P.top_nleaf[v];
+      const double k0 = __ddiv_rn(P.leaf[P.top_first[v]].p0, sqrt((double)D));
+      for (int r = P.top_base[v]; r < P.top_base[v] + D * P.maxdof[v]; ++r) { W.data[r * W.T] = k0; W.gidx[r * W.T] = 0; }
+    }
+}
+
 /* probability of (variable v, slot pos): the leaf's own for plain variables, the product over the leaves in leaf
  * order for a CompositeVar (sampler.jl:431-440 keeps exactly this product in its cache) */
 __device__ __forceinline__ double top_prob(const Problem &P, const Walker<true> &W, int v, int pos) {
@@ -159,6 +267,7 @@ template <bool HP, class CTX>
 __device__ __forceinline__ double var_create(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
+  if constexpr (CTX::fermik && !HP) { if (is_fermik<true>(P, v)) return fermik_create(C, W, v, pos); }
   if (nl == 1) return leaf_create(C, W, P.leaf[P.top_first[v]], pos);
   double prop = 1.0;
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_create(C, W, P.leaf[P.top_first[v] + k], pos));
@@ -168,6 +277,7 @@ template <bool HP, class CTX>
 __device__ __forceinline__ double var_remove(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
+  if constexpr (CTX::fermik && !HP) { if (is_fermik<true>(P, v)) return fermik_remove(C, W, v, pos); }
   if (nl == 1) return leaf_remove(C, W, P.leaf[P.top_first[v]], pos);
   double prop = 1.0;
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_remove(C, W, P.leaf[P.top_first[v] + k], pos));
@@ -177,6 +287,7 @@ template <bool HP, class CTX>
 __device__ __forceinline__ double var_shift(CTX &C, Walker<HP> &W, int v, int pos) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
+  if constexpr (CTX::fermik && !HP) { if (is_fermik<true>(P, v)) return fermik_shift(C, W, v, pos); }
   if (nl == 1) return leaf_shift(C, W, P.leaf[P.top_first[v]], pos, 0);
   double prop = 1.0;
   for (int k = 0; k < nl; ++k) prop = __dmul_rn(prop, leaf_shift(C, W, P.leaf[P.top_first[v] + k], pos, k));
@@ -211,6 +322,12 @@ template <bool HP, class CTX>
 __device__ __forceinline__ void var_initialize(CTX &C, Walker<HP> &W, int v) {
   const Problem &P = C.P;
   const int nl = P.top_nleaf[v];
+  if constexpr (CTX::fermik && !HP) {
+    if (is_fermik<true>(P, v)) {
+      for (int pos = 1; pos <= P.maxdof[v]; ++pos) fermik_create(C, W, v, pos);
+      return;
+    }
+  }
   for (int k = 0; k < nl; ++k)
     for (int pos = 1; pos <= P.maxdof[v]; ++pos) leaf_create(C, W, P.leaf[P.top_first[v] + k], pos);
 }
@@ -319,6 +436,16 @@ struct ChainNobs {
 #endif
 };
 #define PA_IDX(P, u, i, j) (((u) * (P).nd + (i)) * (P).pa_dim + (j))
+/* FermiK proposals are compiled into the mcmc kernel of the integrand that takes one, and into a JIT program whose
+ * problem holds one: every other mcmc kernel stays as it was */
+template <int FID>
+__device__ __host__ constexpr bool chain_has_fermik() {
+#ifdef MCI_JIT
+  return JitProblem::has_fermik;
+#else
+  return FID == MCI_F_BUBBLE_FERMIK;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* VegasMC                                                                                      */
@@ -603,8 +730,10 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
-  ChainCtxT<RngAhead<MCMC_DRAWS_AHEAD>> C(P, S.maps, K);
+  constexpr bool FK = chain_has_fermik<FID>();
+  ChainCtxT<RngAhead<MCMC_DRAWS_AHEAD>, FK> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
+  if constexpr (FK) fermik_reset(P, W);
   ChainX X{W.data, &P, W.T};
   double rw[NI + 1];
 #pragma unroll

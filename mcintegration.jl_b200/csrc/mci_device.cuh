@@ -53,6 +53,7 @@ struct DevLeaf {
   int smem_off; /* offset (in doubles) of this leaf's map inside the CTA's shared-memory map area   */
   int pad_;
   double nbins_d;
+  double p0, p1; /* FermiK component: kF, dk                                                         */
 };
 
 /* Passed by value as a __grid_constant__ kernel parameter (constant bank, uniform loads). */

@@ -164,6 +164,28 @@ struct Integrand<MCI_F_BUBBLE> {
   }
 };
 
+/* test/bubble_FermiK.jl:54-75: the same diagram on vars (T, K::FermiK{dim}, Ext) — the loop momentum is the FermiK
+ * variable itself (leaves 1..dim = its Cartesian components), so there is no spherical Jacobian; userdata as above;
+ * fconst[0] = 1/(2pi)^dim (the test fixes dim = 3) */
+template <>
+struct Integrand<MCI_F_BUBBLE_FERMIK> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA, bool EXACT = false>
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
+    const double *ud = P.userdata;
+    const int D = P.nleaf - 2;
+    double kF = ud[0], beta = ud[1], me = ud[2], spin = ud[3];
+    double tau = X(0, 1), k0 = X(1, 1), k1 = X(2, 1), k2 = D == 3 ? X(3, 1) : 0.0;
+    int ext = (int)X(D + 1, 1);
+    double kq0 = k0 + ud[6 + ext - 1];
+    double w1 = ((k0 * k0 + k1 * k1 + k2 * k2) - kF * kF) / (2 * me);
+    double g1 = green(tau, w1, beta);
+    double w2 = ((kq0 * kq0 + k1 * k1 + k2 * k2) - kF * kF) / (2 * me);
+    double g2 = green(-tau, w2, beta);
+    w[0] = g1 * g2 * spin * P.fconst[0]; /* * cos(2 pi 0 tau / beta) == 1 */
+  }
+};
+
 /* f_k = prod_i (1 + a_k (x_i - 1/2)), a = userdata[0..3] */
 template <>
 struct Integrand<MCI_F_PRODUCT_4> {
@@ -287,5 +309,7 @@ struct Integrand<MCI_F_X2_PLUS_Y2> {
   M(MCI_F_GAUSS_ND) M(MCI_F_LOG_OVER_SQRT) M(MCI_F_GENZ_CORNER_POOL) M(MCI_F_GENZ_CORNER_COMP) M(MCI_F_BUBBLE)      \
   M(MCI_F_PRODUCT_4) M(MCI_F_SPHERE1) M(MCI_F_SPHERE2) M(MCI_F_DISCRETE_X) M(MCI_F_DISCRETE2_CONST)                 \
   M(MCI_F_LATTICE_POOL) M(MCI_F_LATTICE_COMP) M(MCI_F_HYPERSPHERE3) M(MCI_F_POLY3) M(MCI_F_X2_PLUS_Y2)
+/* integrands on a FermiK variable: mcmc only (test/bubble_FermiK.jl:139-140) */
+#define MCI_FOR_EACH_MCMC_ONLY_FID(M) M(MCI_F_BUBBLE_FERMIK)
 
 }  // namespace mci

@@ -101,6 +101,8 @@ std::string jit_problem_header(const DevProblem &P) {
   std::string tabs, members, o;
   char buf[640];
   const int nvv = P.nv > 0 ? P.nv : 1;
+  bool has_fermik = false;
+  for (int l = 0; l < P.nleaf; ++l) has_fermik = has_fermik || P.leaf[l].kind == MCI_LEAF_FERMIK;
   itab(tabs, members, "top_nleaf", P.top_nleaf, nvv); itab(tabs, members, "top_first", P.top_first, nvv);
   itab(tabs, members, "top_base", P.top_base, nvv); itab(tabs, members, "maxdof", P.maxdof, nvv);
   itab(tabs, members, "top_tslot", P.top_tslot, nvv); itab(tabs, members, "top_skip", P.top_skip, nvv);
@@ -113,8 +115,8 @@ std::string jit_problem_header(const DevProblem &P) {
   tabs += buf;
   for (int l = 0; l < P.nleaf; ++l) {
     const DevLeaf &L = P.leaf[l];
-    snprintf(buf, sizeof buf, "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, 0, %d.0},\n", L.kind, L.nbins, L.adapt, L.lower_i, L.map_off,
-             L.acc_off, L.hist_off, L.top, L.base, L.stride, L.smem_off, L.nbins);
+    snprintf(buf, sizeof buf, "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, 0, %d.0, %.17g, %.17g},\n", L.kind, L.nbins, L.adapt,
+             L.lower_i, L.map_off, L.acc_off, L.hist_off, L.top, L.base, L.stride, L.smem_off, L.nbins, L.p0, L.p1);
     tabs += buf;
   }
   tabs += "};\n";
@@ -125,9 +127,9 @@ std::string jit_problem_header(const DevProblem &P) {
   snprintf(buf, sizeof buf,
            "  static constexpr int solver = %d, fid = %d, measure_kind = %d, ni = %d, nd = %d, nv = %d, nleaf = %d, n_draw = %d;\n"
            "  static constexpr int obs_total = %d, hist_len = %d, pa_dim = %d, measurefreq = %d, need_pad = %d, any_adapt = %d;\n"
-           "  static constexpr int map_doubles = %d, n_tslot = %d;\n",
+           "  static constexpr int map_doubles = %d, n_tslot = %d;\n  static constexpr bool has_fermik = %s;\n",
            P.solver, P.fid, P.measure_kind, P.ni, P.nd, P.nv, P.nleaf, P.n_draw, P.obs_total, P.hist_len, P.pa_dim, P.measurefreq,
-           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot);
+           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot, has_fermik ? "true" : "false");
   o += buf;
   o += members;
   o += "  struct T_leaf { __device__ __forceinline__ const DevLeaf &operator[](int i) const { return jit_tab::leaf[i]; } } leaf;\n";

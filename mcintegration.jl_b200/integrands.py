@@ -159,6 +159,13 @@ def bubble(para: BubblePara | None = None) -> Integrand:
     return Integrand("bubble", _abi.F_BUBBLE, 1, tuple(ud))
 
 
+def bubble_fermik(para: BubblePara | None = None) -> Integrand:
+    """test/bubble_FermiK.jl:54-75; variables (T, K::FermiK{3}, Ext), solver=:mcmc; userdata as `bubble`."""
+    para = para or BubblePara()
+    ud = (para.kF, para.β, para.me, float(para.spin), float(para.dim), float(para.Qsize), *para.extQ)
+    return Integrand("bubble_fermik", _abi.F_BUBBLE_FERMIK, 1, tuple(ud))
+
+
 REGISTRY = {
     f.name: f
     for f in (gauss_nd, log_over_sqrt, sphere1, sphere2, discrete_x, discrete2_const, lattice_pool, lattice_comp,

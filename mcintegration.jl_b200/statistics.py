@@ -119,7 +119,7 @@ def report_config(config, io=None):
         for n in config.neighbor[idx - 1]:
             row(f"  {idx} ->Norm:" if n == Nd else f"  {idx} -> {n:2d}:", propose[0, idx - 1, n - 1], accept[0, idx - 1, n - 1])
     print(bar, file=io)
-    kinds = {"Continuous": "Continuous", "Discrete": "Discrete", "CompositeVar": "Composite"}
+    kinds = {"Continuous": "Continuous", "Discrete": "Discrete", "CompositeVar": "Composite", "FermiK": "FermiK"}
     for title, u in (("ChangeVariable", 1), ("SwapVariable", 2)):
         print(f"{title:<20s} {'Proposed':>12s} {'Accepted':>12s} {'Ratio  ':>12s}", file=io)
         for idx in range(1, Nd):

@@ -146,6 +146,40 @@ class Discrete:
                 + (f" Offset = {self.offset}." if self.offset > 0 else ""))
 
 
+class FermiK:
+    """FermiK(dim, kF, δk, maxK, size=16; offset=0) (variable.jl:1-21): a momentum proposed near the Fermi surface
+    (sampler.jl:109-281).  Has no map and no histogram; like in the reference (test/bubble_FermiK.jl:2,139-140) it
+    works under solver=:mcmc only."""
+
+    def __init__(self, dim, kF, δk, maxK, size=MaxOrder, *, offset=0):
+        assert offset + 1 < size
+        assert dim in (2, 3), "FermiK is implemented for dim = 2 or 3 (sampler.jl:124-148)"
+        self.dim = int(dim)
+        self.kF = float(kF)
+        self.δk = float(δk)
+        self.maxK = float(maxK)
+        self.size = size  # k = zeros(dim, size) .+ kF / sqrt(dim): no extra cache element (variable.jl:13)
+        self.offset = int(offset)
+        self.adapt = False
+        self.histogram = np.array([0.0])
+
+    kind = 2
+
+    def poolsize(self):
+        return self.size
+
+    def resize(self, size):  # not defined by the reference for FermiK; pools only ever grow
+        assert size > self.size
+        self.size = size
+
+    def leaves(self):
+        return [self] * self.dim  # one ABI leaf per component
+
+    def __repr__(self):
+        return (f"{self.dim}D FermiK variable ∈ [0, {self.maxK})." + f" Max number = {self.size - 1 - self.offset}."
+                + (f" Offset = {self.offset}." if self.offset > 0 else ""))
+
+
 class CompositeVar:
     """CompositeVar(vargs...; adapt=true, offset=0, size=16) (variable.jl:415-427): the bundled
     leaves are sampled together; the probability is the product of the leaves' probabilities."""
@@ -188,4 +222,4 @@ class CompositeVar:
 
 
 def is_variable(v):
-    return isinstance(v, (Continuous, Discrete, CompositeVar))
+    return isinstance(v, (Continuous, Discrete, CompositeVar, FermiK))

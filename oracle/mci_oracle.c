@@ -295,6 +295,7 @@ typedef struct {
 
 typedef struct {
   int n_leaf, first_leaf, offset, len, composite, adapt;
+  int fermik; /* FermiK{D}: the n_leaf = D leaves are its Cartesian components (variable.jl:1-21) */
   double *prob; /* composite: own array; otherwise aliases the leaf's */
   double prob_cache;
 } otop;
@@ -405,9 +406,78 @@ static double leaf_remove(oleaf *l, int idx) { return l->kind == MCI_LEAF_CONTIN
 static double leaf_shift(oleaf *l, int idx, orng *rng) { return l->kind == MCI_LEAF_CONTINUOUS ? cont_shift(l, idx, rng) : disc_shift(l, idx, rng); }
 static void leaf_shift_rollback(oleaf *l, int idx) { if (l->kind == MCI_LEAF_CONTINUOUS) cont_shift_rollback(l, idx); else disc_shift_rollback(l, idx); }
 
+/* ---- FermiK{D}: sampler.jl:109-281.  Component c of K[idx] is leaf[first + c].data[idx - 1]; leaf.lower = kF,
+ * leaf.upper = dk.  K.prob is read by :vegas/:vegasmc only, under which the reference itself declares FermiK broken
+ * (test/bubble_FermiK.jl:2) and which mci_create / orc_create refuse, so it is not kept. ---- */
+static double fermik_create(oleaf *K, int D, int idx, orng *rng) { /* :109-149 */
+  double kF = K[0].lower, dk = K[0].upper;
+  double Kamp = kF + (orng_rand(rng) - 0.5) * 2.0 * dk;
+  if (Kamp <= 0.0) return 0.0;
+  double phi = 2 * PI * orng_rand(rng);
+  if (D == 3) {
+    double theta = PI * orng_rand(rng);
+    K[0].data[idx - 1] = Kamp * cos(phi) * sin(theta);
+    K[1].data[idx - 1] = Kamp * sin(phi) * sin(theta);
+    K[2].data[idx - 1] = Kamp * cos(theta);
+    return 2 * dk * (2 * PI) * PI * (sin(theta) * (Kamp * Kamp));
+  }
+  K[0].data[idx - 1] = Kamp * cos(phi);
+  K[1].data[idx - 1] = Kamp * sin(phi);
+  return 2 * dk * (2 * PI) * Kamp;
+}
+static double fermik_remove(oleaf *K, int D, int idx) { /* :160-189 */
+  double kF = K[0].lower, dk = K[0].upper;
+  double k1 = K[0].data[idx - 1], k2 = K[1].data[idx - 1];
+  if (D == 3) {
+    double k3 = K[2].data[idx - 1];
+    double Kamp = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+    if (!(kF - dk < Kamp && Kamp < kF + dk)) return 0.0;
+    double sint = sqrt(k1 * k1 + k2 * k2) / Kamp;
+    if (sint < 1.0e-15) return 0.0;
+    return 1.0 / (2 * dk * (2 * PI) * PI * sint * (Kamp * Kamp));
+  }
+  double Kamp = sqrt(k1 * k1 + k2 * k2);
+  if (!(kF - dk < Kamp && Kamp < kF + dk)) return 0.0;
+  return 1.0 / (2 * dk * (2 * PI) * Kamp);
+}
+static double fermik_shift(oleaf *K, int D, int idx, orng *rng) { /* :199-251 */
+  int e = K[0].len - 1;
+  for (int c = 0; c < D; ++c) K[c].data[e] = K[c].data[idx - 1]; /* K[end] = K[idx] */
+  double x = orng_rand(rng);
+  if (x < 1.0 / 3) {
+    double lambda = 1.5;
+    double ratio = 1.0 / lambda + orng_rand(rng) * (lambda - 1.0 / lambda);
+    for (int c = 0; c < D; ++c) K[c].data[idx - 1] *= ratio;
+    return D == 2 ? 1.0 : ratio;
+  } else if (x < 2.0 / 3) {
+    double phi = orng_rand(rng) * (2 * PI);
+    double k1 = K[0].data[idx - 1], k2 = K[1].data[idx - 1];
+    if (D == 3) {
+      double theta = acos(1 - 2 * orng_rand(rng));
+      double k3 = K[2].data[idx - 1];
+      double Kamp = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+      K[0].data[idx - 1] = Kamp * cos(phi) * sin(theta);
+      K[1].data[idx - 1] = Kamp * sin(phi) * sin(theta);
+      K[2].data[idx - 1] = Kamp * cos(theta);
+    } else {
+      double Kamp = sqrt(k1 * k1 + k2 * k2);
+      K[0].data[idx - 1] = Kamp * cos(phi);
+      K[1].data[idx - 1] = Kamp * sin(phi);
+    }
+    return 1.0;
+  }
+  for (int c = 0; c < D; ++c) K[c].data[idx - 1] = K[c].data[idx - 1] + (orng_rand(rng) - 0.5) * K[0].upper;
+  return 1.0;
+}
+static void fermik_shift_rollback(oleaf *K, int D, int idx) { /* :253-257 */
+  int e = K[0].len - 1;
+  for (int c = 0; c < D; ++c) K[c].data[idx - 1] = K[c].data[e];
+}
+
 /* top-level dispatch incl. CompositeVar: sampler.jl:410-462 */
 static double var_create(oconfig *c, int vi, int idx) {
   otop *T = &c->top[vi];
+  if (T->fermik) return fermik_create(&c->leaf[T->first_leaf], T->n_leaf, idx, &c->rng);
   if (!T->composite) return leaf_create(&c->leaf[T->first_leaf], idx, &c->rng);
   double prop = 1.0;
   T->prob[idx - 1] = 1.0;
@@ -420,6 +490,7 @@ static double var_create(oconfig *c, int vi, int idx) {
 }
 static double var_remove(oconfig *c, int vi, int idx) {
   otop *T = &c->top[vi];
+  if (T->fermik) return fermik_remove(&c->leaf[T->first_leaf], T->n_leaf, idx);
   if (!T->composite) return leaf_remove(&c->leaf[T->first_leaf], idx);
   double prop = 1.0;
   for (int k = 0; k < T->n_leaf; ++k) prop *= leaf_remove(&c->leaf[T->first_leaf + k], idx);
@@ -427,6 +498,7 @@ static double var_remove(oconfig *c, int vi, int idx) {
 }
 static double var_shift(oconfig *c, int vi, int idx) {
   otop *T = &c->top[vi];
+  if (T->fermik) return fermik_shift(&c->leaf[T->first_leaf], T->n_leaf, idx, &c->rng);
   if (!T->composite) return leaf_shift(&c->leaf[T->first_leaf], idx, &c->rng);
   double prop = 1.0;
   T->prob_cache = T->prob[idx - 1];
@@ -440,6 +512,7 @@ static double var_shift(oconfig *c, int vi, int idx) {
 }
 static void var_shift_rollback(oconfig *c, int vi, int idx) {
   otop *T = &c->top[vi];
+  if (T->fermik) { fermik_shift_rollback(&c->leaf[T->first_leaf], T->n_leaf, idx); return; }
   for (int k = 0; k < T->n_leaf; ++k) leaf_shift_rollback(&c->leaf[T->first_leaf + k], idx);
   if (T->composite) T->prob[idx - 1] = T->prob_cache;
 }
@@ -467,6 +540,10 @@ static void var_accumulate(oconfig *c, int vi, int idx, double w) {
 static void var_initialize(oconfig *c, int vi) {
   otop *T = &c->top[vi];
   int last = T->offset + c->maxdof[vi];
+  if (T->fermik) { /* the generic initialize!(T, config), variable.jl:576-580 */
+    for (int i = 1 + T->offset; i <= last; ++i) fermik_create(&c->leaf[T->first_leaf], T->n_leaf, i, &c->rng);
+    return;
+  }
   for (int k = 0; k < T->n_leaf; ++k)
     for (int i = 1 + T->offset; i <= last; ++i) leaf_create(&c->leaf[T->first_leaf + k], i, &c->rng);
   if (T->composite)
@@ -562,6 +639,19 @@ static void eval_all(const oconfig *c, int id, double *w) {
     double w2 = ((kq0 * kq0 + kq1 * kq1 + kq2 * kq2) - kF * kF) / (2 * me);
     double g2 = green(-tau, w2, beta);
     w[0] = g1 * g2 * spin * factor * cos(2 * PI * 0 * tau / beta);
+    break; }
+  case MCI_F_BUBBLE_FERMIK: { /* test/bubble_FermiK.jl:54-75, vars (T, K::FermiK{dim}, Ext); userdata as MCI_F_BUBBLE */
+    int D = c->nleaf - 2;
+    double kF = ud[0], beta = ud[1], me = ud[2], spin = ud[3];
+    double tau = X(c, 0, 1), k0 = X(c, 1, 1), k1 = X(c, 2, 1), k2 = D == 3 ? X(c, 3, 1) : 0.0;
+    int ext = (int)X(c, D + 1, 1);
+    double kq0 = k0 + ud[6 + ext - 1];
+    double w1 = ((k0 * k0 + k1 * k1 + k2 * k2) - kF * kF) / (2 * me);
+    double g1 = green(tau, w1, beta);
+    double w2 = ((kq0 * kq0 + k1 * k1 + k2 * k2) - kF * kF) / (2 * me);
+    double g2 = green(-tau, w2, beta);
+    double phase = 1.0 / pow(2 * PI, (double)D);
+    w[0] = g1 * g2 * spin * phase * cos(2 * PI * 0 * tau / beta);
     break; }
   case MCI_F_PRODUCT_4: { /* SURVEY §8d C5 */
     int d = c->dof[0];
@@ -664,7 +754,17 @@ int orc_create(const mci_problem_t *p, orc_handle **out) {
     first += p->topvar_nleaf[v];
   }
   if (first != h->nleaf) { snprintf(g_err, sizeof g_err, "sum(topvar_nleaf) != n_leaf"); free(h); return MCI_ERR_INVALID; }
-  for (int l = 0; l < h->nleaf; ++l) h->leaf[l] = p->leaf[l];
+  for (int l = 0; l < h->nleaf; ++l) {
+    h->leaf[l] = p->leaf[l];
+    if (p->leaf[l].kind == MCI_LEAF_FERMIK) { /* no map, no histogram; mcmc only (test/bubble_FermiK.jl:2,139-140) */
+      h->leaf[l].nbins = 0; h->leaf[l].adapt = 0;
+      if (p->solver != MCI_SOLVER_MCMC) {
+        snprintf(g_err, sizeof g_err, "FermiK variables work under :mcmc only");
+        free(h);
+        return MCI_ERR_UNSUPPORTED;
+      }
+    }
+  }
   for (int i = 0; i < h->ni; ++i)
     for (int v = 0; v < h->nv; ++v) h->dof[i * h->nv + v] = p->dof[i * h->nv + v];
   for (int v = 0; v < h->nv; ++v) h->dof[h->ni * h->nv + v] = 0; /* configuration.jl:153 */
@@ -691,7 +791,7 @@ int orc_create(const mci_problem_t *p, orc_handle **out) {
   for (int l = 0; l < h->nleaf; ++l) {
     h->leaf_hist_off[l] = ho; ho += h->leaf[l].nbins;
     if (h->leaf[l].kind == MCI_LEAF_CONTINUOUS) { h->leaf_grid_off[l] = go; go += h->leaf[l].nbins + 1; }
-    else { h->leaf_disc_off[l] = dd; dd += h->leaf[l].nbins; h->leaf_accum_off[l] = da; da += h->leaf[l].nbins + 1; }
+    else if (h->leaf[l].kind == MCI_LEAF_DISCRETE) { h->leaf_disc_off[l] = dd; dd += h->leaf[l].nbins; h->leaf_accum_off[l] = da; da += h->leaf[l].nbins + 1; }
   }
   h->grid_len = go; h->disc_len = dd; h->hist_len = ho;
   h->grids = (double *)calloc(go + 1, sizeof(double));
@@ -709,7 +809,7 @@ int orc_create(const mci_problem_t *p, orc_handle **out) {
         g[i] = (1 - t) * L->lower + t * L->upper;
       }
       g[0] = L->lower; g[npts - 1] = L->upper;
-    } else { /* variable.jl:305-315: uniform distribution and prefix sums */
+    } else if (L->kind == MCI_LEAF_DISCRETE) { /* variable.jl:305-315: uniform distribution and prefix sums */
       int n = L->nbins;
       double *d = h->disc_dist + h->leaf_disc_off[l], *a = h->disc_accum + h->leaf_accum_off[l];
       for (int i = 0; i < n; ++i) d[i] = 1.0 / n;
@@ -803,7 +903,8 @@ static oconfig *config_new(const orc_handle *h) {
   for (int v = 0; v < h->nv; ++v) {
     otop *T = &c->top[v];
     T->n_leaf = h->topvar_nleaf[v]; T->first_leaf = h->topvar_first[v]; T->offset = h->topvar_offset[v];
-    T->len = len[v]; T->composite = T->n_leaf > 1; T->prob_cache = 1.0;
+    T->fermik = h->leaf[h->topvar_first[v]].kind == MCI_LEAF_FERMIK;
+    T->len = len[v]; T->composite = T->n_leaf > 1 && !T->fermik; T->prob_cache = 1.0;
     for (int k = 0; k < T->n_leaf; ++k) {
       int l = T->first_leaf + k;
       oleaf *L = &c->leaf[l];
@@ -811,13 +912,15 @@ static oconfig *config_new(const orc_handle *h) {
       L->kind = P->kind; L->nbins = P->nbins; L->adapt = P->adapt; L->lower_i = P->lower_i;
       L->lower = P->lower; L->upper = P->upper; L->alpha = P->alpha;
       if (P->kind == MCI_LEAF_CONTINUOUS) L->grid = h->grids + h->leaf_grid_off[l];
-      else { L->dist = h->disc_dist + h->leaf_disc_off[l]; L->accum = h->disc_accum + h->leaf_accum_off[l]; }
+      else if (P->kind == MCI_LEAF_DISCRETE) { L->dist = h->disc_dist + h->leaf_disc_off[l]; L->accum = h->disc_accum + h->leaf_accum_off[l]; }
       L->len = len[v];
       L->off = T->offset;
       L->data = q; q += len[v];
       L->prob = q; q += len[v];
       L->gidx = (int *)q; q += len[v]; /* one double slot per int: plenty */
       for (int i = 0; i < len[v]; ++i) { L->prob[i] = 1.0; L->gidx[i] = 1; L->data[i] = P->kind == MCI_LEAF_CONTINUOUS ? P->lower : (double)P->lower_i; }
+      if (P->kind == MCI_LEAF_FERMIK) /* zeros(dim, size) .+ kF / sqrt(dim), variable.jl:13 */
+        for (int i = 0; i < len[v]; ++i) L->data[i] = P->lower / sqrt((double)T->n_leaf);
     }
     if (T->composite) { T->prob = q; q += len[v]; for (int i = 0; i < len[v]; ++i) T->prob[i] = 1.0; }
     else T->prob = c->leaf[T->first_leaf].prob;

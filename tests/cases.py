@@ -68,6 +68,13 @@ def case(name):
                                              mci.Discrete(1, para.Qsize, adapt=False)),
                                         dof=[[1, 1, 1, 1, 1]], obs=[[0.0] * para.Qsize]),
                        expect=None, para=para),
+        # test/bubble_FermiK.jl:91-105: the same diagram on (T, K::FermiK{3}, Ext), :mcmc only
+        "bubble_fermik": dict(f=I.bubble_fermik(para), measure="bin_by_discrete",
+                              cfg=lambda: dict(var=(mci.Continuous(0.0, para.β, alpha=3.0),
+                                                    mci.FermiK(3, para.kF, 0.2 * para.kF, 10.0 * para.kF),
+                                                    mci.Discrete(1, para.Qsize, adapt=False)),
+                                               dof=[[1, 1, 1]], obs=[[0.0] * para.Qsize]),
+                              expect=None, para=para),
     }
     return C[name]
 

@@ -506,6 +506,202 @@ def loop_mcmc(Q, rw, seed, it, nblock, steps, mf, thermal):
     return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose=prop_c, accept=acc_c, neval=neval)
 
 
+class FermiKPool:
+    """FermiK{D}: create!/remove!/shift!/swap! of src/distribution/sampler.jl:109-281 (1-based slots; data[c][pos] is
+    Cartesian component c of K[pos]; slot nslot+1 plays K[end], the rollback cache).  K.prob is not kept: only
+    :vegas/:vegasmc read it, and the reference runs FermiK under :mcmc alone (test/bubble_FermiK.jl:2,139-140)."""
+
+    def __init__(self, D, kF, dk, nslot):
+        self.D, self.kF, self.dk = D, kF, dk
+        self.data = [[kF / math.sqrt(D)] * (nslot + 2) for _ in range(D)]  # variable.jl:13
+
+    def create(self, pos, rng):
+        Kamp = self.kF + (rng.rand() - 0.5) * 2.0 * self.dk
+        if Kamp <= 0.0:
+            return 0.0
+        phi = 2 * math.pi * rng.rand()
+        if self.D == 3:
+            th = math.pi * rng.rand()
+            self.data[0][pos] = Kamp * math.cos(phi) * math.sin(th)
+            self.data[1][pos] = Kamp * math.sin(phi) * math.sin(th)
+            self.data[2][pos] = Kamp * math.cos(th)
+            return 2 * self.dk * (2 * math.pi) * math.pi * (math.sin(th) * (Kamp * Kamp))
+        self.data[0][pos] = Kamp * math.cos(phi)
+        self.data[1][pos] = Kamp * math.sin(phi)
+        return 2 * self.dk * (2 * math.pi) * Kamp
+
+    def remove(self, pos):
+        k = [d[pos] for d in self.data]
+        if self.D == 3:
+            Kamp = math.sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2])
+        else:
+            Kamp = math.sqrt(k[0] * k[0] + k[1] * k[1])
+        if not (self.kF - self.dk < Kamp < self.kF + self.dk):
+            return 0.0
+        if self.D == 3:
+            sint = math.sqrt(k[0] * k[0] + k[1] * k[1]) / Kamp
+            if sint < 1.0e-15:
+                return 0.0
+            return 1.0 / (2 * self.dk * (2 * math.pi) * math.pi * sint * (Kamp * Kamp))
+        return 1.0 / (2 * self.dk * (2 * math.pi) * Kamp)
+
+    def shift(self, pos, rng):
+        self.bk = [d[pos] for d in self.data]
+        x = rng.rand()
+        if x < 1.0 / 3:
+            lam = 1.5
+            ratio = 1.0 / lam + rng.rand() * (lam - 1.0 / lam)
+            for d in self.data:
+                d[pos] *= ratio
+            return 1.0 if self.D == 2 else ratio
+        if x < 2.0 / 3:
+            phi = rng.rand() * (2 * math.pi)
+            k = [d[pos] for d in self.data]
+            if self.D == 3:
+                th = math.acos(1 - 2 * rng.rand())
+                Kamp = math.sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2])
+                self.data[0][pos] = Kamp * math.cos(phi) * math.sin(th)
+                self.data[1][pos] = Kamp * math.sin(phi) * math.sin(th)
+                self.data[2][pos] = Kamp * math.cos(th)
+            else:
+                Kamp = math.sqrt(k[0] * k[0] + k[1] * k[1])
+                self.data[0][pos] = Kamp * math.cos(phi)
+                self.data[1][pos] = Kamp * math.sin(phi)
+            return 1.0
+        for d in self.data:
+            d[pos] = d[pos] + (rng.rand() - 0.5) * self.dk
+        return 1.0
+
+    def rollback(self, pos):
+        for d, b in zip(self.data, self.bk):
+            d[pos] = b
+
+    def swap(self, a, b):
+        for d in self.data:
+            d[a], d[b] = d[b], d[a]
+
+    def hist_len(self):
+        return 0
+
+    def accumulate(self, pos, w, hist):  # the no-op fallback, variable.jl:551
+        pass
+
+
+class DiscreteOne(DiscretePair):
+    """A plain Discrete variable (one leaf); adapt=False keeps it out of the histogram (variable.jl:363)."""
+
+    def __init__(self, dist, lower, nslot, adapt=True):
+        super().__init__([dist], [lower], nslot)
+        self.adapt = adapt
+
+    def hist_len(self):
+        return len(self.dist[0]) if self.adapt else 0
+
+    def accumulate(self, pos, w, hist):
+        if self.adapt:
+            super().accumulate(pos, w, hist)
+
+
+def green(tau, w, beta):  # test/bubble_FermiK.jl:41-52
+    if tau >= 0.0:
+        return math.exp(-w * tau) / (1 + math.exp(-w * beta)) if w > 0.0 else math.exp(w * (beta - tau)) / (1 + math.exp(w * beta))
+    return -math.exp(-w * (tau + beta)) / (1 + math.exp(-w * beta)) if w > 0.0 else -math.exp(-w * tau) / (1 + math.exp(w * beta))
+
+
+def bubble_fermik(ud, D):
+    """test/bubble_FermiK.jl:54-75 on vars (T, K, Ext); ud = [kF, beta, me, spin, dim, Qsize, extQ...]"""
+    kF, beta, me, spin = ud[0], ud[1], ud[2], ud[3]
+
+    def f(T, K, Ext):
+        tau = T.data[1]
+        k = [K.data[c][1] for c in range(D)] + [0.0] * (3 - D)
+        kq0 = k[0] + ud[6 + Ext.val[0][1] - 1]
+        w1 = ((k[0] * k[0] + k[1] * k[1] + k[2] * k[2]) - kF * kF) / (2 * me)
+        w2 = ((kq0 * kq0 + k[1] * k[1] + k[2] * k[2]) - kF * kF) / (2 * me)
+        phase = 1.0 / math.pow(2 * math.pi, float(D))
+        return green(tau, w1, beta) * green(-tau, w2, beta) * spin * phase * math.cos(2 * math.pi * 0 * tau / beta)
+    return f
+
+
+def loop_mcmc_vars(make_vars, f, rw, seed, it, nblock, steps, mf, thermal, nbins_obs):
+    """mcmc/montecarlo.jl:99-177 + updates.jl:1-147 for ONE integrand of dof [1, 1, ..., 1] over several variables
+    (Nd = 2, neighbours [[2], [1]]), measure = bin by the last (Discrete) variable (test/bubble_FermiK.jl:80-88);
+    counters [update][curr][new or vi] with dimension max(Nd, Nv)"""
+    V0 = make_vars()
+    Nv, Nd, NORM = len(V0), 2, 1
+    pa = max(Nd, Nv)
+    hoff = [0]
+    for v in V0:
+        hoff.append(hoff[-1] + v.hist_len())
+    hist = [0.0] * hoff[-1]
+    obs, norm, visited, neval = [], [], [0.0] * Nd, 0
+    prop_c = [[[0.0] * pa for _ in range(Nd)] for _ in range(3)]
+    acc_c = [[[0.0] * pa for _ in range(Nd)] for _ in range(3)]
+    for b in range(nblock):
+        rng, V = Stream(seed, it, b, 0), make_vars()
+        curr = 0
+        for _ in range(10000):
+            for v in V:  # initialize!: variable.jl:576-580, slots 1..maxdof
+                v.create(1, rng)
+            weight = f(*V)
+            prob = abs(weight) * rw[curr]
+            if prob > TINY_:
+                break
+        o, n = [0.0] * nbins_obs, 0.0
+        nburn = int(math.floor(steps * thermal))
+        for i in range(1, steps + nburn + 1):
+            visited[curr] += 1
+            u = rng.randint(2 * Nv + 2)  # [changeIntegrand, swapVariable, changeVariable x 2Nv]: montecarlo.jl:117-120
+            if u == 1:
+                new = 1 - curr  # the only neighbour; rand(rng, [x]) still consumes a draw
+                rng.randint(1)
+                prop = 1.0  # length(neighbor[curr]) / length(neighbor[new]) = 1 / 1
+                for v in V:
+                    prop *= v.create(1, rng) if curr == NORM else v.remove(1)
+                if prop > EPS0:
+                    nw = 0.0 if new == NORM else f(*V)
+                    neval += 1
+                    nprob = rw[new] if new == NORM else abs(nw) * rw[new]
+                    R = prop * nprob / prob
+                    prop_c[0][curr][new] += 1.0
+                    if rng.rand() < R:
+                        acc_c[0][curr][new] += 1.0
+                        curr, weight, prob = new, nw, nprob
+            elif curr != NORM:
+                vi = rng.randint(Nv) - 1
+                if u == 2:  # swapVariable: both slots are drawn from 1:1, so nothing is ever swapped
+                    rng.randint(1), rng.randint(1)
+                else:  # changeVariable
+                    v = V[vi]
+                    if not (isinstance(v, DiscreteOne) and len(v.dist[0]) == 1):
+                        rng.randint(1)
+                        prop = v.shift(1, rng)
+                        if prop > EPS0:
+                            nw = f(*V)
+                            neval += 1
+                            nprob = abs(nw) * rw[curr]
+                            R = prop * nprob / prob
+                            prop_c[1][curr][vi] += 1.0
+                            if rng.rand() < R:
+                                acc_c[1][curr][vi] += 1.0
+                                weight, prob = nw, nprob
+                            else:
+                                v.rollback(1)
+            if i % mf == 0 and i >= nburn:
+                if curr == NORM:
+                    n += 1.0 / rw[NORM]
+                else:
+                    for k, v in enumerate(V):
+                        sub = [0.0] * v.hist_len()
+                        v.accumulate(1, 1.0, sub)
+                        for j, x in enumerate(sub):
+                            hist[hoff[k] + j] += x
+                    o[V[-1].val[0][1] - V[-1].lower[0]] += weight / prob
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose=prop_c, accept=acc_c, neval=neval)
+
+
 def main():
     rnd = random.Random(20261017)
     G = {}
@@ -611,6 +807,23 @@ def main():
                                vegas=dict(npb=80, measurefreq=1, out=loop_vegas(QD, 777, 1, 2, 80, 1)),
                                vegasmc=dict(steps=250, measurefreq=1, out=loop_vegasmc(QD, drw, 777, 1, 2, 250, 1)),
                                mcmc=dict(steps=250, measurefreq=1, thermal_ratio=0.2, out=loop_mcmc(QD, drw, 777, 1, 2, 250, 1, 0.2)))
+
+    # :mcmc on vars (T::Continuous, K::FermiK{D}, Ext::Discrete nonadaptive), test/bubble_FermiK.jl, D = 3 and 2:
+    # pins the FermiK proposals (create!/remove!/shift!) and the multi-variable update mix
+    G["loops_fermik"] = []
+    for D, seedF in ((3, 31337), (2, 2718)):
+        spin, me, beta0, rs, Qsize = 2, 0.5, 25.0, 1.0, 4
+        kF = (9 * math.pi / (2 * spin)) ** (1 / 3) / rs if D == 3 else math.sqrt(4 / spin) / rs
+        beta = beta0 / (kF ** 2 / 2 / me)
+        extQ = [((1 - i / (Qsize - 1)) * 0.0 * kF + (i / (Qsize - 1)) * 1.5 * kF) for i in range(Qsize)]
+        ud = [kF, beta, me, float(spin), float(D), float(Qsize)] + extQ
+        tgrid = [0.0, 0.04 * beta, 0.15 * beta, 0.5 * beta, 0.87 * beta, beta]
+        dk = 0.2 * kF
+        frw = [0.7, 0.3]
+        mk = lambda: [Pool(tgrid, 1), FermiKPool(D, kF, dk, 1), DiscreteOne([0.25] * 4, 1, 1, adapt=False)]
+        G["loops_fermik"].append(dict(dim=D, userdata=ud, tgrid=tgrid, kF=kF, dk=dk, reweight=frw, seed=seedF, iter=2, n_block=2,
+                                      steps=400, measurefreq=1, thermal_ratio=0.1,
+                                      out=loop_mcmc_vars(mk, bubble_fermik(ud, D), frw, seedF, 2, 2, 400, 1, 0.1, Qsize)))
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:

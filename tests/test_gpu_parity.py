@@ -165,7 +165,35 @@ def test_L1_chain_iteration(name, solver):
         gpu.close(); cpu.close()
 
 
-@pytest.mark.parametrize("name,solver", [("bubble", "vegasmc"), ("sphere2", "vegasmc"), ("bubble", "mcmc"), ("product4_d6", "mcmc")])
+def test_L1_fermik_mcmc_iteration():
+    """test/bubble_FermiK.jl: (T, K::FermiK{3}, Ext) under :mcmc — the FermiK proposals (sampler.jl:109-281) against the
+    oracle, walker for walker.  sin/cos/acos come from CUDA's libm on one side and glibc's on the other (<= 2 ulp), so
+    the momenta agree to the last bits and the chains stay identical until an acceptance ties at that level."""
+    W = 96
+    gpu, cpu, _ = _pair("bubble_fermik", "mcmc", n_block=4, neval_per_block=W * 200, walkers=W)
+    try:
+        for it in range(2):
+            a, b = gpu.run_iteration(it), cpu.run_iteration(it)
+            _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
+            np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
+            assert np.array_equal(np.round(a.propose - b.propose, 6), np.zeros_like(a.propose))
+            assert np.array_equal(np.round(a.accept - b.accept, 6), np.zeros_like(a.accept))
+            gpu.reweight(1.0); cpu.reweight(1.0)
+            np.testing.assert_allclose(gpu.get_maps()[3], cpu.get_maps()[3], rtol=1e-9)
+            cpu.refine(); _sync_maps(cpu, gpu)
+    finally:
+        gpu.close(); cpu.close()
+
+
+def test_fermik_is_mcmc_only_on_the_device_too():
+    for solver in ("vegas", "vegasmc"):
+        spec, _ = make_spec("bubble_fermik", solver)
+        with pytest.raises(mci.MCIError, match="mcmc only"):
+            mci.CudaEngine(spec)
+
+
+@pytest.mark.parametrize("name,solver", [("bubble", "vegasmc"), ("sphere2", "vegasmc"), ("bubble", "mcmc"), ("product4_d6", "mcmc"),
+                                          ("bubble_fermik", "mcmc")])
 def test_chain_burnin_parity(name, solver):
     """mci_problem_t.chain_burnin: extra unmeasured steps before the reference's loop, same on the oracle"""
     gpu, cpu, _ = _pair(name, solver, n_block=4, neval_per_block=96 * 100, walkers=96, chain_burnin=37)
@@ -465,3 +493,41 @@ def test_gpu_against_independent_discrete_loop_fixtures(solver):
             assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_gpu_against_independent_fermik_loop_fixtures(i):
+    """golden.json["loops_fermik"]: the :mcmc loop of test/bubble_FermiK.jl on (T, K::FermiK{3 or 2}, Ext), restated in
+    pure Python (tests/golden/make_golden.py) — no C oracle in between"""
+    import json, os
+    from test_oracle_units import fermik_loop_spec
+    F = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))["loops_fermik"][i]
+    _, spec = fermik_loop_spec(F)
+    gpu = mci.CudaEngine(spec)
+    try:
+        gpu.set_maps(grids=np.array(F["tgrid"]), reweight=np.array(F["reweight"]))
+        st = gpu.run_iteration(F["iter"])
+        want, B1 = F["out"], F["n_block"] + 1
+        np.testing.assert_allclose(st.block_obs, want["obs"], rtol=1e-9)
+        np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=1e-12)
+        np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"] + [0.0] * 4, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+        assert st.neval == want["neval"]
+        assert np.array_equal(np.round(st.propose - B1 * 1e-8, 3), np.array(want["propose"]))
+        assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
+    finally:
+        gpu.close()
+
+
+def test_bubble_fermik_against_finite_temperature_exact():
+    """test/bubble_FermiK.jl:91-136 at size on the GPU decomposition (auto walkers, default burn-in): :mcmc on
+    (T, K::FermiK{3}, Ext) against the exact finite-temperature polarisation, 5 sigma (the reference: 5 sigma vs T = 0)"""
+    from mcintegration_jl_b200.integrands import lindhard_finite_temperature
+    c = case("bubble_fermik")
+    para = c["para"]
+    res = mci.integrate(c["f"], solver="mcmc", measure="bin_by_discrete", neval=2e7, niter=10, seed=99, **c["cfg"]())
+    avg, std = res.mean[0], res.stdev[0]
+    for i, q in enumerate(para.extQ):
+        ex = lindhard_finite_temperature(para, q)
+        assert abs(avg[i] - ex) < 5.0 * std[i], (i, avg[i], std[i], ex)
+        assert std[i] < 1e-3

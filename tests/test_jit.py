@@ -94,7 +94,8 @@ def test_user_source_errors_are_reported():
 
 
 @pytest.mark.parametrize("name,solver", [("gauss10", "vegas"), ("bubble", "vegas"), ("bubble", "vegasmc"), ("product4", "mcmc"),
-                                          ("discrete2", "vegasmc"), ("genz6_comp", "vegas"), ("sphere2_offset", "mcmc")])
+                                          ("discrete2", "vegasmc"), ("genz6_comp", "vegas"), ("sphere2_offset", "mcmc"),
+                                          ("bubble_fermik", "mcmc")])
 def test_builtin_integrands_compile_specialised(name, solver):
     spec, _ = make_spec(name, solver, walkers=64 if solver != "vegas" else 1)
     spec.jit = 1
@@ -180,7 +181,7 @@ def test_complex2_as_real_pairs(solver):
 @pytest.mark.parametrize("name,solver", [("gauss10", "vegas"), ("sphere2", "vegas"), ("bubble", "vegas"), ("genz6_comp", "vegas"),
                                           ("discrete2", "vegas"), ("bubble", "vegasmc"), ("sphere2", "vegasmc"),
                                           ("product4_d6", "vegasmc"), ("bubble", "mcmc"), ("sphere2_offset", "mcmc"),
-                                          ("product4_d6", "mcmc"), ("lattice_comp", "mcmc")])
+                                          ("product4_d6", "mcmc"), ("lattice_comp", "mcmc"), ("bubble_fermik", "mcmc")])
 def test_specialised_kernels_keep_parity(name, solver):
     """jit=1: the same templates compiled against compile-time layout tables must reproduce the oracle like the
     ahead-of-time kernels do (tolerances of tests/test_gpu_parity.py)."""
@@ -204,3 +205,48 @@ def test_specialised_kernels_keep_parity(name, solver):
             gpu.set_maps(*cpu.get_maps())
     finally:
         gpu.close(); cpu.close()
+
+
+# a user integrand on a FermiK{2} momentum: the occupied area of a Fermi disc smeared by a Gaussian (any smooth positive f)
+FERMIK_SRC = """
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  double kx = X(0, 1), ky = X(1, 1);              // the two Cartesian components of K[1]
+  double k = sqrt(kx * kx + ky * ky), d = (k - userdata[0]) / userdata[1];
+  w[0] = exp(-0.5 * d * d);
+}
+"""
+
+
+def _fermik_user_spec(solver):
+    cfg = mci.Configuration(var=mci.FermiK(2, 1.0, 0.2, 10.0), dof=[[1]], seed=5)
+    f = I.user_integrand(FERMIK_SRC, 1, [1.0, 0.1])
+    return mci.problem_from_config(cfg, f, solver=solver, measure_kind=0, n_block=16, neval_per_block=4096, walkers_per_block=64), cfg
+
+
+def test_fermik_user_source_compiles_under_mcmc_only():
+    """A FermiK variable reaches a user integrand as D component leaves; like in the reference (test/bubble_FermiK.jl:2,
+    139-140) only :mcmc takes it"""
+    rc, log = _check(_fermik_user_spec(_abi.SOLVER_MCMC)[0])
+    assert rc == 0, log
+    for solver in (_abi.SOLVER_VEGAS, _abi.SOLVER_VEGASMC):
+        rc, log = _check(_fermik_user_spec(solver)[0])
+        assert rc == _abi.ERR_UNSUPPORTED and "mcmc only" in log, log
+
+
+def test_fermik_needs_an_integrand_that_takes_it():
+    cfg = mci.Configuration(var=mci.FermiK(3, 1.0, 0.2, 10.0), dof=[[1]], seed=5)
+    spec = mci.problem_from_config(cfg, I.discrete_x, solver=_abi.SOLVER_MCMC, measure_kind=0, n_block=16, neval_per_block=64)
+    rc, log = _check(spec)
+    assert rc == _abi.ERR_INVALID and "FermiK" in log, log
+
+
+@pytest.mark.gpu
+def test_fermik_user_integrand_end_to_end():
+    """int d^2k exp(-(|k| - kF)^2 / 2 s^2) = 2 pi (s^2 exp(-kF^2/2s^2) + kF s sqrt(pi/2) (1 + erf(kF / (s sqrt 2)))) on the
+    plane, sampled with FermiK{2} proposals only (create!/remove! through the normalisation integrand, shift!)"""
+    kF, s = 1.0, 0.1
+    exact = 2 * math.pi * (s * s * math.exp(-kF * kF / (2 * s * s)) + kF * s * math.sqrt(math.pi / 2) * (1 + math.erf(kF / (s * math.sqrt(2)))))
+    res = mci.integrate(I.user_integrand(FERMIK_SRC, 1, [kF, s]), var=mci.FermiK(2, kF, 0.2, 10.0), dof=[[1]], solver="mcmc",
+                        neval=2e6, niter=10, block=16, seed=5)
+    assert abs(res.mean[0] - exact) < 6.0 * res.stdev[0], (res.mean[0], res.stdev[0], exact)
+    assert res.stdev[0] < 0.02 * exact

@@ -315,3 +315,71 @@ def test_discrete_composite_loops_against_independent_restatement(solver_name):
             assert got["propose"].tolist() == want["propose"] and got["accept"].tolist() == want["accept"]
     finally:
         eng.close()
+
+
+def fermik_loop_spec(F, solver=None):
+    """The problem behind golden.json["loops_fermik"][i]: vars (T::Continuous, K::FermiK{dim}, Ext::Discrete), mcmc"""
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import _abi, integrands
+    ud = F["userdata"]
+    T = mci.Continuous(0.0, ud[1], grid=F["tgrid"], alpha=3.0)
+    K = mci.FermiK(F["dim"], F["kF"], F["dk"], 10.0 * F["kF"])
+    Ext = mci.Discrete(1, 4, adapt=False)
+    cfg = mci.Configuration(var=(T, K, Ext), dof=[[1, 1, 1]], obs=[np.zeros(4)], seed=F["seed"])
+    f = integrands.Integrand("bubble_fermik", _abi.F_BUBBLE_FERMIK, 1, tuple(ud))
+    spec = mci.problem_from_config(cfg, f, solver=_abi.SOLVER_MCMC if solver is None else solver,
+                                   measure_kind=_abi.MEASURE_BIN_BY_DISCRETE, n_block=F["n_block"], neval_per_block=F["steps"],
+                                   measurefreq=F["measurefreq"], walkers_per_block=1, thermal_ratio=F["thermal_ratio"])
+    return cfg, spec
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_fermik_mcmc_loop_against_independent_restatement(case):
+    """FermiK{3} and FermiK{2} proposals (sampler.jl:109-281) inside the whole :mcmc loop of test/bubble_FermiK.jl,
+    against the pure-Python restatement in tests/golden/make_golden.py"""
+    import mcintegration_jl_b200 as mci
+    from oracle_lib import OracleEngine
+    F = GOLD["loops_fermik"][case]
+    cfg, spec = fermik_loop_spec(F)
+    eng = OracleEngine(spec, nthreads=1)
+    try:
+        eng.set_maps(grids=arr(F["tgrid"]), reweight=arr(F["reweight"]))
+        st = eng.run_iteration(F["iter"])
+        want, B1 = F["out"], F["n_block"] + 1
+        np.testing.assert_allclose(st.block_obs, want["obs"], rtol=1e-12)
+        np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=1e-12)
+        # histogram layout: T's 5 increments, nothing for K, then Ext's 4 values (adapt = false: never filled)
+        np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"] + [0.0] * 4, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+        assert st.neval == want["neval"]
+        assert np.array_equal(np.round(st.propose - B1 * 1e-8, 3), np.array(want["propose"]))
+        assert np.array_equal(np.round(st.accept - B1 * 1e-10, 3), np.array(want["accept"]))
+    finally:
+        eng.close()
+
+
+def test_fermik_is_mcmc_only():
+    """test/bubble_FermiK.jl:2,139-140: the reference runs FermiK under :mcmc alone; vegas / vegasmc are refused"""
+    from mcintegration_jl_b200 import _abi
+    from mcintegration_jl_b200.engine import MCIError
+    from oracle_lib import OracleEngine
+    for solver in (_abi.SOLVER_VEGAS, _abi.SOLVER_VEGASMC):
+        _, spec = fermik_loop_spec(GOLD["loops_fermik"][0], solver)
+        with pytest.raises(MCIError, match="mcmc only"):
+            OracleEngine(spec, nthreads=1)
+
+
+def test_fermik_bubble_oracle_vs_lindhard():
+    """test/bubble_FermiK.jl:91-136: :mcmc on (T, FermiK, Ext) against the polarisation, 5 sigma (the reference compares
+    with the T = 0 Lindhard value; the exact finite-temperature value is used here)"""
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import integrands as I
+    from oracle_lib import oracle_integrate
+    para = I.BubblePara()
+    res = oracle_integrate(I.bubble_fermik(para), solver="mcmc", measure="bin_by_discrete", neval=2e5, niter=10, block=16, seed=11,
+                           var=(mci.Continuous(0.0, para.β, alpha=3.0), mci.FermiK(3, para.kF, 0.2 * para.kF, 10.0 * para.kF),
+                                mci.Discrete(1, para.Qsize, adapt=False)), dof=[[1, 1, 1]], obs=[np.zeros(4)])
+    for i, q in enumerate(para.extQ):
+        exact = I.lindhard_finite_temperature(para, q)
+        assert abs(res.mean[0][i] - exact) < 5.0 * res.stdev[0][i], (q, res.mean[0][i], res.stdev[0][i], exact)
+        assert res.stdev[0][i] < 0.03 * abs(exact)
