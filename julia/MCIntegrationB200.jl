@@ -44,11 +44,13 @@ check(h, rc) = rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_erro
 
 leaves(v::Union{Continuous,Discrete}) = [v]
 leaves(v::CompositeVar) = collect(v.vars)
+leaves(v::FermiK{D}) where {D} = fill(v, D)      # one MCI_LEAF_FERMIK record per Cartesian component; :mcmc only
+leafdesc(v::FermiK) = MciLeaf(2, 0, false, 0, v.kF, v.δk, v.maxK)
 leafdesc(v::Continuous) = MciLeaf(0, length(v.grid) - 1, v.adapt, 0, v.lower, v.lower + v.range, v.alpha)
 leafdesc(v::Discrete) = MciLeaf(1, v.upper - v.lower + 1, v.adapt, v.lower, 0.0, 0.0, v.alpha)
 
 """
-    integrate_b200(integrand::Union{Integer,AbstractString}; userdata=Float64[], measure_kind=0, walkers=4096, device=0, jit=0, kwargs...)
+    integrate_b200(integrand::Union{Integer,AbstractString}; userdata=Float64[], measure_kind=0, walkers=0, device=0, jit=0, chain_burnin=1024, kwargs...)
 
 Same keyword surface as `MCIntegration.integrate` (src/main.jl:71-90): `solver, config, neval, niter, block, gamma,
 adapt, reweight_goal, ignore, measurefreq, thermal_ratio` plus the `Configuration` kwargs (`var, dof, obs, reweight,

@@ -28,6 +28,9 @@
  *      iteration as (n_block+1)*floor on the summed raw statistics.
  *  D7  With a fixed seed the reference gives every MPI rank the same stream
  *      (main.jl:136); here streams are keyed by the global block index.
+ *  D8  FermiK (sampler.jl:109-281) is accepted under :mcmc only, the one solver
+ *      the reference runs it under (test/bubble_FermiK.jl:2,139-140); K.prob,
+ *      which only :vegas/:vegasmc would read, is not kept.
  */
 #include "mci_oracle.h"
 

@@ -26,8 +26,10 @@
  *   - golden vectors for the map, train! and rescale AND for the three whole
  *     solver loops (vegas, vegasmc, mcmc on a two-integrand pool problem:
  *     observables, normalisation, histograms, visited / propose / accept
- *     counters) produced by an independent pure-Python restatement of the
- *     Julia sources (tests/golden/make_golden.py);
+ *     counters; the same loops on a CompositeVar of two Discrete leaves with
+ *     non-uniform distributions; the :mcmc loop of test/bubble_FermiK.jl on
+ *     (T, K::FermiK{3 or 2}, Ext)) produced by an independent pure-Python
+ *     restatement of the Julia sources (tests/golden/make_golden.py);
  *   - Philox4x32-10 against the Random123 known-answer vectors.
  */
 #ifndef MCI_ORACLE_H
