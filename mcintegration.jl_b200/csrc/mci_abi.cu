@@ -64,7 +64,7 @@ bool nccl_load() {
 constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 
 thread_local char g_err[256];
-/* auto policy of the pool kernel = 16 bank-striped shared copies: measured 39.8 vs 28.0 G samples/s (one shared copy) on C2, profiles/r1_hist_policies.md */
+/* auto policy of the pool kernel = 16 bank-striped shared copies: measured 39.8 vs 28.0 G samples/s (one shared copy) on C2, profiles/r1_hist_policy_sweeps.jsonl */
 constexpr bool MCI_AUTO_STRIPED = true;
 }  // namespace
 
@@ -240,7 +240,7 @@ int plan(mci_handle_t *h) {
     if (policy == MCI_HIST_WARP_PRIVATE && allow_private && base + nwarp * hist_bytes <= SMEM_MAX) return (int)HIST_WARP_PRIVATE;
     if (policy == MCI_HIST_SMEM_ATOMIC && base + hist_bytes <= SMEM_MAX) return (int)HIST_SMEM_ATOMIC;
     if (policy == MCI_HIST_GLOBAL_RED) return (int)HIST_GLOBAL_RED;
-    /* auto (measured on B200, C2, profiles/r1_hist_policies.md): one CTA-shared fp64 histogram with shared-memory CAS
+    /* auto (measured on B200, C2, profiles/r1_hist_policy_sweeps.jsonl): one CTA-shared fp64 histogram with shared-memory CAS
      * beats per-warp private copies with MATCH.ANY conflict ranking (ADU-pipe bound) by 2.3x and L2 REDs by 1.5x */
     /* a shared histogram that leaves room for only one 256-thread CTA per SM starves the SM of warps: L2 REDs then win
      * (16-leaf composite: 9.1 vs 6.1 G samples/s) */

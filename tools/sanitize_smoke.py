@@ -12,7 +12,7 @@ from cases import make_spec
 
 CASES = [("gauss10", "vegas", {}), ("sphere2", "vegas", {}), ("bubble", "vegas", {}), ("genz6_comp", "vegas", dict(hist_policy=2)),
          ("bubble", "vegasmc", dict(walkers=96)), ("product4", "mcmc", dict(walkers=96)), ("sphere2_offset", "mcmc", dict(walkers=96)),
-         ("discrete2", "vegasmc", dict(walkers=96))]
+         ("discrete2", "vegasmc", dict(walkers=96)), ("bubble_fermik", "mcmc", dict(walkers=96))]
 for jit in (2, 1):
     for name, solver, kw in CASES:
         kw = dict(kw)
