@@ -353,6 +353,11 @@ EDGE = {
     # non-adaptive variables: no histogram at all
     "no_adapt": lambda s: _edge_spec(s, mci.Continuous(0.0, 1.0, adapt=False), [[2], [3]], mci.integrands.sphere2, walkers=32,
                                      npb=32 * 60),
+    # the most leaves the ABI takes (MCI_MAX_LEAF = 32): a 32-leaf CompositeVar, 32 maps and histograms
+    "comp32_max_leaves": lambda s: _edge_spec(s, mci.Continuous([(0.0, 1.0)] * 32), [[1]], mci.integrands.genz_corner_peak(32, "comp"),
+                                              walkers=32, npb=32 * 40),
+    # the smallest job there is: one block, one chain, one step / one sample
+    "one_sample": lambda s: _edge_spec(s, mci.Continuous(0.0, 1.0), [[2], [3]], mci.integrands.sphere2, n_block=1, npb=1, walkers=1),
     # measure every 7th step only
     "measurefreq7": lambda s: _edge_spec(s, mci.Continuous(-1.0, 1.0), [[2], [3], [4]], mci.integrands.hypersphere3, walkers=32,
                                          npb=32 * 70, measurefreq=7),
