@@ -380,6 +380,10 @@ int plan(mci_handle_t *h) {
   } else {
     const int W = std::max(1, h->walkers);
     h->steps = p.neval_per_block / W;
+    /* propose / accept (and mcmc's visited) are counted in u32 per CTA and turned into the f64 statistics at the end */
+    if ((double)std::min(W, h->threads) * ((double)h->steps * (1.0 + P.thermal_ratio) + (double)p.chain_burnin + 1.0) >= 4.0e9)
+      return fail(h, MCI_ERR_UNSUPPORTED, "%llu steps per chain overflow the per-CTA counters: cut the block into more chains (walkers_per_block)",
+                  (unsigned long long)h->steps);
     h->ctas_per_block = (W + h->threads - 1) / h->threads;
     h->grid = h->ctas_per_block * n_local;
     h->tiles_per_block = 0;

@@ -331,6 +331,11 @@ def test_error_paths():
     with pytest.raises(MCIError):
         eng.refine()  # nothing to refine yet
     eng.close()
+    # one chain of 5e9 steps would overflow the per-CTA u32 counters: refused with advice, not wrapped around
+    spec, _ = make_spec("sphere2", "mcmc", neval_per_block=5_000_000_000, walkers=1)
+    with pytest.raises(MCIError, match="more chains") as e:
+        mci.CudaEngine(spec)
+    assert e.value.code == _abi.ERR_UNSUPPORTED
 
 
 # ---- edge cases of the layout / sizes (GPU against the oracle) -------------------------------------------------------
