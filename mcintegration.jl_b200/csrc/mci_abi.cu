@@ -90,6 +90,10 @@ struct mci_handle_t {
   double *d_tile_obs = nullptr, *d_tile_cnt = nullptr, *d_cta_hist = nullptr, *d_cta_stats = nullptr, *d_packed = nullptr;
   unsigned long long *d_flags = nullptr;
   int *d_err = nullptr;
+  /* the buffers above are carved out of three allocations (cudaMalloc / cudaFree / cudaMallocHost cost 0.1-1 ms each
+   * and synchronise the device: a job of the reference's default size, neval = 1e4, is over in 4 ms):
+   * the fixed state, the per-launch partials (re-planned by mci_set_partition) and the pinned host mirrors */
+  void *d_state_arena = nullptr, *d_launch_arena = nullptr, *h_arena = nullptr;
   /* pinned host mirrors */
   double *h_packed = nullptr;
   unsigned long long *h_flags = nullptr;
@@ -163,10 +167,19 @@ double volume_inverse(int d) { /* test/montecarlo.jl:201-204 */
   return pow(d / (2 * pi * euler), d / 2.0) * sqrt((double)d) * sqrt(pi);
 }
 
-template <class T>
-int dev_alloc(mci_handle_t *h, T **p, size_t n) {
-  CU(h, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
-  CU(h, cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+/* bump allocation out of one cudaMalloc: sizes are summed first (256-byte aligned), then the pointers are handed out */
+struct Arena {
+  size_t total = 0;
+  char *base = nullptr;
+  template <class T>
+  size_t reserve(size_t n) { const size_t off = total; total += (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255; return off; }
+  template <class T>
+  T *at(size_t off) const { return reinterpret_cast<T *>(base + off); }
+};
+int arena_device(mci_handle_t *h, Arena &A, void **keep) {
+  CU(h, cudaMalloc(keep, std::max<size_t>(A.total, 256)));
+  CU(h, cudaMemset(*keep, 0, std::max<size_t>(A.total, 256)));
+  A.base = static_cast<char *>(*keep);
   return MCI_OK;
 }
 
@@ -392,18 +405,23 @@ int plan(mci_handle_t *h) {
   if (h->n_hist_copies < 1) h->n_hist_copies = 1;
 
   /* (re)allocate per-launch partial buffers */
-  cudaFree(h->d_tile_obs); cudaFree(h->d_tile_cnt); cudaFree(h->d_cta_hist); cudaFree(h->d_cta_stats);
+  cudaFree(h->d_launch_arena);
+  h->d_launch_arena = nullptr;
   h->d_tile_obs = h->d_tile_cnt = h->d_cta_hist = h->d_cta_stats = nullptr;
-  int rc;
-  if (p.solver == MCI_SOLVER_VEGAS) {
+  {
+    Arena L;
+    size_t o_obs = 0, o_cnt = 0, o_stats = 0;
     const size_t nt = (size_t)h->tiles_per_block * n_local;
-    if ((rc = dev_alloc(h, &h->d_tile_obs, nt * P.obs_total))) return rc;
-    if ((rc = dev_alloc(h, &h->d_tile_cnt, nt))) return rc;
-  } else {
     const size_t stat_len = P.obs_total + 1 + P.nd + 2 * (size_t)h->pa_len + 1;
-    if ((rc = dev_alloc(h, &h->d_cta_stats, (size_t)h->grid * stat_len))) return rc;
+    if (p.solver == MCI_SOLVER_VEGAS) { o_obs = L.reserve<double>(nt * P.obs_total); o_cnt = L.reserve<double>(nt); }
+    else o_stats = L.reserve<double>((size_t)h->grid * stat_len);
+    const size_t o_hist = L.reserve<double>((size_t)h->n_hist_copies * std::max(1, P.hist_len));
+    int rc;
+    if ((rc = arena_device(h, L, &h->d_launch_arena))) return rc;
+    if (p.solver == MCI_SOLVER_VEGAS) { h->d_tile_obs = L.at<double>(o_obs); h->d_tile_cnt = L.at<double>(o_cnt); }
+    else h->d_cta_stats = L.at<double>(o_stats);
+    h->d_cta_hist = L.at<double>(o_hist);
   }
-  if ((rc = dev_alloc(h, &h->d_cta_hist, (size_t)h->n_hist_copies * std::max(1, P.hist_len)))) return rc;
   return MCI_OK;
 }
 
@@ -430,13 +448,8 @@ void mci_destroy(mci_handle_t *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->jit_lib) jit_unload(h->jit_lib);
-  cudaFree(h->d_grids); cudaFree(h->d_dist); cudaFree(h->d_accum); cudaFree(h->d_reweight); cudaFree(h->d_goal);
-  cudaFree(h->d_alpha); cudaFree(h->d_gmaps); cudaFree(h->d_leaf_grid_off); cudaFree(h->d_leaf_dist_off);
-  cudaFree(h->d_leaf_acc_off); cudaFree(h->d_tile_obs); cudaFree(h->d_tile_cnt); cudaFree(h->d_cta_hist);
-  cudaFree(h->d_cta_stats); cudaFree(h->d_packed); cudaFree(h->d_flags); cudaFree(h->d_err);
-  if (h->h_packed) cudaFreeHost(h->h_packed);
-  if (h->h_flags) cudaFreeHost(h->h_flags);
-  if (h->h_err) cudaFreeHost(h->h_err);
+  cudaFree(h->d_state_arena); cudaFree(h->d_launch_arena);
+  if (h->h_arena) cudaFreeHost(h->h_arena);
   if (h->ev_iter0) cudaEventDestroy(h->ev_iter0);
   for (int i = 0; i < mci_handle_t::FILL_RING; ++i) {
     if (h->ev_fill0[i]) cudaEventDestroy(h->ev_fill0[i]);
@@ -638,11 +651,12 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || p->device < 0 || p->device >= ndev)
     { delete h; return fail(nullptr, MCI_ERR_NO_DEVICE, "no CUDA device %d (found %d): libmcib200 has no CPU fallback", p->device, ndev); }
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
+  int cc_major = 0, n_sm = 0; /* two attributes, not cudaGetDeviceProperties (milliseconds) */
+  if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || cc_major < 10)
     { delete h; return fail(nullptr, MCI_ERR_NO_DEVICE, "device %d is not a Blackwell (sm_100a) GPU", p->device); }
 
-  h->n_sm = prop.multiProcessorCount;
+  h->n_sm = n_sm;
   const int nd = h->nd, nleaf = h->nleaf, go = h->grid_len, dd = h->disc_len, da = h->accum_len, mo = h->dp.map_doubles;
   const PackedLayout &Y = h->Y;
   /* ---- device resources ---- */
@@ -652,15 +666,26 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   CUT(cudaSetDevice(h->device));
   CUT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUT(cudaEventCreate(&h->ev_iter0)); CUT(cudaEventCreate(&h->ev_iter1));
-  for (int i = 0; i < mci_handle_t::FILL_RING; ++i) { CUT(cudaEventCreate(&h->ev_fill0[i])); CUT(cudaEventCreate(&h->ev_fill1[i])); }
-  TRY(dev_alloc(h, &h->d_grids, go + 1)); TRY(dev_alloc(h, &h->d_dist, dd + 1)); TRY(dev_alloc(h, &h->d_accum, da + 1));
-  TRY(dev_alloc(h, &h->d_reweight, nd)); TRY(dev_alloc(h, &h->d_goal, nd)); TRY(dev_alloc(h, &h->d_alpha, nleaf));
-  TRY(dev_alloc(h, &h->d_gmaps, mo + 2));
-  TRY(dev_alloc(h, &h->d_leaf_grid_off, nleaf)); TRY(dev_alloc(h, &h->d_leaf_dist_off, nleaf)); TRY(dev_alloc(h, &h->d_leaf_acc_off, nleaf));
-  TRY(dev_alloc(h, &h->d_packed, Y.len)); TRY(dev_alloc(h, &h->d_flags, 2)); TRY(dev_alloc(h, &h->d_err, 1));
-  CUT(cudaMallocHost((void **)&h->h_packed, Y.len * sizeof(double)));
-  CUT(cudaMallocHost((void **)&h->h_flags, 2 * sizeof(unsigned long long)));
-  CUT(cudaMallocHost((void **)&h->h_err, sizeof(int)));
+  /* (the ring of fill-kernel events is created on first use, launch_fill) */
+  {
+    Arena D;
+    const size_t o_grids = D.reserve<double>(go + 1), o_dist = D.reserve<double>(dd + 1), o_accum = D.reserve<double>(da + 1);
+    const size_t o_rw = D.reserve<double>(nd), o_goal = D.reserve<double>(nd), o_alpha = D.reserve<double>(nleaf);
+    const size_t o_gmaps = D.reserve<double>(mo + 2);
+    const size_t o_lg = D.reserve<int>(nleaf), o_ld = D.reserve<int>(nleaf), o_la = D.reserve<int>(nleaf);
+    const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(2), o_err = D.reserve<int>(1);
+    TRY(arena_device(h, D, &h->d_state_arena));
+    h->d_grids = D.at<double>(o_grids); h->d_dist = D.at<double>(o_dist); h->d_accum = D.at<double>(o_accum);
+    h->d_reweight = D.at<double>(o_rw); h->d_goal = D.at<double>(o_goal); h->d_alpha = D.at<double>(o_alpha);
+    h->d_gmaps = D.at<double>(o_gmaps);
+    h->d_leaf_grid_off = D.at<int>(o_lg); h->d_leaf_dist_off = D.at<int>(o_ld); h->d_leaf_acc_off = D.at<int>(o_la);
+    h->d_packed = D.at<double>(o_packed); h->d_flags = D.at<unsigned long long>(o_flags); h->d_err = D.at<int>(o_err);
+    Arena H;
+    const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(2), ho_err = H.reserve<int>(1);
+    CUT(cudaMallocHost(&h->h_arena, H.total));
+    H.base = static_cast<char *>(h->h_arena);
+    h->h_packed = H.at<double>(ho_packed); h->h_flags = H.at<unsigned long long>(ho_flags); h->h_err = H.at<int>(ho_err);
+  }
   memset(h->h_packed, 0, Y.len * sizeof(double));
   h->h_flags[0] = h->h_flags[1] = 0; *h->h_err = 0;
   CUT(cudaMemcpy(h->d_alpha, h->alpha.data(), nleaf * sizeof(double), cudaMemcpyHostToDevice));
@@ -770,6 +795,7 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     args[0] = &h->dp; args[1] = &CA;
   }
   const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);
+  if (!h->ev_fill0[slot]) { CU(h, cudaEventCreate(&h->ev_fill0[slot])); CU(h, cudaEventCreate(&h->ev_fill1[slot])); }
   CU(h, cudaEventRecord(h->ev_fill0[slot], h->stream));
   CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
   CU(h, cudaEventRecord(h->ev_fill1[slot], h->stream));
