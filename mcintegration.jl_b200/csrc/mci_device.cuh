@@ -38,9 +38,12 @@ constexpr int HIST_SMEM_STRIPED = 4; /* CTA-shared fp64 histogram in 16 bank-str
 constexpr int STRIPE_LOG2 = 4;
 constexpr int STRIPE = 1 << STRIPE_LOG2;
 #ifndef MCI_POOL_MAP_REP
-#define MCI_POOL_MAP_REP 1
+#define MCI_POOL_MAP_REP 4
 #endif
-constexpr int POOL_MAP_REP = MCI_POOL_MAP_REP; /* copies of the pool's map in the striped variant (1 or 4), see PoolMap: 4 measured -0.8 % on C2, +3 % on C3-A, so 1 */
+/* copies of the pool's (edge, width) table in the striped variant, interleaved [increment][copy] (PoolMap, mci_vegas.cuh):
+ * 4 copies cut the bank conflicts of the ten random LDS.128 lookups of a sample from ~10.9 to ~7.8 wavefronts each at no
+ * extra instruction — measured (A/B in one job, B200) C2 38.9 -> 41.3, C3-A 25.2 -> 26.3, C5 integrand 19.3 -> 20.3 G samples/s */
+constexpr int POOL_MAP_REP = MCI_POOL_MAP_REP;
 
 struct DevLeaf {
   int kind, nbins, adapt, lower_i;

@@ -96,24 +96,18 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
  *   REP == 1: one table of (edge, width) pairs, one LDS.128 per draw.  32 lanes at random increments conflict on the 8
  *             16-byte bank groups: ~10 wavefronts per instruction — with the histogram the shared-memory pipe was 80 %
  *             busy (ncu, profiles/r1_fill_ncu.json), THE limiter of the kernel.
- *   REP == 4: edges and widths as two arrays, each in 4 copies interleaved [increment][copy]; lane l reads copy l % 4,
- *             which lives in bank pairs (l % 4) + 4 k.  The 4 lanes of a half-warp that share a copy collide only when
- *             their increments agree mod 4: ~3.2 wavefronts per LDS.64, 6.4 per draw instead of 10, for 48 KB more
- *             shared memory (affordable in the striped variant, which owns the SM).  MEASURED (B200, A/B in one job):
- *             C2 38.5 vs 38.8 G samples/s with one table, C3-A 25.6 vs 24.8 — the saved wavefronts are paid back by the
- *             second LDS per draw, so the kernel is not purely wavefront-bound and REP = 1 stays the default. */
+ *   REP == 4: the same pairs in 4 copies interleaved [increment][copy]; lane l reads copy l % 4.  The 8 lanes of one
+ *             LDS.128 phase fall on the 4 copies two by two, and a copy owns the 16-byte bank groups c and c + 4, so a
+ *             phase takes 2 wavefronts whenever one of its four lane pairs differs in increment parity: ~7.8 wavefronts
+ *             per draw instead of ~10.9, no extra instruction, 48 KB more shared memory (affordable in the striped
+ *             variant, which owns the SM).  An earlier split edge / width variant (two LDS.64 per draw, 6.4
+ *             wavefronts) was measured neutral: C2 38.5 vs 38.8 G samples/s. */
 template <int REP>
 struct PoolMap {
-  const double2 *pair;      /* REP == 1 */
-  uint32_t g_saddr, d_saddr; /* REP == 4: shared addresses of this lane's copy of edge[0] / width[0] */
+  const double2 *pair; /* this lane's copy of pair 0; pairs of one copy are REP entries apart */
   __device__ __forceinline__ void lookup(int iy, double &g, double &dx) const {
-    if (REP == 1) {
-      const double2 v = pair[iy];
-      g = v.x; dx = v.y;
-    } else {
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(g) : "r"(g_saddr + (uint32_t)iy * (8u * REP)));
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(d_saddr + (uint32_t)iy * (8u * REP)));
-    }
+    const double2 v = pair[iy * REP];
+    g = v.x; dx = v.y;
   }
 };
 
@@ -234,18 +228,12 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   if (REP == 1) {
     stage_maps(P, smaps, A.gmaps);
     M.pair = reinterpret_cast<const double2 *>(smaps);
-    M.g_saddr = M.d_saddr = 0;
-  } else { /* edges [nbins][REP] | widths [nbins][REP] */
+  } else { /* (edge, width) pairs in REP copies, interleaved [increment][copy]: lane l reads copy l % REP */
     const int nb = P.leaf[0].nbins;
     const double2 *src = reinterpret_cast<const double2 *>(A.gmaps);
-    for (int i = tid; i < nb * REP; i += THREADS) {
-      const double2 v = __ldg(src + i / REP);
-      smaps[i] = v.x;
-      smaps[nb * REP + i] = v.y;
-    }
-    M.pair = nullptr;
-    M.g_saddr = (uint32_t)__cvta_generic_to_shared(smaps) + 8u * (lane & (REP - 1));
-    M.d_saddr = M.g_saddr + 8u * REP * (uint32_t)nb;
+    double2 *dst = reinterpret_cast<double2 *>(smaps);
+    for (int i = tid; i < nb * REP; i += THREADS) dst[i] = __ldg(src + i / REP);
+    M.pair = dst + (lane & (REP - 1));
   }
   for (int i = tid; i < NCOPY * P.hist_len; i += THREADS) shist[i] = 0.0;
   __syncthreads();
