@@ -702,6 +702,122 @@ def loop_mcmc_vars(make_vars, f, rw, seed, it, nblock, steps, mf, thermal, nbins
     return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose=prop_c, accept=acc_c, neval=neval)
 
 
+def _prob_all(V, dofs):  # variable.jl:606-619: ONE running product over the variables in order
+    p = 1.0
+    for v, d in zip(V, dofs):
+        for pos in range(1, d + 1):
+            p *= v.prob[pos]
+    return p
+
+
+def _pad_all(V, dofs, maxdof):  # variable.jl:628-641
+    p = 1.0
+    for v, d, m in zip(V, dofs, maxdof):
+        for pos in range(d + 1, m + 1):
+            p *= v.prob[pos]
+    return p
+
+
+def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf):
+    """vegas/montecarlo.jl:117-187 over SEVERAL top-level variables; DOF[i][v] incl. the normalisation row"""
+    NI, Nv = len(DOF) - 1, len(DOF[0])
+    maxdof = [max(d[v] for d in DOF) for v in range(Nv)]
+    V0 = make_vars()
+    hoff = [0]
+    for v in V0:
+        hoff.append(hoff[-1] + v.hist_len())
+    hist = [0.0] * hoff[-1]
+    obs, norm = [], []
+    for b in range(nblock):
+        o, n = [0.0] * NI, 0.0
+        for ne in range(1, npb + 1):
+            rng, V = Stream(seed, it, b, ne - 1), make_vars()
+            jac = 1.0
+            for v, m in zip(V, maxdof):
+                for pos in range(1, m + 1):
+                    v.create(pos, rng)
+                    jac /= v.prob[pos]
+            pad = [1.0 if DOF[i] == maxdof else _pad_all(V, DOF[i], maxdof) for i in range(NI)]
+            w = f(*V)
+            if ne % mf == 0:
+                for i in range(NI):
+                    o[i] += w[i] * pad[i] * jac
+                n += 1.0
+            for k, v in enumerate(V):
+                sub = [0.0] * v.hist_len()
+                for i in range(NI):
+                    for pos in range(1, DOF[i][k] + 1):
+                        v.accumulate(pos, (abs(w[i]) * jac) * (abs(w[i]) * jac), sub)
+                for j, x in enumerate(sub):
+                    hist[hoff[k] + j] += x
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist)
+
+
+def loop_vegasmc_vars(make_vars, f, DOF, rw, seed, it, nblock, steps, mf):
+    """vegas_mc/montecarlo.jl:151-232 + updates.jl:45-106 over several top-level variables, one chain per block;
+    propose/accept[2, 1, vi] come back as lists over vi"""
+    NI, Nv = len(DOF) - 1, len(DOF[0])
+    maxdof = [max(d[v] for d in DOF) for v in range(Nv)]
+    V0 = make_vars()
+    hoff = [0]
+    for v in V0:
+        hoff.append(hoff[-1] + v.hist_len())
+    hist = [0.0] * hoff[-1]
+    obs, norm, visited, neval = [], [], [0.0] * (NI + 1), 0
+    prop_c, acc_c = [0.0] * Nv, [0.0] * Nv
+    for b in range(nblock):
+        rng, V = Stream(seed, it, b, 0), make_vars()
+        for v, m in zip(V, maxdof):
+            for pos in range(1, m + 1):
+                v.create(pos, rng)
+        w = f(*V)
+        pad = [_pad_all(V, DOF[i], maxdof) for i in range(NI + 1)]
+        cur = rw[NI] * pad[NI]
+        for i in range(NI):
+            cur += abs(w[i]) * rw[i] * pad[i]
+        o, n = [0.0] * NI, 0.0
+        for ne in range(1, steps + 1):
+            vi = rng.randint(Nv) - 1
+            v = V[vi]
+            if not (isinstance(v, DiscreteOne) and len(v.dist[0]) == 1) and maxdof[vi] > 0:
+                pos = rng.randint(maxdof[vi])
+                prop = v.shift(pos, rng)
+                if prop > EPS0:
+                    nw = f(*V)
+                    neval += 1
+                    npad = [_pad_all(V, DOF[i], maxdof) for i in range(NI + 1)]
+                    new = rw[NI] * npad[NI]
+                    for i in range(NI):
+                        new += abs(nw[i]) * rw[i] * npad[i]
+                    R = prop * new / cur
+                    prop_c[vi] += 1.0
+                    if rng.rand() < R:
+                        acc_c[vi] += 1.0
+                        w, pad, cur = nw, npad, new
+                    else:
+                        v.rollback(pos)
+            for i in range(NI):
+                f2 = abs(w[i]) * abs(w[i]) / _prob_all(V, DOF[i])
+                wf2 = f2 * pad[i] / cur
+                for k, vv in enumerate(V):
+                    sub = [0.0] * vv.hist_len()
+                    for p_ in range(1, DOF[i][k] + 1):
+                        vv.accumulate(p_, wf2, sub)
+                    for j, x in enumerate(sub):
+                        hist[hoff[k] + j] += x
+            if ne % mf == 0 and ne >= steps / 100:
+                for i in range(NI):
+                    visited[i] += abs(w[i] * pad[i] * rw[i]) / cur
+                    o[i] += w[i] * pad[i] / cur
+                n += 1.0 * pad[NI] / cur
+                visited[NI] += rw[NI] * pad[NI] / cur
+        obs.append(o)
+        norm.append(n)
+    return dict(obs=obs, norm=norm, hist=hist, visited=visited, propose_cv=prop_c, accept_cv=acc_c, neval=neval)
+
+
 def main():
     rnd = random.Random(20261017)
     G = {}
@@ -824,6 +940,16 @@ def main():
         G["loops_fermik"].append(dict(dim=D, userdata=ud, tgrid=tgrid, kF=kF, dk=dk, reweight=frw, seed=seedF, iter=2, n_block=2,
                                       steps=400, measurefreq=1, thermal_ratio=0.1,
                                       out=loop_mcmc_vars(mk, bubble_fermik(ud, D), frw, seedF, 2, 2, 400, 1, 0.1, Qsize)))
+
+    # :vegas and :vegasmc over TWO top-level variables with padding across them: var = (Continuous pool on the hand grid,
+    # Discrete(1,4) with a non-uniform distribution), sphere2 on the pool, dof = [[2, 1], [3, 0]]
+    vdist = [0.1, 0.4, 0.15, 0.35]
+    vdof = [[2, 1], [3, 0], [0, 0]]
+    mkv = lambda: [Pool(lgrid, 3), DiscreteOne(vdist, 1, 1, adapt=True)]
+    fv = lambda P, D: sphere2(P.data)
+    G["loops_vars"] = dict(grid=lgrid, dist=vdist, reweight=lrw, seed=909, iter=2, n_block=2,
+                           vegas=dict(npb=70, measurefreq=1, out=loop_vegas_vars(mkv, fv, vdof, 909, 2, 2, 70, 1)),
+                           vegasmc=dict(steps=300, measurefreq=1, out=loop_vegasmc_vars(mkv, fv, vdof, lrw, 909, 2, 2, 300, 1)))
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:

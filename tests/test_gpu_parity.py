@@ -541,3 +541,17 @@ def test_bubble_fermik_against_finite_temperature_exact():
         ex = lindhard_finite_temperature(para, q)
         assert abs(avg[i] - ex) < 5.0 * std[i], (i, avg[i], std[i], ex)
         assert std[i] < 1e-3
+
+
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc"])
+def test_gpu_against_independent_two_variable_loop_fixtures(solver):
+    """golden.json["loops_vars"]: two top-level variables (Continuous pool + Discrete) with padding across them — the
+    layout class of example/bubble.jl — whole :vegas / :vegasmc loops restated in pure Python"""
+    from test_oracle_units import check_vars_loop, vars_loop_spec
+    spec, maps, G, L0 = vars_loop_spec(solver)
+    gpu = mci.CudaEngine(spec)
+    try:
+        gpu.set_maps(**maps)
+        check_vars_loop(gpu.run_iteration(G["iter"]), G, L0, solver, rtol=1e-10)
+    finally:
+        gpu.close()

@@ -383,3 +383,44 @@ def test_fermik_bubble_oracle_vs_lindhard():
         exact = I.lindhard_finite_temperature(para, q)
         assert abs(res.mean[0][i] - exact) < 5.0 * res.stdev[0][i], (q, res.mean[0][i], res.stdev[0][i], exact)
         assert res.stdev[0][i] < 0.03 * abs(exact)
+
+
+def vars_loop_spec(solver_name):
+    """golden.json["loops_vars"]: var = (Continuous pool, Discrete(1,4)), sphere2 on the pool, dof = [[2, 1], [3, 0]]"""
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import _abi, integrands
+    G = GOLD["loops_vars"]
+    L0 = G[solver_name]
+    cfg = mci.Configuration(var=(mci.Continuous(0.0, 1.0, grid=G["grid"]), mci.Discrete(1, 4)), dof=[[2, 1], [3, 0]], seed=G["seed"])
+    solver = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC}[solver_name]
+    spec = mci.problem_from_config(cfg, integrands.sphere2, solver=solver, measure_kind=0, n_block=G["n_block"],
+                                   neval_per_block=L0.get("npb", L0.get("steps")), measurefreq=L0["measurefreq"], walkers_per_block=1)
+    d = G["dist"]
+    maps = dict(grids=arr(G["grid"]), dist=arr(d), accum=arr([0.0] + [sum(d[: i + 1], 0.0) for i in range(len(d))]), reweight=arr(G["reweight"]))
+    return spec, maps, G, L0
+
+
+def check_vars_loop(st, G, L0, solver_name, rtol=1e-12):
+    want, B1 = L0["out"], G["n_block"] + 1
+    np.testing.assert_allclose(st.block_obs, want["obs"], rtol=rtol)
+    np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=rtol)
+    np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"], rtol=1e-9, atol=1e-9)
+    if solver_name == "vegasmc":
+        np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+        assert st.neval == want["neval"]
+        # propose/accept[2, 1, vi] (vegas_mc/updates.jl:90,92): row-major [3][Nd][max(Nd, Nv)] -> [1][0][vi]
+        assert np.array_equal(np.round(st.propose[1, 0, :2] - B1 * 1e-8, 3), np.array(want["propose_cv"]))
+        assert np.array_equal(np.round(st.accept[1, 0, :2] - B1 * 1e-10, 3), np.array(want["accept_cv"]))
+
+
+@pytest.mark.parametrize("solver_name", ["vegas", "vegasmc"])
+def test_two_variable_loops_against_independent_restatement(solver_name):
+    """Several top-level variables with padding across them (the layout class of example/bubble.jl), whole loops"""
+    from oracle_lib import OracleEngine
+    spec, maps, G, L0 = vars_loop_spec(solver_name)
+    eng = OracleEngine(spec, nthreads=1)
+    try:
+        eng.set_maps(**maps)
+        check_vars_loop(eng.run_iteration(G["iter"]), G, L0, solver_name)
+    finally:
+        eng.close()
