@@ -27,7 +27,8 @@
  *     solver loops (vegas, vegasmc, mcmc on a two-integrand pool problem:
  *     observables, normalisation, histograms, visited / propose / accept
  *     counters; the same loops on a CompositeVar of two Discrete leaves with
- *     non-uniform distributions; the :mcmc loop of test/bubble_FermiK.jl on
+ *     non-uniform distributions; :vegas / :vegasmc over two top-level
+ *     variables with padding across them; the :mcmc loop of test/bubble_FermiK.jl on
  *     (T, K::FermiK{3 or 2}, Ext)) produced by an independent pure-Python
  *     restatement of the Julia sources (tests/golden/make_golden.py);
  *   - Philox4x32-10 against the Random123 known-answer vectors.
