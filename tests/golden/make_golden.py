@@ -718,8 +718,9 @@ def _pad_all(V, dofs, maxdof):  # variable.jl:628-641
     return p
 
 
-def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf):
-    """vegas/montecarlo.jl:117-187 over SEVERAL top-level variables; DOF[i][v] incl. the normalisation row"""
+def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf, nbins_obs=0):
+    """vegas/montecarlo.jl:117-187 over SEVERAL top-level variables; DOF[i][v] incl. the normalisation row.
+    nbins_obs > 0: measure = the bubble's (example/bubble.jl:81-84): obs[1][Ext[1]] += relative weight of integrand 1"""
     NI, Nv = len(DOF) - 1, len(DOF[0])
     maxdof = [max(d[v] for d in DOF) for v in range(Nv)]
     V0 = make_vars()
@@ -729,7 +730,7 @@ def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf):
     hist = [0.0] * hoff[-1]
     obs, norm = [], []
     for b in range(nblock):
-        o, n = [0.0] * NI, 0.0
+        o, n = [0.0] * (nbins_obs or NI), 0.0
         for ne in range(1, npb + 1):
             rng, V = Stream(seed, it, b, ne - 1), make_vars()
             jac = 1.0
@@ -740,8 +741,11 @@ def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf):
             pad = [1.0 if DOF[i] == maxdof else _pad_all(V, DOF[i], maxdof) for i in range(NI)]
             w = f(*V)
             if ne % mf == 0:
-                for i in range(NI):
-                    o[i] += w[i] * pad[i] * jac
+                if nbins_obs:
+                    o[V[-1].val[0][1] - V[-1].lower[0]] += w[0] * pad[0] * jac
+                else:
+                    for i in range(NI):
+                        o[i] += w[i] * pad[i] * jac
                 n += 1.0
             for k, v in enumerate(V):
                 sub = [0.0] * v.hist_len()
@@ -755,7 +759,7 @@ def loop_vegas_vars(make_vars, f, DOF, seed, it, nblock, npb, mf):
     return dict(obs=obs, norm=norm, hist=hist)
 
 
-def loop_vegasmc_vars(make_vars, f, DOF, rw, seed, it, nblock, steps, mf):
+def loop_vegasmc_vars(make_vars, f, DOF, rw, seed, it, nblock, steps, mf, nbins_obs=0):
     """vegas_mc/montecarlo.jl:151-232 + updates.jl:45-106 over several top-level variables, one chain per block;
     propose/accept[2, 1, vi] come back as lists over vi"""
     NI, Nv = len(DOF) - 1, len(DOF[0])
@@ -777,7 +781,7 @@ def loop_vegasmc_vars(make_vars, f, DOF, rw, seed, it, nblock, steps, mf):
         cur = rw[NI] * pad[NI]
         for i in range(NI):
             cur += abs(w[i]) * rw[i] * pad[i]
-        o, n = [0.0] * NI, 0.0
+        o, n = [0.0] * (nbins_obs or NI), 0.0
         for ne in range(1, steps + 1):
             vi = rng.randint(Nv) - 1
             v = V[vi]
@@ -810,7 +814,10 @@ def loop_vegasmc_vars(make_vars, f, DOF, rw, seed, it, nblock, steps, mf):
             if ne % mf == 0 and ne >= steps / 100:
                 for i in range(NI):
                     visited[i] += abs(w[i] * pad[i] * rw[i]) / cur
-                    o[i] += w[i] * pad[i] / cur
+                    if nbins_obs:
+                        o[V[-1].val[0][1] - V[-1].lower[0]] += w[i] * pad[i] / cur
+                    else:
+                        o[i] += w[i] * pad[i] / cur
                 n += 1.0 * pad[NI] / cur
                 visited[NI] += rw[NI] * pad[NI] / cur
         obs.append(o)
@@ -950,6 +957,17 @@ def main():
     G["loops_vars"] = dict(grid=lgrid, dist=vdist, reweight=lrw, seed=909, iter=2, n_block=2,
                            vegas=dict(npb=70, measurefreq=1, out=loop_vegas_vars(mkv, fv, vdof, 909, 2, 2, 70, 1)),
                            vegasmc=dict(steps=300, measurefreq=1, out=loop_vegasmc_vars(mkv, fv, vdof, lrw, 909, 2, 2, 300, 1)))
+
+    # the bubble's measure (bin the one integrand by the last, non-adaptive Discrete variable) under :vegas / :vegasmc:
+    # var = (Continuous pool, Discrete(1,4; adapt=false)), f = x, dof = [[1, 1]]
+    bdof = [[1, 1], [0, 0]]
+    mkb = lambda: [Pool(lgrid, 1), DiscreteOne([0.25] * 4, 1, 1, adapt=False)]
+    fb = lambda P, D: [P.data[1]]
+    brw = [0.8, 0.2]
+    G["loops_binned"] = dict(grid=lgrid, reweight=brw, seed=5150, iter=4, n_block=2,
+                             vegas=dict(npb=90, measurefreq=1, out=loop_vegas_vars(mkb, fb, bdof, 5150, 4, 2, 90, 1, nbins_obs=4)),
+                             vegasmc=dict(steps=300, measurefreq=1,
+                                          out=loop_vegasmc_vars(mkb, fb, bdof, brw, 5150, 4, 2, 300, 1, nbins_obs=4)))
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:

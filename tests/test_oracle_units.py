@@ -424,3 +424,34 @@ def test_two_variable_loops_against_independent_restatement(solver_name):
         check_vars_loop(eng.run_iteration(G["iter"]), G, L0, solver_name)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("solver_name", ["vegas", "vegasmc"])
+def test_binned_measure_loops_against_independent_restatement(solver_name):
+    """The bubble's measure (example/bubble.jl:81-84: bin the integrand by the last, non-adaptive Discrete variable) inside
+    whole :vegas / :vegasmc loops.  The GPU runs this measure against the oracle in the L1 bubble tests."""
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import _abi, integrands
+    from oracle_lib import OracleEngine
+    G = GOLD["loops_binned"]
+    L0 = G[solver_name]
+    cfg = mci.Configuration(var=(mci.Continuous(0.0, 1.0, grid=G["grid"]), mci.Discrete(1, 4, adapt=False)), dof=[[1, 1]],
+                            obs=[np.zeros(4)], seed=G["seed"])
+    solver = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC}[solver_name]
+    spec = mci.problem_from_config(cfg, integrands.discrete_x, solver=solver, measure_kind=_abi.MEASURE_BIN_BY_DISCRETE,
+                                   n_block=G["n_block"], neval_per_block=L0.get("npb", L0.get("steps")),
+                                   measurefreq=L0["measurefreq"], walkers_per_block=1)
+    eng = OracleEngine(spec, nthreads=1)
+    try:
+        eng.set_maps(grids=arr(G["grid"]), reweight=arr(G["reweight"]))
+        st = eng.run_iteration(G["iter"])
+        want, B1 = L0["out"], G["n_block"] + 1
+        np.testing.assert_allclose(st.block_obs, want["obs"], rtol=1e-12)
+        np.testing.assert_allclose(st.block_norm - 1e-10, want["norm"], rtol=1e-12)
+        # histogram: the pool's 8 increments, then the 4 values of the non-adaptive Discrete (never filled)
+        np.testing.assert_allclose(st.hist - B1 * 1e-10, want["hist"] + [0.0] * 4, rtol=1e-9, atol=1e-9)
+        if solver_name == "vegasmc":
+            np.testing.assert_allclose(st.visited - B1 * 1e-8, want["visited"], rtol=1e-9, atol=1e-6)
+            assert st.neval == want["neval"]
+    finally:
+        eng.close()
