@@ -30,7 +30,9 @@
  *     non-uniform distributions; :vegas / :vegasmc over two top-level
  *     variables with padding across them; the :mcmc loop of test/bubble_FermiK.jl on
  *     (T, K::FermiK{3 or 2}, Ext)) produced by an independent pure-Python
- *     restatement of the Julia sources (tests/golden/make_golden.py);
+ *     restatement of the Julia sources (tests/golden/make_golden.py), which
+ *     tests/test_oracle_fuzz.py also runs against this file on seeded random
+ *     problems;
  *   - Philox4x32-10 against the Random123 known-answer vectors.
  */
 #ifndef MCI_ORACLE_H
