@@ -555,3 +555,32 @@ def test_gpu_against_independent_two_variable_loop_fixtures(solver):
         check_vars_loop(gpu.run_iteration(G["iter"]), G, L0, solver, rtol=1e-10)
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("solver", ["vegas", "vegasmc", "mcmc"])
+@pytest.mark.parametrize("seed", range(1, 9))
+def test_gpu_against_oracle_on_random_problems(seed, solver):
+    """The random problems of tests/test_oracle_fuzz.py (random grids, integrand sets with and without padding, reweight
+    factors, seeds, iteration numbers, block counts, measurement frequency, thermal ratio), cut into a random number of
+    chains per block: GPU against the oracle, one iteration."""
+    import random
+    from test_oracle_fuzz import _case
+    from cases import SOLVER_ID
+    c = _case(7000 + 100 * seed + len(solver))
+    rnd = random.Random(seed)
+    walkers = 1 if solver == "vegas" else rnd.choice([1, 7, 32, 96])
+    npb = walkers * rnd.randint(20, 120) if solver != "vegas" else rnd.randint(1, 5000)
+    cfg = mci.Configuration(var=mci.Continuous(c["grid"][0], c["grid"][-1], grid=c["grid"]), dof=c["dof"], seed=c["seed"])
+    spec = mci.problem_from_config(cfg, c["f_dev"], solver=SOLVER_ID[solver], measure_kind=0, n_block=c["n_block"], neval_per_block=npb,
+                                   measurefreq=c["mf"], walkers_per_block=walkers, thermal_ratio=c["thermal"])
+    gpu, cpu = mci.CudaEngine(spec), OracleEngine(spec)
+    try:
+        for e in (gpu, cpu):
+            e.set_maps(grids=np.array(c["grid"]), reweight=np.array(c["rw"]))
+        a, b = gpu.run_iteration(c["it"]), cpu.run_iteration(c["it"])
+        _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
+        np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
+        assert np.array_equal(np.round(a.propose - b.propose, 6), np.zeros_like(a.propose))
+        assert np.array_equal(np.round(a.accept - b.accept, 6), np.zeros_like(a.accept))
+    finally:
+        gpu.close(); cpu.close()
