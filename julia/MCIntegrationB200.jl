@@ -10,7 +10,7 @@
 module MCIntegrationB200
 
 using MCIntegration
-using MCIntegration: Configuration, Continuous, Discrete, CompositeVar, Result, Dist
+using MCIntegration: Configuration, Continuous, Discrete, CompositeVar, FermiK, Result, Dist
 
 const LIB = get(ENV, "LIBMCIB200", "libmcib200")
 
@@ -141,7 +141,7 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
         for l in lv
             if l isa Continuous
                 n = length(l.grid); l.grid .= grids[go+1:go+n]; go += n
-            else
+            elseif l isa Discrete                                                  # a FermiK has no map to pull back
                 n = length(l.distribution); l.distribution .= dist[dd+1:dd+n]; l.accumulation .= accum[da+1:da+n+1]
                 dd += n; da += n + 1
             end
