@@ -38,14 +38,15 @@ typedef unsigned long long uint64_t;
 extern "C" {
 #endif
 
-#define MCI_ABI_VERSION 2
+#define MCI_ABI_VERSION 3
 
 /* ---- limits of the POD problem description ------------------------------ */
 #define MCI_MAX_TOPVAR 16    /* top-level variables (`config.var` tuple, configuration.jl:40) */
 #define MCI_MAX_LEAF 32      /* leaf maps over all top-level variables                  */
-#define MCI_MAX_INTEGRAND 8  /* Ni, without the normalisation integrand                 */
+#define MCI_MAX_INTEGRAND 16 /* Ni, without the normalisation integrand: the reference's own bound
+                                MaxOrder = 16 (src/distribution/distribution.jl:59)        */
 #define MCI_MAX_SLOT 24      /* max dof of one pool variable on the device              */
-#define MCI_MAX_USERDATA 32  /* doubles                                                 */
+#define MCI_MAX_USERDATA 64  /* doubles                                                 */
 #define MCI_MAX_OBS 64       /* total observable length (sum of obs_len)                */
 
 /* ---- error codes ------------------------------------------------------- */
@@ -93,6 +94,8 @@ enum mci_integrand_id {
   MCI_F_POLY3 = 14,         /* (x, x^2, x^3), dof=[[1],[1],[1]]       test/thread.jl                       */
   MCI_F_X2_PLUS_Y2 = 15,    /* x1^2+x2^2, pool dof=[[2]]              main.jl:64, vegas/montecarlo.jl:69   */
   MCI_F_BUBBLE_FERMIK = 16, /* the same polarization bubble on vars (T, K::FermiK{3}, Ext), mcmc  test/bubble_FermiK.jl:54-75 */
+  MCI_F_COMPLEX1 = 17,      /* x + i x^2, one COMPLEX integrand, pool dof=[[1]]   test/montecarlo.jl:166-170 (TestComplex1) */
+  MCI_F_COMPLEX2 = 18,      /* (x, i x^2), two COMPLEX integrands, dof=[[1],[1]]  test/montecarlo.jl:172-198 (TestComplex2) */
   MCI_F_USER = 100          /* the caller's own integrand: CUDA C++ source in mci_problem_t.user_source, compiled with
                                NVRTC at mci_create into a kernel specialised to the problem — the equivalent of the
                                reference taking any closure f(x, c) (main.jl:25-33).  The source defines
@@ -100,7 +103,8 @@ enum mci_integrand_id {
                                                                    const double *userdata, double *w);
                                X(leaf, pos): value of pool slot pos (1-based, the reference's x[pos]) of leaf variable
                                `leaf` (0-based: top-level order, then leaf order inside a CompositeVar);
-                               w[0 .. n_integrand-1] receives the integrand values.                                */
+                               w[0 .. n_integrand-1] receives the integrand values (weight_kind = MCI_WEIGHT_COMPLEX:
+                               w[2i], w[2i+1] = real and imaginary part of integrand i).                            */
 };
 
 /* `measure` kwarg (main.jl:35-37, 83).  Default = obs[i] += relw[i]. */
@@ -171,7 +175,18 @@ typedef struct mci_problem_t {
                               touching no statistic (0 = the reference).  A GPU cuts a block into many short chains
                               and each starts from a draw of the VEGAS map, not of the target density: chains of
                               ~10^3 steps carry a visible start bias, which this burns away          */
+  /* ---- ABI v3 ---- */
+  int32_t mcmc_start_idx;  /* mcmc: the integrand every chain starts in, 1-based — the `idx` kwarg of MCMC.montecarlo
+                              (mcmc/montecarlo.jl:76); 0 = the reference's default 1                                 */
+  int32_t weight_kind;     /* MCI_WEIGHT_*: the `type` kwarg of Configuration (configuration.jl:108): Float64 or
+                              ComplexF64 integrand values and observables (main.jl:276-286,302-305)                  */
 } mci_problem_t;
+
+/* weight_kind.  COMPLEX: every integrand value is (re, im); every observable entry is (re, im) — obs_len[i] counts
+ * COMPLEX entries and block_obs holds 2 * sum(obs_len) doubles per block, interleaved re, im; the sampling weight of
+ * a value is abs(z) = hypot(re, im) wherever the reference takes abs(weight) (vegas/montecarlo.jl:172,
+ * vegas_mc/montecarlo.jl:159,200, mcmc/updates.jl:40,95,130).  Built-in real integrands stay real. */
+enum { MCI_WEIGHT_REAL = 0, MCI_WEIGHT_COMPLEX = 1 };
 
 enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };
 /* where the per-bin variance histogram (accumulate!, variable.jl:196-200) is kept during a launch; every policy
@@ -188,7 +203,8 @@ enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI
  * (main.jl:236-292, configuration.jl:252-299).  Any pointer may be NULL.
  */
 typedef struct mci_iteration_out_t {
-  double *block_obs;   /* [n_block][sum obs_len]  config_n.observable of each block (un-normalised) */
+  double *block_obs;   /* [n_block][sum obs_len]  config_n.observable of each block (un-normalised);
+                          MCI_WEIGHT_COMPLEX: [n_block][sum obs_len][2] = (re, im)                       */
   double *block_norm;  /* [n_block]               config_n.normalization (incl. the 1e-10 floor)    */
   double *hist;        /* [sum_leaf nbins]        summed leaf histograms incl. (n_block+1)*1e-10     */
   double *visited;     /* [Nd]                    incl. floors                                       */
@@ -223,7 +239,8 @@ const char *mci_last_error(const mci_handle_t *h);
 /* sizes the caller needs to allocate the arrays below */
 int mci_sizes(const mci_handle_t *h, int32_t *grid_len /* sum (nbins+1) over Continuous */,
               int32_t *disc_len /* sum nbins over Discrete */, int32_t *hist_len /* sum nbins all leaves */,
-              int32_t *obs_len /* sum obs_len */, int32_t *nd /* Ni+1 */, int32_t *pa_len /* 3*Nd*max(Nd,Nv) */);
+              int32_t *obs_len /* sum obs_len, in DOUBLES (x2 for MCI_WEIGHT_COMPLEX) */, int32_t *nd /* Ni+1 */,
+              int32_t *pa_len /* 3*Nd*max(Nd,Nv) */);
 
 /*
  * Upload maps (warm restart `config=result.config`, main.jl:95-97; and the
@@ -297,7 +314,7 @@ int mci_stats_sync_host(mci_handle_t *h);
  * Parity probe (L0): regenerate samples [first, first+count) of block `block`
  * of iteration `iter` with the current maps, VEGAS sampler only.  Layout:
  * x[count][n_draw], bins[count][n_draw] (0-based grid bin / discrete index),
- * jac[count], weights[count][Ni].  n_draw = draws per sample in the
+ * jac[count], weights[count][Ni] ([count][Ni][2] = (re, im) for MCI_WEIGHT_COMPLEX).  n_draw = draws per sample in the
  * reference's draw order (vegas/montecarlo.jl:122-131, sampler.jl:431-440).
  */
 int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t first, int32_t count, double *x,
@@ -309,6 +326,25 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
  * log in `log` (NUL-terminated, at most log_cap bytes).  Lets a host validate user_source before it has a device.
  */
 int mci_jit_check(const mci_problem_t *problem, char *log, int32_t log_cap);
+
+/*
+ * Number of non-finite integrand values seen by the fill kernel of the last fetched iteration, summed over this
+ * rank's blocks.  Replaces the `debug = true` warnings of the solver loops ("abs of the integrand ... is not
+ * finite", vegas/montecarlo.jl:176-178, vegas_mc/montecarlo.jl:189-191, mcmc/montecarlo.jl:142-144): the host prints
+ * the warning when the count is non-zero.
+ */
+int mci_nonfinite_count(const mci_handle_t *h, uint64_t *n);
+
+/*
+ * Small jobs: run `niter` whole iterations — fill -> statistics [-> all-reduce] -> doReweight! (chain solvers) ->
+ * train! -> staged maps — as ONE CUDA graph launch per iteration with no host synchronisation in between, and copy
+ * every iteration's statistics out at the end.  out[k] receives iteration first_iter + k (any pointer may be NULL).
+ * Equivalent to niter x (mci_run_iteration, mci_reweight(gamma, goal), mci_refine) — the body of the loop of
+ * main.jl:142-207 with adapt = true — minus 2 host round trips per iteration.  `do_reweight` / `do_refine` select the
+ * steps (main.jl:183, :193-198).
+ */
+int mci_run_iterations(mci_handle_t *h, uint64_t first_iter, int32_t niter, double gamma, const double *goal,
+                       int32_t do_reweight, int32_t do_refine, mci_iteration_out_t *out);
 
 /* measurement helpers ---------------------------------------------------- */
 /* number of kernel launches issued by this handle so far */

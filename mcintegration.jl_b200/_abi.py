@@ -8,13 +8,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MAX_TOPVAR = 16
 MAX_LEAF = 32
-MAX_INTEGRAND = 8
+MAX_INTEGRAND = 16
 MAX_SLOT = 24
-MAX_USERDATA = 32
+MAX_USERDATA = 64
 MAX_OBS = 64
 
 OK = 0
@@ -30,6 +30,7 @@ SOLVER_VEGAS, SOLVER_VEGASMC, SOLVER_MCMC = 0, 1, 2
 LEAF_CONTINUOUS, LEAF_DISCRETE, LEAF_FERMIK = 0, 1, 2
 MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE, MEASURE_USER = 0, 1, 2
 JIT_AUTO, JIT_ON, JIT_OFF = 0, 1, 2
+WEIGHT_REAL, WEIGHT_COMPLEX = 0, 1
 HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
 
 # enum mci_integrand_id
@@ -49,6 +50,8 @@ F_HYPERSPHERE3 = 13
 F_POLY3 = 14
 F_X2_PLUS_Y2 = 15
 F_BUBBLE_FERMIK = 16
+F_COMPLEX1 = 17
+F_COMPLEX2 = 18
 F_USER = 100
 
 
@@ -93,6 +96,8 @@ class Problem(C.Structure):
         ("reserved_", C.c_int32),
         ("user_source", C.c_char_p),
         ("chain_burnin", C.c_uint64),
+        ("mcmc_start_idx", C.c_int32),
+        ("weight_kind", C.c_int32),
     ]
 
 
@@ -139,6 +144,8 @@ EXPORTS = [
     "mci_fill_history",
     "mci_jit_check",
     "mci_chain_info",
+    "mci_nonfinite_count",
+    "mci_run_iterations",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -197,6 +204,8 @@ def declare(lib, prefix="mci_"):
         f("jit_check", C.c_int, [C.POINTER(Problem), C.c_char_p, C.c_int32])
         f("chain_info", C.c_int, [H, ip, C.POINTER(C.c_uint64), ip])
         f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
+        f("nonfinite_count", C.c_int, [H, C.POINTER(C.c_uint64)])
+        f("run_iterations", C.c_int, [H, C.c_uint64, C.c_int32, C.c_double, dp, C.c_int32, C.c_int32, C.POINTER(IterationOut)])
     return lib
 
 

@@ -91,8 +91,9 @@ class Configuration:
         if obs is None:
             obs = [0.0] * (Nd - 1)
         assert len(obs) == Nd - 1, "The number of observables should be equal to the number of integrands"
-        self.observable = [np.zeros(len(o)) if isinstance(o, (list, tuple, np.ndarray)) else 0.0 for o in obs]
         self.type = type
+        dt = np.complex128 if self.is_complex() else np.float64
+        self.observable = [np.zeros(len(o), dtype=dt) if isinstance(o, (list, tuple, np.ndarray)) else dt(0.0) for o in obs]
         self.N = Nd - 1
         self.norm = Nd
         self.neighbor = _neighbor(neighbor, Nd)
@@ -103,6 +104,9 @@ class Configuration:
         assert np.all(reweight > 0), "All reweight factors should be positive."
         self.reweight = reweight / reweight.sum()
         self.seed = int(seed) if seed is not None else random.SystemRandom().randint(1, 1000000)
+        # config.rng = MersenneTwister(seed) (configuration.jl:177-178): every integrate() call draws the seed of its
+        # sample streams from it (main.jl:136), so successive calls on one Configuration use independent samples
+        self.rng = random.Random(self.seed)
         self.userdata = userdata
         self.normalization = 1.0e-10
         self.visited = np.full(Nd, 1.0e-8)
@@ -120,6 +124,14 @@ class Configuration:
 
     def obs_len(self):
         return [len(o) if isinstance(o, np.ndarray) else 1 for o in self.observable]
+
+    def is_complex(self):
+        """type = ComplexF64 (configuration.jl:108): integrand values and observables are complex"""
+        return self.type is complex or self.type in (np.complex128, "ComplexF64", "complex")
+
+    def next_seed(self):
+        """rand(config.rng, 1:1000000): the seed one integrate() call gives its solver streams (main.jl:136)"""
+        return self.rng.randint(1, 1000000)
 
     def __repr__(self):
         return f"Configuration(N={self.N}, var={self.var}, dof={self.dof[:-1]}, seed={self.seed})"
@@ -150,6 +162,8 @@ class ProblemSpec:
     jit: int = 0
     user_source: str | None = None
     chain_burnin: int = 0
+    mcmc_start_idx: int = 0  # `idx` of MCMC.montecarlo (mcmc/montecarlo.jl:76), 1-based; 0 = default 1
+    weight_kind: int = 0     # _abi.WEIGHT_REAL / WEIGHT_COMPLEX
 
     def to_ctypes(self):
         keep = []
@@ -193,6 +207,8 @@ class ProblemSpec:
         p.hist_policy = self.hist_policy
         p.jit = self.jit
         p.chain_burnin = int(self.chain_burnin)
+        p.mcmc_start_idx = int(self.mcmc_start_idx)
+        p.weight_kind = int(self.weight_kind)
         if self.user_source is not None:
             src = self.user_source.encode()
             keep.append(src)
@@ -204,7 +220,7 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
                         neval_per_block: int, measurefreq: int = 1, walkers_per_block: int = 1,
                         thermal_ratio: float = 0.1, device: int = 0, hist_policy: int = 0,
                         default_neighbor: bool = False, jit: int = 0, chain_burnin: int = 0,
-                        measure_source: str | None = None) -> ProblemSpec:
+                        measure_source: str | None = None, seed: int | None = None, mcmc_start_idx: int = 0) -> ProblemSpec:
     leaves = []
     for L in config.leaves():
         if isinstance(L, Continuous):
@@ -217,12 +233,17 @@ def problem_from_config(config: Configuration, integrand, *, solver: int, measur
     sources = [x for x in (getattr(integrand, "source", None), measure_source) if x]
     assert integrand.n_integrand == config.N, (
         f"integrand {integrand.name} returns {integrand.n_integrand} values but dof has {config.N} rows")
+    assert bool(getattr(integrand, "complex", False)) == config.is_complex(), (
+        f"integrand {integrand.name} is {'complex' if getattr(integrand, 'complex', False) else 'real'}-valued: "
+        f"Configuration(type=...) must say the same (configuration.jl:108)")
     return ProblemSpec(
         solver=solver, integrand_id=integrand.id, measure_kind=measure_kind, n_integrand=config.N,
         topvar_nleaf=[len(v.leaves()) for v in config.var], topvar_offset=[v.offset for v in config.var],
         leaves=leaves, dof=[list(d) for d in config.dof[:-1]], obs_len=config.obs_len(),
         neighbor=None if default_neighbor else config.neighbor, userdata=list(integrand.userdata),
-        n_block=n_block, neval_per_block=neval_per_block, seed=config.seed, measurefreq=measurefreq,
+        n_block=n_block, neval_per_block=neval_per_block, seed=config.seed if seed is None else int(seed),
+        measurefreq=measurefreq, mcmc_start_idx=mcmc_start_idx,
+        weight_kind=_abi.WEIGHT_COMPLEX if config.is_complex() else _abi.WEIGHT_REAL,
         walkers_per_block=walkers_per_block, thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit,
         user_source="\n".join(sources) if sources else None, chain_burnin=chain_burnin)
 

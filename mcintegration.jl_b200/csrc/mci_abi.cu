@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,21 +45,25 @@ struct NcclApi {
   bool ok = false;
 };
 NcclApi g_nccl;
+std::once_flag g_nccl_once;
 
-bool nccl_load() {
-  if (g_nccl.ok) return true;
+void nccl_load_once() {
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
     g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (g_nccl.lib) break;
   }
-  if (!g_nccl.lib) return false;
+  if (!g_nccl.lib) return;
   g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+/* two handles on two host threads may attach communicators at the same time: bind libnccl exactly once */
+bool nccl_load() {
+  std::call_once(g_nccl_once, nccl_load_once);
   return g_nccl.ok;
 }
 constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
@@ -94,6 +99,10 @@ struct mci_handle_t {
    * and synchronise the device: a job of the reference's default size, neval = 1e4, is over in 4 ms):
    * the fixed state, the per-launch partials (re-planned by mci_set_partition) and the pinned host mirrors */
   void *d_state_arena = nullptr, *d_launch_arena = nullptr, *h_arena = nullptr;
+  size_t state_cap = 0, launch_cap = 0, host_cap = 0; /* capacities, for the block cache */
+  /* mci_run_iterations: the statistics (and flags) of every iteration of one call, kept on the device until the end */
+  void *d_history = nullptr, *h_history = nullptr;
+  size_t history_cap = 0, h_history_cap = 0;
   /* pinned host mirrors */
   double *h_packed = nullptr;
   unsigned long long *h_flags = nullptr;
@@ -116,6 +125,7 @@ struct mci_handle_t {
   bool jit_failed = false;
   int jit_mode = 0, chain_maxt = 1024;
   uint64_t launches = 0;
+  uint64_t nonfinite = 0; /* non-finite integrand values of the last fetched iteration (flags[0]) */
   float fill_ms = 0.f, iter_ms = 0.f;
   char err[256];
 };
@@ -156,9 +166,24 @@ bool fid_info(int fid, FidInfo &I) {
     case MCI_F_HYPERSPHERE3: I = {3, 1, 4}; return true;
     case MCI_F_POLY3: I = {3, 1, 1}; return true;
     case MCI_F_X2_PLUS_Y2: I = {1, 1, 2}; return true;
+    case MCI_F_COMPLEX1: I = {1, 1, 1}; return true;
+    case MCI_F_COMPLEX2: I = {2, 1, 1}; return true;
     case MCI_F_USER: I = {0, 1, 0}; return true; /* any number of values, any layout: the source decides */
   }
   return false;
+}
+
+/* doubles of userdata a built-in integrand reads (mci_integrands.cuh): a short blob would be zero-filled and give a
+ * wrong integral without any error, so mci_create insists on at least this many */
+int userdata_needed(const DevProblem &P) {
+  switch (P.fid) {
+    case MCI_F_GENZ_CORNER_POOL: return P.dof[0];
+    case MCI_F_GENZ_CORNER_COMP: return P.nleaf;
+    case MCI_F_BUBBLE:
+    case MCI_F_BUBBLE_FERMIK: return 6 + P.leaf[P.nleaf - 1].nbins; /* [kF, beta, me, spin, dim, Qsize, extQ_x[Ext]...] */
+    case MCI_F_PRODUCT_4: return 4;
+  }
+  return 0;
 }
 
 double volume_inverse(int d) { /* test/montecarlo.jl:201-204 */
@@ -166,6 +191,42 @@ double volume_inverse(int d) { /* test/montecarlo.jl:201-204 */
   const double pi = 3.14159265358979323846;
   return pow(d / (2 * pi * euler), d / 2.0) * sqrt((double)d) * sqrt(pi);
 }
+
+/* A process-wide cache of released arenas.  cudaMalloc / cudaFree / cudaMallocHost / cudaFreeHost cost 0.1-1 ms each
+ * and synchronise the device; a job of the reference's default size (neval = 1e4, main.jl:74) is over in ~1 ms of
+ * device time, so a host that calls integrate() in a loop pays more for allocation than for integration.  Blocks
+ * are rounded up to a power of two (>= 4 KB), at most 8 per kind are kept, none above 32 MB. */
+struct BlockCache {
+  std::mutex mu;
+  struct Blk { void *p; size_t cap; int dev; };
+  std::vector<Blk> dev, host;
+  static size_t round_up(size_t n) { size_t c = 4096; while (c < n) c <<= 1; return c; }
+  cudaError_t get(bool pinned, int device, size_t bytes, void **out, size_t *cap) {
+    const size_t want = round_up(bytes);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      std::vector<Blk> &v = pinned ? host : dev;
+      for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].cap == want && (pinned || v[i].dev == device)) {
+          *out = v[i].p; *cap = want;
+          v.erase(v.begin() + i);
+          return cudaSuccess;
+        }
+    }
+    *cap = want;
+    return pinned ? cudaMallocHost(out, want) : cudaMalloc(out, want);
+  }
+  void put(bool pinned, int device, void *p, size_t cap) {
+    if (!p) return;
+    if (cap <= ((size_t)32 << 20)) {
+      std::lock_guard<std::mutex> lk(mu);
+      std::vector<Blk> &v = pinned ? host : dev;
+      if (v.size() < 8) { v.push_back({p, cap, device}); return; }
+    }
+    if (pinned) cudaFreeHost(p); else cudaFree(p);
+  }
+};
+BlockCache g_blocks;
 
 /* bump allocation out of one cudaMalloc: sizes are summed first (256-byte aligned), then the pointers are handed out */
 struct Arena {
@@ -176,9 +237,9 @@ struct Arena {
   template <class T>
   T *at(size_t off) const { return reinterpret_cast<T *>(base + off); }
 };
-int arena_device(mci_handle_t *h, Arena &A, void **keep) {
-  CU(h, cudaMalloc(keep, std::max<size_t>(A.total, 256)));
-  CU(h, cudaMemset(*keep, 0, std::max<size_t>(A.total, 256)));
+int arena_device(mci_handle_t *h, Arena &A, void **keep, size_t *cap, bool zero = true) {
+  CU(h, g_blocks.get(false, h->device, std::max<size_t>(A.total, 256), keep, cap));
+  if (zero) CU(h, cudaMemsetAsync(*keep, 0, std::max<size_t>(A.total, 256), h->stream));
   A.base = static_cast<char *>(*keep);
   return MCI_OK;
 }
@@ -225,6 +286,11 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
     h->jit_failed = true;
     return nullptr;
   }
+  if (ks.size() != exprs.size() + 1) { /* one kernel per name expression + the library handle */
+    snprintf(h->err, sizeof h->err, "NVRTC build of %s returned %zu entries, expected %zu", name, ks.size(), exprs.size() + 1);
+    h->jit_failed = true;
+    return nullptr;
+  }
   if (h->jit_lib) jit_unload(h->jit_lib);
   h->jit_lib = ks.back();
   h->trace_kernel = kind <= 1 ? ks[1] : nullptr;
@@ -267,7 +333,7 @@ int plan(mci_handle_t *h) {
   if (p.solver == MCI_SOLVER_VEGAS) {
     bool pool_layout = P.nv == 1 && P.nleaf == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS &&
                        p.measure_kind == MCI_MEASURE_DEFAULT && P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT &&
-                       p.measurefreq == 1;
+                       p.measurefreq == 1 && P.wdim == 1;
     h->is_pool = false;
     if (pool_layout) {
       int nwarp = POOL_THREADS / 32;
@@ -397,6 +463,16 @@ int plan(mci_handle_t *h) {
     if ((double)std::min(W, h->threads) * ((double)h->steps * (1.0 + P.thermal_ratio) + (double)p.chain_burnin + 1.0) >= 4.0e9)
       return fail(h, MCI_ERR_UNSUPPORTED, "%llu steps per chain overflow the per-CTA counters: cut the block into more chains (walkers_per_block)",
                   (unsigned long long)h->steps);
+    /* a walker's position in its Philox stream is a 32-bit count of uniforms: a step draws at most 4 (update kind,
+     * variable, slot(s), acceptance) plus one per leaf it redraws — every slot of the largest integrand when an mcmc
+     * changeIntegrand creates them all, three per FermiK proposal.  Refuse chains that would wrap it and replay */
+    {
+      const double per_step = 4.0 + (p.solver == MCI_SOLVER_MCMC ? (double)P.n_draw + 3.0 : (double)(h->chain_rows - P.n_draw));
+      const double total_steps = (double)h->steps * (1.0 + (p.solver == MCI_SOLVER_MCMC ? P.thermal_ratio : 0.0)) + (double)p.chain_burnin + 1.0;
+      if (per_step * total_steps + 10000.0 * (double)P.n_draw >= 4294967296.0)
+        return fail(h, MCI_ERR_UNSUPPORTED, "%llu steps per chain exhaust the 2^32 uniforms of a walker's stream: cut the block into more chains (walkers_per_block)",
+                    (unsigned long long)h->steps);
+    }
     h->ctas_per_block = (W + h->threads - 1) / h->threads;
     h->grid = h->ctas_per_block * n_local;
     h->tiles_per_block = 0;
@@ -405,7 +481,7 @@ int plan(mci_handle_t *h) {
   if (h->n_hist_copies < 1) h->n_hist_copies = 1;
 
   /* (re)allocate per-launch partial buffers */
-  cudaFree(h->d_launch_arena);
+  g_blocks.put(false, h->device, h->d_launch_arena, h->launch_cap);
   h->d_launch_arena = nullptr;
   h->d_tile_obs = h->d_tile_cnt = h->d_cta_hist = h->d_cta_stats = nullptr;
   {
@@ -417,7 +493,9 @@ int plan(mci_handle_t *h) {
     else o_stats = L.reserve<double>((size_t)h->grid * stat_len);
     const size_t o_hist = L.reserve<double>((size_t)h->n_hist_copies * std::max(1, P.hist_len));
     int rc;
-    if ((rc = arena_device(h, L, &h->d_launch_arena))) return rc;
+    /* no memset: the fill kernels write every partial they own before the finalize kernel reads it, and the L2-RED
+     * histogram copies are zeroed per launch */
+    if ((rc = arena_device(h, L, &h->d_launch_arena, &h->launch_cap, false))) return rc;
     if (p.solver == MCI_SOLVER_VEGAS) { h->d_tile_obs = L.at<double>(o_obs); h->d_tile_cnt = L.at<double>(o_cnt); }
     else h->d_cta_stats = L.at<double>(o_stats);
     h->d_cta_hist = L.at<double>(o_hist);
@@ -448,8 +526,11 @@ void mci_destroy(mci_handle_t *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->jit_lib) jit_unload(h->jit_lib);
-  cudaFree(h->d_state_arena); cudaFree(h->d_launch_arena);
-  if (h->h_arena) cudaFreeHost(h->h_arena);
+  g_blocks.put(false, h->device, h->d_state_arena, h->state_cap);
+  g_blocks.put(false, h->device, h->d_launch_arena, h->launch_cap);
+  g_blocks.put(false, h->device, h->d_history, h->history_cap);
+  g_blocks.put(true, 0, h->h_arena, h->host_cap);
+  g_blocks.put(true, 0, h->h_history, h->h_history_cap);
   if (h->ev_iter0) cudaEventDestroy(h->ev_iter0);
   for (int i = 0; i < mci_handle_t::FILL_RING; ++i) {
     if (h->ev_fill0[i]) cudaEventDestroy(h->ev_fill0[i]);
@@ -478,6 +559,17 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
   if (p->integrand_id != MCI_F_USER && FI.ni != p->n_integrand)
     return fail(nullptr, MCI_ERR_INVALID, "integrand %d returns %d values but n_integrand = %d", p->integrand_id, FI.ni, p->n_integrand);
   if (p->n_leaf < FI.nleaf_min) return fail(nullptr, MCI_ERR_INVALID, "integrand %d needs %d leaf variables", p->integrand_id, FI.nleaf_min);
+  if (p->weight_kind != MCI_WEIGHT_REAL && p->weight_kind != MCI_WEIGHT_COMPLEX) return fail(nullptr, MCI_ERR_INVALID, "unknown weight_kind %d", p->weight_kind);
+  {
+    const bool cplx_id = p->integrand_id == MCI_F_COMPLEX1 || p->integrand_id == MCI_F_COMPLEX2;
+    if (p->integrand_id != MCI_F_USER && cplx_id != (p->weight_kind == MCI_WEIGHT_COMPLEX))
+      return fail(nullptr, MCI_ERR_INVALID, "integrand %d is %s: weight_kind must be %s", p->integrand_id, cplx_id ? "complex" : "real",
+                  cplx_id ? "MCI_WEIGHT_COMPLEX" : "MCI_WEIGHT_REAL");
+  }
+  if (p->mcmc_start_idx < 0 || p->mcmc_start_idx > p->n_integrand + 1)
+    return fail(nullptr, MCI_ERR_INVALID, "mcmc_start_idx = %d is not an integrand (1..%d)", p->mcmc_start_idx, p->n_integrand + 1);
+  if (p->n_userdata < 0 || p->n_userdata > MCI_MAX_USERDATA || (p->n_userdata > 0 && !p->userdata))
+    return fail(nullptr, MCI_ERR_INVALID, "userdata: %d doubles at %p (at most %d, and a non-NULL pointer)", p->n_userdata, (const void *)p->userdata, MCI_MAX_USERDATA);
   h->err[0] = 0;
   h->p = *p;
   h->device = p->device;
@@ -488,6 +580,8 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
   P.solver = p->solver; P.fid = p->integrand_id; P.measure_kind = p->measure_kind;
   P.ni = ni; P.nd = nd; P.nv = nv; P.nleaf = nleaf; P.measurefreq = p->measurefreq;
   P.thermal_ratio = p->thermal_ratio; P.seed = p->seed;
+  P.wdim = p->weight_kind == MCI_WEIGHT_COMPLEX ? 2 : 1;
+  P.start_idx = p->mcmc_start_idx > 0 ? p->mcmc_start_idx - 1 : 0;
   int first = 0;
   for (int v = 0; v < nv; ++v) { P.top_nleaf[v] = p->topvar_nleaf[v]; P.top_first[v] = first; first += p->topvar_nleaf[v]; }
 #define BAIL(code, ...) return fail(nullptr, code, __VA_ARGS__)
@@ -514,14 +608,18 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
     if (!same) P.need_pad = 1;
   }
   int ot = 0;
-  for (int i = 0; i < ni; ++i) { P.obs_len[i] = p->obs_len ? p->obs_len[i] : 1; P.obs_off[i] = ot; ot += P.obs_len[i]; }
-  if (ot > MCI_MAX_OBS) BAIL(MCI_ERR_UNSUPPORTED, "total observable length %d exceeds %d", ot, MCI_MAX_OBS);
+  /* device-side observable layout in doubles: a complex entry is (re, im) */
+  for (int i = 0; i < ni; ++i) {
+    if (p->obs_len && p->obs_len[i] < 1) BAIL(MCI_ERR_INVALID, "obs_len[%d] = %d", i, p->obs_len[i]);
+    P.obs_len[i] = (p->obs_len ? p->obs_len[i] : 1) * P.wdim; P.obs_off[i] = ot; ot += P.obs_len[i];
+  }
+  if (ot > MCI_MAX_OBS) BAIL(MCI_ERR_UNSUPPORTED, "total observable length %d doubles exceeds %d", ot, MCI_MAX_OBS);
   P.obs_total = ot; h->obs_total = ot;
   /* leaves */
   h->leaf_grid_off.assign(nleaf, 0); h->leaf_dist_off.assign(nleaf, 0); h->leaf_acc_off.assign(nleaf, 0);
   h->alpha.assign(nleaf, 2.0);
   int go = 0, dd = 0, da = 0, ho = 0, mo = 0;
-  bool has_fermik = false;
+  bool has_fermik = false, force_jit = false;
   for (int v = 0; v < nv; ++v)
     for (int k = 0; k < P.top_nleaf[v]; ++k) {
       const int l = P.top_first[v] + k;
@@ -578,10 +676,14 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
       for (int l = 0; l < FI.nleaf_min; ++l) if (P.maxdof[P.leaf[l].top] < 1) BAIL(MCI_ERR_INVALID, "integrand %d needs one slot of every variable", P.fid);
     if (p->measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
       const DevLeaf &E = P.leaf[nleaf - 1];
-      if (E.kind != MCI_LEAF_DISCRETE || P.obs_len[0] < E.nbins || P.maxdof[E.top] < 1)
+      if (E.kind != MCI_LEAF_DISCRETE || P.obs_len[0] < E.nbins * P.wdim || P.maxdof[E.top] < 1)
         BAIL(MCI_ERR_INVALID, "bin-by-discrete measure needs a Discrete last leaf and obs_len[0] >= its size");
-      if (p->solver != MCI_SOLVER_VEGAS && E.nbins > CHAIN_MAX_BINNED_OBS)
-        BAIL(MCI_ERR_UNSUPPORTED, "bin-by-discrete measure of the chain solvers keeps at most %d bins", CHAIN_MAX_BINNED_OBS);
+      /* the measure bins integrand 1 only (example/bubble.jl:81-84); the chain kernels keep its bins in per-thread
+       * accumulators, which for several integrands would silently drop bins: refuse instead */
+      if (p->solver != MCI_SOLVER_VEGAS && ni != 1)
+        BAIL(MCI_ERR_UNSUPPORTED, "bin-by-discrete measure under the chain solvers takes one integrand, not %d", ni);
+      /* more bins than the ahead-of-time chain kernels keep accumulators for: the NVRTC build sizes them to the problem */
+      if (p->solver != MCI_SOLVER_VEGAS && E.nbins > CHAIN_MAX_BINNED_OBS) force_jit = true;
     } else if (p->measure_kind == MCI_MEASURE_USER) {
       if (!p->user_source || !*p->user_source) BAIL(MCI_ERR_INVALID, "measure_kind = MCI_MEASURE_USER needs user_source defining mci_user_measure");
     } else if (p->measure_kind != MCI_MEASURE_DEFAULT) BAIL(MCI_ERR_INVALID, "unknown measure kind %d", p->measure_kind);
@@ -606,7 +708,9 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
     }
     P.nb_ptr[nd] = k;
   }
-  for (int i = 0; i < p->n_userdata && i < MCI_MAX_USERDATA; ++i) P.userdata[i] = p->userdata[i];
+  if (p->n_userdata < userdata_needed(P))
+    BAIL(MCI_ERR_INVALID, "integrand %d reads %d doubles of userdata, got %d", P.fid, userdata_needed(P), p->n_userdata);
+  for (int i = 0; i < p->n_userdata; ++i) P.userdata[i] = p->userdata[i];
   {
     const double pi = 3.14159265358979323846;
     if (P.fid == MCI_F_GAUSS_ND) P.fconst[0] = pow(2 * pi, -0.5 * P.dof[0]);
@@ -631,7 +735,9 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
    * what the JIT would build */
   h->jit_mode = p->jit;
   if (const char *e = getenv("MCIB200_JIT")) h->jit_mode = atoi(e) == 0 ? MCI_JIT_OFF : MCI_JIT_ON;
-  h->use_jit = p->integrand_id == MCI_F_USER || p->measure_kind == MCI_MEASURE_USER || h->jit_mode == MCI_JIT_ON ||
+  if (force_jit && h->jit_mode == MCI_JIT_OFF)
+    BAIL(MCI_ERR_UNSUPPORTED, "bin-by-discrete measure with more than %d bins under a chain solver needs the NVRTC build (jit != MCI_JIT_OFF)", CHAIN_MAX_BINNED_OBS);
+  h->use_jit = force_jit || p->integrand_id == MCI_F_USER || p->measure_kind == MCI_MEASURE_USER || h->jit_mode == MCI_JIT_ON ||
                (h->jit_mode == MCI_JIT_AUTO && (double)p->n_block * (double)p->neval_per_block >= 16777216.0);
 #undef BAIL
 
@@ -668,13 +774,14 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
   CUT(cudaEventCreate(&h->ev_iter0)); CUT(cudaEventCreate(&h->ev_iter1));
   /* (the ring of fill-kernel events is created on first use, launch_fill) */
   {
+    /* the whole fixed device state is laid out in one arena, built in a host image and uploaded with ONE copy */
     Arena D;
     const size_t o_grids = D.reserve<double>(go + 1), o_dist = D.reserve<double>(dd + 1), o_accum = D.reserve<double>(da + 1);
     const size_t o_rw = D.reserve<double>(nd), o_goal = D.reserve<double>(nd), o_alpha = D.reserve<double>(nleaf);
     const size_t o_gmaps = D.reserve<double>(mo + 2);
     const size_t o_lg = D.reserve<int>(nleaf), o_ld = D.reserve<int>(nleaf), o_la = D.reserve<int>(nleaf);
     const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(2), o_err = D.reserve<int>(1);
-    TRY(arena_device(h, D, &h->d_state_arena));
+    TRY(arena_device(h, D, &h->d_state_arena, &h->state_cap, false));
     h->d_grids = D.at<double>(o_grids); h->d_dist = D.at<double>(o_dist); h->d_accum = D.at<double>(o_accum);
     h->d_reweight = D.at<double>(o_rw); h->d_goal = D.at<double>(o_goal); h->d_alpha = D.at<double>(o_alpha);
     h->d_gmaps = D.at<double>(o_gmaps);
@@ -682,39 +789,40 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
     h->d_packed = D.at<double>(o_packed); h->d_flags = D.at<unsigned long long>(o_flags); h->d_err = D.at<int>(o_err);
     Arena H;
     const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(2), ho_err = H.reserve<int>(1);
-    CUT(cudaMallocHost(&h->h_arena, H.total));
+    const size_t ho_init = H.reserve<char>(D.total); /* staging image of the device state */
+    CUT(g_blocks.get(true, 0, H.total, &h->h_arena, &h->host_cap));
     H.base = static_cast<char *>(h->h_arena);
     h->h_packed = H.at<double>(ho_packed); h->h_flags = H.at<unsigned long long>(ho_flags); h->h_err = H.at<int>(ho_err);
-  }
-  memset(h->h_packed, 0, Y.len * sizeof(double));
-  h->h_flags[0] = h->h_flags[1] = 0; *h->h_err = 0;
-  CUT(cudaMemcpy(h->d_alpha, h->alpha.data(), nleaf * sizeof(double), cudaMemcpyHostToDevice));
-  CUT(cudaMemcpy(h->d_leaf_grid_off, h->leaf_grid_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
-  CUT(cudaMemcpy(h->d_leaf_dist_off, h->leaf_dist_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
-  CUT(cudaMemcpy(h->d_leaf_acc_off, h->leaf_acc_off.data(), nleaf * sizeof(int), cudaMemcpyHostToDevice));
-  /* initial maps as the reference constructors leave them (variable.jl:137, 305-315; configuration.jl:172-175) */
-  {
-    std::vector<double> g(go + 1), di(dd + 1), ac(da + 1), rw(nd);
+    memset(h->h_packed, 0, Y.len * sizeof(double));
+    h->h_flags[0] = h->h_flags[1] = 0; *h->h_err = 0;
+    char *img = H.at<char>(ho_init);
+    memset(img, 0, D.total);
+    auto at = [&](size_t off) { return img + off; };
+    memcpy(at(o_alpha), h->alpha.data(), nleaf * sizeof(double));
+    memcpy(at(o_lg), h->leaf_grid_off.data(), nleaf * sizeof(int));
+    memcpy(at(o_ld), h->leaf_dist_off.data(), nleaf * sizeof(int));
+    memcpy(at(o_la), h->leaf_acc_off.data(), nleaf * sizeof(int));
+    /* initial maps as the reference constructors leave them (variable.jl:137, 305-315; configuration.jl:172-175) */
+    double *g = reinterpret_cast<double *>(at(o_grids)), *di = reinterpret_cast<double *>(at(o_dist));
+    double *ac = reinterpret_cast<double *>(at(o_accum)), *rw = reinterpret_cast<double *>(at(o_rw));
     for (int l = 0; l < nleaf; ++l) {
       const mci_leaf_t &S = p->leaf[l];
       if (S.kind == MCI_LEAF_CONTINUOUS) {
         const int npts = S.nbins + 1;
-        double *q = g.data() + h->leaf_grid_off[l];
+        double *q = g + h->leaf_grid_off[l];
         for (int i = 0; i < npts; ++i) { double t = (double)i / (npts - 1); q[i] = (1 - t) * S.lower + t * S.upper; }
         q[0] = S.lower; q[npts - 1] = S.upper;
       } else if (S.kind == MCI_LEAF_DISCRETE) {
         const int n = S.nbins;
-        double *d = di.data() + h->leaf_dist_off[l], *a = ac.data() + h->leaf_acc_off[l];
+        double *d = di + h->leaf_dist_off[l], *a = ac + h->leaf_acc_off[l];
         for (int i = 0; i < n; ++i) d[i] = 1.0 / n;
         a[0] = 0.0;
         for (int i = 1; i <= n; ++i) { double s = 0.0; for (int k = 0; k < i; ++k) s += d[k]; a[i] = s; }
       }
     }
     for (int d = 0; d < nd; ++d) rw[d] = 1.0 / nd;
-    CUT(cudaMemcpy(h->d_grids, g.data(), (go + 1) * sizeof(double), cudaMemcpyHostToDevice));
-    CUT(cudaMemcpy(h->d_dist, di.data(), (dd + 1) * sizeof(double), cudaMemcpyHostToDevice));
-    CUT(cudaMemcpy(h->d_accum, ac.data(), (da + 1) * sizeof(double), cudaMemcpyHostToDevice));
-    CUT(cudaMemcpy(h->d_reweight, rw.data(), nd * sizeof(double), cudaMemcpyHostToDevice));
+    CUT(cudaMemcpyAsync(h->d_state_arena, img, D.total, cudaMemcpyHostToDevice, h->stream));
+    /* the staging image lives in the pinned block until the handle dies, so the copy needs no synchronisation here */
   }
   TRY(plan(h));
 #undef TRY
@@ -767,9 +875,9 @@ int mci_set_partition(mci_handle_t *h, int32_t rank, int32_t world) {
   return plan(h);
 }
 
-int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
-  if (!h) return MCI_ERR_INVALID;
-  CU(h, cudaSetDevice(h->device));
+/* enqueue one iteration on the handle's stream: [staged maps] -> fill -> finalize -> [all-reduce]; with_d2h also
+ * queues the copy of the statistics into the pinned mirrors that mci_fetch_iteration reads */
+static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   const mci_problem_t &p = h->p;
   const int n_local = p.n_block / h->world;
   CU(h, cudaEventRecord(h->ev_iter0, h->stream));
@@ -820,11 +928,51 @@ int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
     int rc = g_nccl.AllReduce(h->d_packed, h->d_packed, (size_t)h->Y.len, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream);
     if (rc != 0) return fail(h, MCI_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   }
-  CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  if (with_d2h) {
+    CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(h, cudaEventRecord(h->ev_iter1, h->stream));
   h->have_iteration = true;
   return MCI_OK;
+}
+
+/* raw packed statistics + flags of one iteration -> the caller's arrays, with the floors of clearStatistics! /
+ * addConfig! (configuration.jl:238-262, variable.jl:565: one per block config + the summed config) and the error
+ * checks of the reference's loop (mcmc start point, block normalisation) */
+static int unpack_iteration(mci_handle_t *h, const double *pk, const unsigned long long *flags, mci_iteration_out_t *out) {
+  const PackedLayout &Y = h->Y;
+  const int nb = Y.n_block;
+  const double B1 = (double)(nb + 1);
+  /* floors of clearStatistics! (configuration.jl:238-250, variable.jl:565): one per block config + the summed config */
+  if (out->block_obs) memcpy(out->block_obs, pk + Y.off_obs, sizeof(double) * nb * Y.obs_total);
+  if (out->block_norm) for (int b = 0; b < nb; ++b) out->block_norm[b] = 1.0e-10 + pk[Y.off_cnt + b];
+  if (out->hist) for (int i = 0; i < Y.hist_len; ++i) out->hist[i] = B1 * 1.0e-10 + pk[Y.off_hist + i];
+  if (out->visited) for (int i = 0; i < Y.nd; ++i) out->visited[i] = B1 * 1.0e-8 + pk[Y.off_visited + i];
+  if (out->propose) for (int i = 0; i < Y.pa_len; ++i) out->propose[i] = B1 * 1.0e-8 + pk[Y.off_propose + i];
+  if (out->accept) for (int i = 0; i < Y.pa_len; ++i) out->accept[i] = B1 * 1.0e-10 + pk[Y.off_accept + i];
+  if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
+  h->nonfinite = flags[0];
+  if (flags[1]) /* mcmc/montecarlo.jl:109-113 */
+    return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #%d integrand nonzero!", h->dp.start_idx + 1);
+  for (int b = 0; b < nb; ++b)
+    if (!(1.0e-10 + pk[Y.off_cnt + b] > 0.0)) /* main.jl:269-271 */
+      return fail(h, MCI_ERR_NUMERIC, "Block normalization = %g is not positively defined!", pk[Y.off_cnt + b]);
+  return MCI_OK;
+}
+
+/* a failed assert of train! on the device (variable.jl:212-213, common.jl:71,79) surfaces at the next host sync */
+static int check_train_error(mci_handle_t *h) {
+  if (!*h->h_err) return MCI_OK;
+  *h->h_err = 0;
+  cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+  return fail(h, MCI_ERR_NUMERIC, "train!: histogram should be all finite and positive");
+}
+
+int mci_launch_iteration(mci_handle_t *h, uint64_t iter) {
+  if (!h) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  return enqueue_iteration(h, iter, true);
 }
 
 int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out) {
@@ -838,28 +986,9 @@ int mci_fetch_iteration(mci_handle_t *h, mci_iteration_out_t *out) {
     cudaEventElapsedTime(&h->fill_ms, h->ev_fill0[slot], h->ev_fill1[slot]);
   }
   cudaEventElapsedTime(&h->iter_ms, h->ev_iter0, h->ev_iter1);
-  const PackedLayout &Y = h->Y;
-  const double *pk = h->h_packed;
-  const int nb = Y.n_block;
-  const double B1 = (double)(nb + 1);
-  /* floors of clearStatistics! (configuration.jl:238-250, variable.jl:565): one per block config + the summed config */
-  if (out->block_obs) memcpy(out->block_obs, pk + Y.off_obs, sizeof(double) * nb * Y.obs_total);
-  if (out->block_norm) for (int b = 0; b < nb; ++b) out->block_norm[b] = 1.0e-10 + pk[Y.off_cnt + b];
-  if (out->hist) for (int i = 0; i < Y.hist_len; ++i) out->hist[i] = B1 * 1.0e-10 + pk[Y.off_hist + i];
-  if (out->visited) for (int i = 0; i < Y.nd; ++i) out->visited[i] = B1 * 1.0e-8 + pk[Y.off_visited + i];
-  if (out->propose) for (int i = 0; i < Y.pa_len; ++i) out->propose[i] = B1 * 1.0e-8 + pk[Y.off_propose + i];
-  if (out->accept) for (int i = 0; i < Y.pa_len; ++i) out->accept[i] = B1 * 1.0e-10 + pk[Y.off_accept + i];
-  if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
-  if (h->h_flags[1]) return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #1 integrand nonzero!"); /* mcmc/montecarlo.jl:109-113 */
-  if (*h->h_err) {
-    *h->h_err = 0;
-    cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
-    return fail(h, MCI_ERR_NUMERIC, "train!: histogram should be all finite and positive"); /* variable.jl:212-213 */
-  }
-  for (int b = 0; b < nb; ++b)
-    if (!(1.0e-10 + pk[Y.off_cnt + b] > 0.0)) /* main.jl:269-271 */
-      return fail(h, MCI_ERR_NUMERIC, "Block normalization = %g is not positively defined!", pk[Y.off_cnt + b]);
-  return MCI_OK;
+  int rc = unpack_iteration(h, h->h_packed, h->h_flags, out);
+  if (rc) return rc;
+  return check_train_error(h);
 }
 
 int mci_run_iteration(mci_handle_t *h, uint64_t iter, mci_iteration_out_t *out) {
@@ -907,6 +1036,72 @@ int mci_reweight(mci_handle_t *h, double gamma, const double *goal) {
   h->launches++;
   if (goal) CU(h, cudaStreamSynchronize(h->stream));
   return MCI_OK;
+}
+
+int mci_run_iterations(mci_handle_t *h, uint64_t first_iter, int32_t niter, double gamma, const double *goal,
+                       int32_t do_reweight, int32_t do_refine, mci_iteration_out_t *out) {
+  if (!h || niter < 1) return MCI_ERR_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  const PackedLayout &Y = h->Y;
+  const size_t rec = (size_t)Y.len + 2; /* packed statistics + the two flag words, in 8-byte slots */
+  const size_t bytes = rec * (size_t)niter * sizeof(double);
+  if (h->history_cap < bytes) {
+    g_blocks.put(false, h->device, h->d_history, h->history_cap);
+    h->d_history = nullptr; h->history_cap = 0;
+    CU(h, g_blocks.get(false, h->device, bytes, &h->d_history, &h->history_cap));
+  }
+  if (h->h_history_cap < bytes) {
+    g_blocks.put(true, 0, h->h_history, h->h_history_cap);
+    h->h_history = nullptr; h->h_history_cap = 0;
+    CU(h, g_blocks.get(true, 0, bytes, &h->h_history, &h->h_history_cap));
+  }
+  double *dh = static_cast<double *>(h->d_history), *hh = static_cast<double *>(h->h_history);
+  const bool chain = h->p.solver != MCI_SOLVER_VEGAS;
+  if (goal && do_reweight && chain) CU(h, cudaMemcpyAsync(h->d_goal, goal, h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int nmax = 1;
+  for (int l = 0; l < h->nleaf; ++l) nmax = std::max(nmax, h->dp.leaf[l].nbins);
+  const size_t sm = (size_t)(3 * nmax + 2) * sizeof(double);
+  if (do_refine && h->dp.any_adapt && sm > 48 * 1024)
+    CU(h, cudaFuncSetAttribute((const void *)refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  for (int k = 0; k < niter; ++k) {
+    int rc = enqueue_iteration(h, first_iter + (uint64_t)k, false);
+    if (rc) return rc;
+    snapshot_kernel<<<std::max(1, std::min(8, (Y.len + 255) / 256)), 256, 0, h->stream>>>(h->d_packed, Y.len, h->d_flags, dh + rec * k);
+    h->launches++;
+    if (do_reweight && chain) { /* main.jl:183 */
+      reweight_kernel<<<1, 32, 0, h->stream>>>(Y, h->d_packed, gamma, goal ? h->d_goal : nullptr, h->d_reweight);
+      h->launches++;
+    }
+    if (do_refine && h->dp.any_adapt) { /* main.jl:193-198 */
+      refine_kernel<<<h->nleaf, 256, sm, h->stream>>>(h->dp, Y, h->d_packed, h->d_alpha, h->d_leaf_grid_off, h->d_leaf_dist_off,
+                                                      h->d_leaf_acc_off, h->d_grids, h->d_dist, h->d_accum, h->d_err);
+      h->launches++;
+      rc = enqueue_build_maps(h);
+      if (rc) return rc;
+    }
+    CU(h, cudaGetLastError());
+  }
+  CU(h, cudaMemcpyAsync(hh, dh, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  /* leave the handle as after a fetch of the last iteration */
+  memcpy(h->h_packed, hh + rec * (niter - 1), Y.len * sizeof(double));
+  memcpy(h->h_flags, hh + rec * (niter - 1) + Y.len, 2 * sizeof(unsigned long long));
+  {
+    const int slot = (int)((h->n_iterations - 1) % mci_handle_t::FILL_RING);
+    cudaEventElapsedTime(&h->fill_ms, h->ev_fill0[slot], h->ev_fill1[slot]);
+  }
+  uint64_t bad = 0;
+  mci_iteration_out_t none;
+  memset(&none, 0, sizeof none);
+  for (int k = 0; k < niter; ++k) {
+    const double *pk = hh + rec * k;
+    const int rc = unpack_iteration(h, pk, reinterpret_cast<const unsigned long long *>(pk + Y.len), out ? &out[k] : &none);
+    if (rc) return rc;
+    bad += h->nonfinite;
+  }
+  h->nonfinite = bad; /* over the whole call */
+  return check_train_error(h);
 }
 
 int mci_set_async(mci_handle_t *h, int32_t on) {
@@ -964,13 +1159,14 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
   const void *k = h->use_jit ? h->trace_kernel : lookup_vegas_trace(h->dp.fid);
   if (!k) return fail(h, MCI_ERR_UNSUPPORTED, "no trace kernel for integrand %d", h->dp.fid);
   if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
-  const int nd = h->dp.n_draw, ni = h->ni;
-  double *dx = nullptr, *dj = nullptr, *dw = nullptr;
-  int *db = nullptr;
-  CU(h, cudaMalloc((void **)&dx, sizeof(double) * (size_t)count * nd));
-  CU(h, cudaMalloc((void **)&db, sizeof(int) * (size_t)count * nd));
-  CU(h, cudaMalloc((void **)&dj, sizeof(double) * (size_t)count));
-  CU(h, cudaMalloc((void **)&dw, sizeof(double) * (size_t)count * ni));
+  const int nd = h->dp.n_draw, ni = h->ni * h->dp.wdim;
+  /* one allocation for the four outputs, released on every path */
+  const size_t n_x = (size_t)count * nd, n_w = (size_t)count * ni; /* ni values per sample: (re, im) pairs when complex */
+  const size_t bytes = sizeof(double) * (n_x + (size_t)count + n_w) + sizeof(int) * n_x;
+  char *buf = nullptr;
+  CU(h, cudaMalloc((void **)&buf, bytes));
+  double *dx = reinterpret_cast<double *>(buf), *dj = dx + n_x, *dw = dj + count;
+  int *db = reinterpret_cast<int *>(dw + n_w);
   const double *gm = h->d_gmaps;
   uint32_t blk = (uint32_t)block;
   void *args[] = {&h->dp, &gm, &iter, &blk, &first, &count, &dx, &db, &dj, &dw};
@@ -981,7 +1177,7 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
   if (e == cudaSuccess && bins) e = cudaMemcpy(bins, db, sizeof(int) * (size_t)count * nd, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && jac) e = cudaMemcpy(jac, dj, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && weights) e = cudaMemcpy(weights, dw, sizeof(double) * (size_t)count * ni, cudaMemcpyDeviceToHost);
-  cudaFree(dx); cudaFree(db); cudaFree(dj); cudaFree(dw);
+  cudaFree(buf);
   if (e != cudaSuccess) return fail(h, MCI_ERR_CUDA, "mci_trace_samples: %s", cudaGetErrorString(e));
   return MCI_OK;
 }
@@ -1002,7 +1198,7 @@ int mci_jit_check(const mci_problem_t *p, char *log, int32_t log_cap) {
   std::vector<std::string> exprs;
   if (p->solver == MCI_SOLVER_VEGAS) {
     const bool pool = P.nv == 1 && P.nleaf == 1 && P.leaf[0].kind == MCI_LEAF_CONTINUOUS && p->measure_kind == MCI_MEASURE_DEFAULT &&
-                      P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT && p->measurefreq == 1;
+                      P.obs_total == P.ni && P.maxdof[0] <= MCI_MAX_SLOT && p->measurefreq == 1 && P.wdim == 1;
     if (pool) {
       const bool striped = P.any_adapt && P.maxdof[0] <= 20;
       snprintf(name, sizeof name, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0],
@@ -1020,14 +1216,18 @@ int mci_jit_check(const mci_problem_t *p, char *log, int32_t log_cap) {
   }
   std::vector<const void *> ks;
   std::string err;
-  setenv("MCIB200_JIT_COMPILE_ONLY", "1", 1);
-  rc = jit_compile(P, p->user_source, exprs, ks, err);
-  unsetenv("MCIB200_JIT_COMPILE_ONLY");
+  rc = jit_compile(P, p->user_source, exprs, ks, err, std::string(), /*compile_only=*/true);
   delete h;
   if (rc != 0) {
     if (log && log_cap > 0) snprintf(log, log_cap, "%s", err.c_str());
     return MCI_ERR_UNSUPPORTED;
   }
+  return MCI_OK;
+}
+
+int mci_nonfinite_count(const mci_handle_t *h, uint64_t *n) {
+  if (!h || !n) return MCI_ERR_INVALID;
+  *n = h->nonfinite;
   return MCI_OK;
 }
 

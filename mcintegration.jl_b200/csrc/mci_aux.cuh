@@ -130,10 +130,31 @@ __global__ void finalize_chain_kernel(PackedLayout Y, const double *__restrict__
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* train! on the device.  One CTA per leaf.  Everything whose rounding depends on the order of   */
-/* a running sum is done by thread 0 in the reference's order; the element-wise parts (smooth,   */
-/* rescale's log/pow) run across the CTA.  err[0] |= 1 when the reference would assert.          */
+/* train! on the device.  One CTA per leaf.                                                      */
+/* Continuous leaves: the three running sums of variable.jl:206-239 (normalisation of rescale,   */
+/* the mean increment weight, the regrid walk) are fixed-shape parallel reductions / a prefix    */
+/* scan, and every new grid point is then computed independently from the prefix sums.  The      */
+/* reference's own `sum` is pairwise and SIMD-reassociated, so no summation order is "the"       */
+/* reference order; against a strictly sequential evaluation (the oracle) the new grid agrees   */
+/* to ~1e-13 of an increment (asserted at rtol 1e-9, tests/test_gpu_parity.py).  A sequential   */
+/* single-thread version of the same step took 0.25 ms per 999-bin leaf (division latency in the */
+/* regrid loop): the whole cost of a small job.                                                   */
+/* Discrete leaves (a handful of bins) keep the reference's order exactly.                       */
+/* err[0] |= 1 when the reference would assert.                                                  */
 /* ------------------------------------------------------------------------------------------ */
+
+/* sum over the CTA in a fixed shape: xor-shuffle tree per warp, then the warp totals the same way; all threads get it */
+__device__ __forceinline__ double cta_allsum(double v, double *sred32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sred32[warp] = v;
+  __syncthreads();
+  double t = lane < nwarp ? sred32[lane] : 0.0;
+  t = warp_sum(t);
+  return t;
+}
+
 __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout Y, const double *__restrict__ packed,
                               const double *__restrict__ alpha, const int *__restrict__ leaf_grid_off,
                               const int *__restrict__ leaf_dist_off, const int *__restrict__ leaf_acc_off,
@@ -144,10 +165,11 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
   const DevLeaf &L = P.leaf[l];
   if (!L.adapt) return;
   const int n = L.nbins;
-  double *hist = sh;          /* n   */
+  double *hist = sh;          /* n   (later: the prefix sums of the rescaled weights) */
   double *avg = sh + n;       /* n   */
   double *og = sh + 2 * n;    /* n+1 old grid */
   __shared__ double s_sum;
+  __shared__ double s_red[32];
   __shared__ int s_bad;
   const double floor_ = __dmul_rn((double)(Y.n_block + 1), 1.0e-10); /* (B+1) x clearStatistics! floor, variable.jl:565 */
   if (threadIdx.x == 0) s_bad = 0;
@@ -174,13 +196,9 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
     __syncthreads();
     /* rescale(avg, alpha): common.jl:67-83 */
     if (n > 1) {
-      if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s = __dadd_rn(s, avg[i]);
-        s_sum = s;
-      }
-      __syncthreads();
-      const double s = s_sum;
+      double part = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) part = __dadd_rn(part, avg[i]);
+      const double s = cta_allsum(part, s_red);
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (!(avg[i] > 0.0)) s_bad = 1;
         double dd = __ddiv_rn(avg[i], s);
@@ -190,21 +208,50 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
       }
       __syncthreads();
     }
-    /* regrid: variable.jl:218-236 */
-    if (threadIdx.x == 0 && !s_bad) {
-      double sum = 0.0;
-      for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, avg[i]);
-      const double f_ninc = __ddiv_rn(sum, (double)n);
-      int j = 0;
-      double acc_f = 0.0;
-      for (int i = 2; i <= n; ++i) {
-        while (acc_f < f_ninc) {
-          j += 1;
-          if (j > n) { j = n; break; }
-          acc_f = __dadd_rn(acc_f, avg[j - 1]);
+    /* regrid: variable.jl:218-236.  The walk `while acc < f: j += 1; acc += avg[j]` ... `acc -= f` leaves, for new
+     * grid point i, j = the first increment whose prefix sum S_j reaches (i - 1) f and acc = S_j - (i - 1) f: with the
+     * prefix sums in shared memory every point is independent */
+    {
+      const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (T + 31) >> 5;
+      const int chunk = (n + T - 1) / T;
+      const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+      double local = 0.0;
+      for (int j = lo; j < hi; ++j) local = __dadd_rn(local, avg[j]);
+      double incl = local; /* inclusive scan of the chunk totals: within the warp, then over the warps */
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = __dadd_rn(incl, up);
+      }
+      __syncthreads();
+      if (lane == 31) s_red[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        double t = lane < nwarp ? s_red[lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, t, o);
+          if (lane >= o) t = __dadd_rn(t, up);
         }
-        acc_f = __dsub_rn(acc_f, f_ninc);
-        g[i - 1] = __dsub_rn(og[j], __dmul_rn(__ddiv_rn(acc_f, avg[j - 1]), __dsub_rn(og[j], og[j - 1])));
+        if (lane < nwarp) s_red[lane] = t;
+      }
+      __syncthreads();
+      double run = __dadd_rn(warp > 0 ? s_red[warp - 1] : 0.0, __dsub_rn(incl, local));
+      double *S = hist; /* the raw histogram is no longer needed */
+      for (int j = lo; j < hi; ++j) { run = __dadd_rn(run, avg[j]); S[j] = run; }
+      __syncthreads();
+      if (!s_bad) {
+        const double f_ninc = __ddiv_rn(S[n - 1], (double)n);
+        for (int i = 2 + tid; i <= n; i += T) {
+          const double target = __dmul_rn((double)(i - 1), f_ninc);
+          int jl = 0, jh = n - 1; /* first j with S[j] >= target (clamped to the last increment) */
+          while (jl < jh) {
+            const int jm = (jl + jh) >> 1;
+            if (S[jm] >= target) jh = jm; else jl = jm + 1;
+          }
+          const double acc_f = __dsub_rn(S[jl], target);
+          g[i - 1] = __dsub_rn(og[jl + 1], __dmul_rn(__ddiv_rn(acc_f, avg[jl]), __dsub_rn(og[jl + 1], og[jl])));
+        }
       }
     }
   } else {
@@ -248,6 +295,13 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_bad) atomicOr(err, 1);
+}
+
+/* mci_run_iterations: keep this iteration's packed statistics and flags in the per-call history (one launch) */
+__global__ void snapshot_kernel(const double *__restrict__ packed, int len, const unsigned long long *__restrict__ flags,
+                                double *__restrict__ rec) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) rec[i] = packed[i];
+  if (blockIdx.x == 0 && threadIdx.x < 2) reinterpret_cast<unsigned long long *>(rec + len)[threadIdx.x] = flags[threadIdx.x];
 }
 
 /* doReweight!: main.jl:322-346; goal may be NULL */

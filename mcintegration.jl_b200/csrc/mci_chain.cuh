@@ -427,12 +427,12 @@ constexpr int MCMC_DRAWS_AHEAD = 6;
 constexpr int CHAIN_MAX_BINNED_OBS = 8;
 /* per-thread observable accumulators: one per integrand (default measure), CHAIN_MAX_BINNED_OBS for the single binned
  * integrand, the whole flattened observable for a user measure (JIT builds only: its length is a compile-time constant) */
-template <int NI>
+template <int NI, int WD>
 struct ChainNobs {
-#ifdef MCI_JIT
-  static constexpr int value = JitProblem::measure_kind == MCI_MEASURE_USER ? JitProblem::obs_total : (NI > 1 ? NI : CHAIN_MAX_BINNED_OBS);
+#ifdef MCI_JIT /* a JIT program knows the observable layout: exactly as many accumulators as the measure writes */
+  static constexpr int value = JitProblem::measure_kind != MCI_MEASURE_DEFAULT ? JitProblem::obs_total : NI * WD;
 #else
-  static constexpr int value = NI > 1 ? NI : CHAIN_MAX_BINNED_OBS;
+  static constexpr int value = (NI > 1 ? NI : CHAIN_MAX_BINNED_OBS) * WD;
 #endif
 };
 #define PA_IDX(P, u, i, j) (((u) * (P).nd + (i)) * (P).pa_dim + (j))
@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   MCI_VIEW(P, Pp);
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
+  constexpr int WD = IntegrandWD<FID>::value; /* doubles per integrand value: 2 = complex (re, im) */
   extern __shared__ __align__(16) double smem[];
   Walker<true> W;
   const int pa_len = P.pa_len_();
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
 
   /* per-thread statistics.  Default measure: one accumulator per integrand; bin-by-Discrete: one per bin, selected
    * with a short compare chain so that the accumulators stay in registers */
-  constexpr int NOBS = ChainNobs<NI>::value;
+  constexpr int NOBS = ChainNobs<NI, WD>::value;
   double obs[NOBS];
 #pragma unroll
   for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   double normalization = 0.0;
   unsigned long long neval = 0, bad = 0;
 
-  double weights[NI], nweights[NI], pad[NI + 1], npad[NI + 1];
+  double weights[NI * WD], nweights[NI * WD], pad[NI + 1], npad[NI + 1];
   /* montecarlo.jl:151-166 */
   for (int v = 0; v < P.nv; ++v) var_initialize(C, W, v);
   F::template eval<0>(X, P, nweights);
@@ -500,10 +501,9 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   for (int i = 0; i <= N; ++i) pad[i] = P.need_pad || i == N ? padding_probability(P, W, i) : 1.0;
   double prob_cur = __dmul_rn(rw[N], pad[N]);
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    weights[i] = nweights[i];
-    prob_cur = __dadd_rn(prob_cur, __dmul_rn(__dmul_rn(fabs(nweights[i]), rw[i]), pad[i]));
-  }
+  for (int i = 0; i < N * WD; ++i) weights[i] = nweights[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) prob_cur = __dadd_rn(prob_cur, __dmul_rn(__dmul_rn(wabs<WD>(nweights, i), rw[i]), pad[i]));
   const double meas_from = (double)A.steps / 100; /* ne >= neval/100 (montecarlo.jl:213) */
 
   for (long long ne = 1 - A.burnin; ne <= (long long)A.steps; ++ne) { /* ne <= 0: burn-in, no statistics */
@@ -515,23 +515,24 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
         const double prop = var_shift(C, W, vi, pos);
         if (prop > 4.9406564584124654e-324) {
           F::template eval<0>(X, P, nweights);
-          neval++;
+          const bool counted = ne >= 1; /* burn-in steps (ne <= 0) touch no statistic, counters included */
+          if (counted) neval++;
           bool finite = true;
 #pragma unroll
-          for (int i = 0; i < N; ++i) finite = finite && isfinite(nweights[i]);
-          if (!finite) bad++;
+          for (int i = 0; i < N * WD; ++i) finite = finite && isfinite(nweights[i]);
+          if (!finite && counted) bad++;
 #pragma unroll
           for (int i = 0; i <= N; ++i) npad[i] = P.need_pad || i == N ? padding_probability(P, W, i) : 1.0;
           double prob_new = __dmul_rn(rw[N], npad[N]);
 #pragma unroll
           for (int i = 0; i < N; ++i)
-            prob_new = __dadd_rn(prob_new, __dmul_rn(__dmul_rn(fabs(nweights[i]), rw[i]), npad[i]));
+            prob_new = __dadd_rn(prob_new, __dmul_rn(__dmul_rn(wabs<WD>(nweights, i), rw[i]), npad[i]));
           const double R = __ddiv_rn(__dmul_rn(prop, prob_new), prob_cur);
-          atomicAdd(&s_prop[PA_IDX(P, 1, 0, vi)], 1u);
+          if (counted) atomicAdd(&s_prop[PA_IDX(P, 1, 0, vi)], 1u);
           if (C.rng.rand(K) < R) {
-            atomicAdd(&s_acc[PA_IDX(P, 1, 0, vi)], 1u);
+            if (counted) atomicAdd(&s_acc[PA_IDX(P, 1, 0, vi)], 1u);
 #pragma unroll
-            for (int i = 0; i < N; ++i) weights[i] = nweights[i];
+            for (int i = 0; i < N * WD; ++i) weights[i] = nweights[i];
 #pragma unroll
             for (int i = 0; i <= N; ++i) pad[i] = npad[i];
             prob_cur = prob_new;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
       double wf2[NI];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const double aw = fabs(weights[i]);
+        const double aw = wabs<WD>(weights, i);
         const double f2 = __ddiv_rn(__dmul_rn(aw, aw), probability(P, W, i));
         wf2[i] = __ddiv_rn(__dmul_rn(f2, pad[i]), prob_cur);
       }
@@ -569,17 +570,24 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
     __syncwarp();
     /* measurement: montecarlo.jl:213-232 */
     if (active && ne >= 1 && (P.measurefreq == 1 || ((uint64_t)ne % (uint64_t)P.measurefreq) == 0) && (double)ne >= meas_from) {
-      double relw_all[NI];
+      double relw_all[NI * WD];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        visited[i] += __ddiv_rn(fabs(__dmul_rn(__dmul_rn(weights[i], pad[i]), rw[i])), prob_cur);
-        const double relw = __ddiv_rn(__dmul_rn(weights[i], pad[i]), prob_cur);
-        relw_all[i] = relw;
-        if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[i < NOBS ? i : 0] += relw;
-        else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE && i == 0) {
-          const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
+        /* abs(weights[i] * pad * reweight) / probability: a complex value is scaled component by component first */
+        double wpr[WD];
 #pragma unroll
-          for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
+        for (int c = 0; c < WD; ++c) wpr[c] = __dmul_rn(__dmul_rn(weights[WD * i + c], pad[i]), rw[i]);
+        visited[i] += __ddiv_rn(wabs<WD>(wpr, 0), prob_cur);
+#pragma unroll
+        for (int c = 0; c < WD; ++c) {
+          const double relw = __ddiv_rn(__dmul_rn(weights[WD * i + c], pad[i]), prob_cur);
+          relw_all[WD * i + c] = relw;
+          if (P.measure_kind == MCI_MEASURE_DEFAULT) obs[WD * i + c < NOBS ? WD * i + c : 0] += relw;
+          else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE && i == 0) {
+            const int b = WD * W.gidx[P.leaf[P.nleaf - 1].base * W.T] + c;
+#pragma unroll
+            for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
+          }
         }
       }
       if (P.measure_kind == MCI_MEASURE_USER) UserMeasureT<0>::call(X, obs, relw_all, P.userdata);
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   __syncthreads();
   if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+    for (int i = 0; i < N * WD; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i / WD] + i % WD] = t; }
   } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
 #pragma unroll
     for (int o = 0; o < NOBS; ++o)
@@ -621,20 +629,24 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
 /* ------------------------------------------------------------------------------------------ */
 /* weight of integrand `idx` at the walker's point.  Integrands whose components are independent pay for one. */
 template <int FID, class XA>
-__device__ __forceinline__ double eval_one(const Problem &P, const XA &X, int idx) {
+__device__ __forceinline__ void eval_one(const Problem &P, const XA &X, int idx, double *out) {
+  constexpr int WD = IntegrandWD<FID>::value;
   if constexpr (FID == MCI_F_PRODUCT_4) {
     const int d = P.dof[0];
     const double a = P.userdata[idx];
     double p = 1.0;
     for (int i = 0; i < d; ++i) p *= (1 + a * (X(0, i + 1) - 0.5));
-    return p;
+    out[0] = p;
   } else {
-    double w[Integrand<FID>::NI];
+    double w[Integrand<FID>::NI * WD];
     Integrand<FID>::template eval<0>(X, P, w);
-    double r = w[0];
 #pragma unroll
-    for (int i = 1; i < Integrand<FID>::NI; ++i) if (i == idx) r = w[i];
-    return r;
+    for (int c = 0; c < WD; ++c) {
+      double r = w[c];
+#pragma unroll
+      for (int i = 1; i < Integrand<FID>::NI; ++i) if (i == idx) r = w[WD * i + c];
+      out[c] = r;
+    }
   }
 }
 
@@ -711,6 +723,7 @@ template <int FID>
 __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_constant__ DevProblem Pp, const ChainArgs A) {
   MCI_VIEW(P, Pp);
   constexpr int NI = Integrand<FID>::NI;
+  constexpr int WD = IntegrandWD<FID>::value; /* doubles per integrand value: 2 = complex (re, im) */
   extern __shared__ __align__(16) double smem[];
   const int pa_len = P.pa_len_();
   Walker<false> W;
@@ -739,7 +752,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
 #pragma unroll
   for (int i = 0; i <= N; ++i) rw[i] = A.reweight[i];
 
-  constexpr int NOBS = ChainNobs<NI>::value;
+  constexpr int NOBS = ChainNobs<NI, WD>::value;
   double obs[NOBS];
 #pragma unroll
   for (int o = 0; o < NOBS; ++o) obs[o] = 0.0;
@@ -749,14 +762,17 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   double normalization = 0.0;
   unsigned long long neval = 0, bad = 0;
 
-  /* start point: montecarlo.jl:99-113, initialize! :190-205 */
-  int curr = 0;
-  double weight = 0.0, prob_cur = 1.0;
+  /* start point: montecarlo.jl:99-113, initialize! :190-205; `idx` = the integrand to start with (:76) */
+  int curr = P.start_idx;
+  double weight[WD], nwgt[WD], prob_cur = 1.0;
+#pragma unroll
+  for (int c = 0; c < WD; ++c) weight[c] = nwgt[c] = 0.0;
   if (active) {
     for (int t = 0; t < 10000; ++t) {
       for (int v = 0; v < P.nv; ++v) var_initialize(C, W, v);
-      weight = eval_one<FID>(P, X, curr);
-      prob_cur = __dmul_rn(fabs(weight), rw[curr]);
+      if (curr == N) { prob_cur = rw[N]; break; } /* the normalisation integrand: weight 1 * reweight (:196-198) */
+      eval_one<FID>(P, X, curr, weight);
+      prob_cur = __dmul_rn(wabs<WD>(weight, 0), rw[curr]);
       if (prob_cur > TINY) break;
     }
     if (prob_cur == 0.0) atomicAdd(A.flags + 1, 1ull);
@@ -841,21 +857,28 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
      * not reconverge the lanes by itself after the divergent proposal code: without the barrier the warp drifts apart
      * for good (ncu: 4 active threads per instruction) ---- */
     __syncwarp();
-    double nwgt = 0.0;
-    if (kind != 0 && tgt != N) nwgt = eval_one<FID>(P, X, tgt);
+#pragma unroll
+    for (int c = 0; c < WD; ++c) nwgt[c] = 0.0;
+    if (kind != 0 && tgt != N) eval_one<FID>(P, X, tgt, nwgt);
     __syncwarp();
     /* ---- accept / rollback (divergent, cheap) ---- */
     if (kind != 0) {
-      neval++;
-      if (!isfinite(nwgt)) bad++;
-      const double nprob = (tgt == N) ? rw[N] : __dmul_rn(fabs(nwgt), rw[tgt]);
+      const bool counted = it >= 1; /* burn-in steps (it <= 0) touch no statistic, counters included */
+      if (counted) neval++;
+      bool finite = true;
+#pragma unroll
+      for (int c = 0; c < WD; ++c) finite = finite && isfinite(nwgt[c]);
+      if (!finite && counted) bad++;
+      const double nprob = (tgt == N) ? rw[N] : __dmul_rn(wabs<WD>(nwgt, 0), rw[tgt]);
       const double R = __ddiv_rn(__dmul_rn(prop, nprob), prob_cur);
       const int j = kind == 1 ? tgt : vi;
       const int pa = PA_IDX(P, kind - 1, curr, j);
-      atomicAdd(&s_prop[pa], 1u);
+      if (counted) atomicAdd(&s_prop[pa], 1u);
       if (C.rng.rand(K) < R) {
-        atomicAdd(&s_acc[pa], 1u);
-        curr = tgt; weight = nwgt; prob_cur = nprob;
+        if (counted) atomicAdd(&s_acc[pa], 1u);
+        curr = tgt; prob_cur = nprob;
+#pragma unroll
+        for (int c = 0; c < WD; ++c) weight[c] = nwgt[c];
       } else if (kind == 2) {
         var_shift_rollback(P, W, vi, p1);
       } else if (kind == 3) {
@@ -881,18 +904,20 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
                 }
               }
           }
-        const double relw = __ddiv_rn(weight, prob_cur);
+        double relw[WD]; /* relativeWeight = state.weight / state.probability (:163), component by component */
+#pragma unroll
+        for (int c = 0; c < WD; ++c) relw[c] = __ddiv_rn(weight[c], prob_cur);
         if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) obs[i < NOBS ? i : 0] += (i == curr) ? relw : 0.0;
+          for (int i = 0; i < N * WD; ++i) obs[i < NOBS ? i : 0] += (i / WD == curr) ? relw[i % WD] : 0.0;
         } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
-          const int b = W.gidx[P.leaf[P.nleaf - 1].base * W.T];
+          const int b = WD * W.gidx[P.leaf[P.nleaf - 1].base * W.T];
 #pragma unroll
-          for (int o = 0; o < NOBS; ++o) obs[o] += (o == b) ? relw : 0.0;
+          for (int o = 0; o < NOBS; ++o) obs[o] += (o / WD * WD == b) ? relw[o % WD] : 0.0;
         } else { /* measure(idx, x, obs, relw, config): a measure is linear in relw, so pass zero for the other integrands */
-          double relw_all[NI];
+          double relw_all[NI * WD];
 #pragma unroll
-          for (int i = 0; i < N; ++i) relw_all[i] = (i == curr) ? relw : 0.0;
+          for (int i = 0; i < N * WD; ++i) relw_all[i] = (i / WD == curr) ? relw[i % WD] : 0.0;
           UserMeasureT<0>::call(X, obs, relw_all, P.userdata);
         }
       }
@@ -906,7 +931,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   __syncthreads();
   if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i]] = t; }
+    for (int i = 0; i < N * WD; ++i) { double t = cta_sum(obs[i < NOBS ? i : 0], S.sred); if (tid == 0) out[P.obs_off[i / WD] + i % WD] = t; }
   } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
 #pragma unroll
     for (int o = 0; o < NOBS; ++o)

@@ -67,6 +67,8 @@ struct DevProblem {
   int any_adapt;
   int map_doubles; /* doubles of shared memory holding all maps                                     */
   int n_tslot;     /* sum of maxdof over top-level variables                                        */
+  int wdim;        /* doubles per integrand value / observable entry: 1 real, 2 complex (re, im)    */
+  int start_idx;   /* mcmc: integrand every chain starts in, 0-based (mcmc/montecarlo.jl:76)        */
   int top_nleaf[MCI_MAX_TOPVAR], top_first[MCI_MAX_TOPVAR], top_base[MCI_MAX_TOPVAR], maxdof[MCI_MAX_TOPVAR];
   int top_tslot[MCI_MAX_TOPVAR]; /* first top-level slot index of the variable                      */
   int top_skip[MCI_MAX_TOPVAR];  /* single Discrete leaf with one value: updates skip it            */
@@ -111,6 +113,15 @@ struct UserMeasureT {
   template <class XA>
   __device__ __forceinline__ static void call(const XA &, double *, const double *, const double *) {}
 };
+
+/* |w_i| of integrand i: abs of a real value, hypot(re, im) of a complex one (Julia's abs(::Complex)) — what the
+ * reference takes wherever it writes abs(weights[i]) (vegas/montecarlo.jl:172, vegas_mc/montecarlo.jl:159,200,
+ * vegas_mc/updates.jl:86, mcmc/updates.jl:40,95,130) */
+template <int WD>
+__device__ __forceinline__ double wabs(const double *w, int i) {
+  if constexpr (WD == 1) return fabs(w[i]);
+  else return hypot(w[2 * i], w[2 * i + 1]);
+}
 
 /* ---------------------------------------------------------------------------------------- */
 /* Philox4x32-10 (Salmon et al. 2011).  Stream layout (DESIGN.md "RNG"):                     */

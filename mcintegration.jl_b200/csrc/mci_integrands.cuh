@@ -86,6 +86,19 @@ __device__ __forceinline__ double green(double tau, double w, double beta) {
 template <int FID>
 struct Integrand;
 
+/* doubles per integrand value: 1 for a real integrand, 2 (re, im) for a complex one (Configuration(type=ComplexF64),
+ * configuration.jl:108).  A JIT program answers for the user integrand from its compile-time problem tables. */
+template <int FID>
+struct IntegrandWD {
+#ifdef MCI_JIT
+  static constexpr int value = FID == MCI_F_USER ? JitProblem::wdim : 1;
+#else
+  static constexpr int value = 1;
+#endif
+};
+template <> struct IntegrandWD<MCI_F_COMPLEX1> { static constexpr int value = 2; };
+template <> struct IntegrandWD<MCI_F_COMPLEX2> { static constexpr int value = 2; };
+
 /* BASELINE C2: (2pi)^(-d/2) exp(-|x|^2/2); fconst[0] = (2pi)^(-d/2) */
 template <>
 struct Integrand<MCI_F_GAUSS_ND> {
@@ -304,11 +317,34 @@ struct Integrand<MCI_F_X2_PLUS_Y2> {
   }
 };
 
+/* test/montecarlo.jl:166-170 (TestComplex1): f = x + i x^2 */
+template <>
+struct Integrand<MCI_F_COMPLEX1> {
+  static constexpr int NI = 1;
+  template <int MAXD, class XA, bool EXACT = false>
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
+    const double x = X(0, 1);
+    w[0] = x; w[1] = __dmul_rn(x, x);
+  }
+};
+
+/* test/montecarlo.jl:172-198 (TestComplex2): (x + 0i, i x^2) */
+template <>
+struct Integrand<MCI_F_COMPLEX2> {
+  static constexpr int NI = 2;
+  template <int MAXD, class XA, bool EXACT = false>
+  __device__ __forceinline__ static void eval(const XA &X, const Problem &P, double *w) {
+    const double x = X(0, 1);
+    w[0] = x; w[1] = 0.0; w[2] = 0.0; w[3] = __dmul_rn(x, x);
+  }
+};
+
 /* run-time dispatch for the generic (non-unrolled) kernels */
 #define MCI_FOR_EACH_FID(M)                                                                                         \
   M(MCI_F_GAUSS_ND) M(MCI_F_LOG_OVER_SQRT) M(MCI_F_GENZ_CORNER_POOL) M(MCI_F_GENZ_CORNER_COMP) M(MCI_F_BUBBLE)      \
   M(MCI_F_PRODUCT_4) M(MCI_F_SPHERE1) M(MCI_F_SPHERE2) M(MCI_F_DISCRETE_X) M(MCI_F_DISCRETE2_CONST)                 \
-  M(MCI_F_LATTICE_POOL) M(MCI_F_LATTICE_COMP) M(MCI_F_HYPERSPHERE3) M(MCI_F_POLY3) M(MCI_F_X2_PLUS_Y2)
+  M(MCI_F_LATTICE_POOL) M(MCI_F_LATTICE_COMP) M(MCI_F_HYPERSPHERE3) M(MCI_F_POLY3) M(MCI_F_X2_PLUS_Y2)                 \
+  M(MCI_F_COMPLEX1) M(MCI_F_COMPLEX2)
 /* integrands on a FermiK variable: mcmc only (test/bubble_FermiK.jl:139-140) */
 #define MCI_FOR_EACH_MCMC_ONLY_FID(M) M(MCI_F_BUBBLE_FERMIK)
 

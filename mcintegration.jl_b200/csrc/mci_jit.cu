@@ -127,9 +127,9 @@ std::string jit_problem_header(const DevProblem &P) {
   snprintf(buf, sizeof buf,
            "  static constexpr int solver = %d, fid = %d, measure_kind = %d, ni = %d, nd = %d, nv = %d, nleaf = %d, n_draw = %d;\n"
            "  static constexpr int obs_total = %d, hist_len = %d, pa_dim = %d, measurefreq = %d, need_pad = %d, any_adapt = %d;\n"
-           "  static constexpr int map_doubles = %d, n_tslot = %d;\n  static constexpr bool has_fermik = %s;\n",
+           "  static constexpr int map_doubles = %d, n_tslot = %d, wdim = %d, start_idx = %d;\n  static constexpr bool has_fermik = %s;\n",
            P.solver, P.fid, P.measure_kind, P.ni, P.nd, P.nv, P.nleaf, P.n_draw, P.obs_total, P.hist_len, P.pa_dim, P.measurefreq,
-           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot, has_fermik ? "true" : "false");
+           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot, P.wdim, P.start_idx, has_fermik ? "true" : "false");
   o += buf;
   o += members;
   o += "  struct T_leaf { __device__ __forceinline__ const DevLeaf &operator[](int i) const { return jit_tab::leaf[i]; } } leaf;\n";
@@ -141,7 +141,7 @@ std::string jit_problem_header(const DevProblem &P) {
 }
 
 int jit_compile(const DevProblem &P, const char *user_source, const std::vector<std::string> &name_exprs,
-                std::vector<const void *> &kernels, std::string &err, const std::string &defines) {
+                std::vector<const void *> &kernels, std::string &err, const std::string &defines, bool compile_only) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (!nvrtc_load(err)) return -1;
   const std::string prob = jit_problem_header(P);
@@ -204,7 +204,7 @@ int jit_compile(const DevProblem &P, const char *user_source, const std::vector<
     }
     it = g_cache.emplace(key, std::move(C)).first;
   }
-  if (getenv("MCIB200_JIT_COMPILE_ONLY")) { kernels.clear(); return 0; } /* CPU-side tests: compile, do not load */
+  if (compile_only) { kernels.clear(); return 0; } /* mci_jit_check: compile, do not load (no device needed) */
   /* one cudaLibrary per handle (context-bound); the cubin itself is cached */
   cudaLibrary_t lib = nullptr;
   cudaError_t e = cudaLibraryLoadData(&lib, it->second.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);

@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   constexpr int NWARP = THREADS / 32;
   static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED,
                 "pool kernel histogram modes");
+  static_assert(IntegrandWD<FID>::value == 1, "complex integrands run on the generic kernel");
   constexpr int NCOPY = HMODE == HIST_SMEM_STRIPED ? STRIPE : (HMODE == HIST_SMEM_ATOMIC ? 1 : 0);
   constexpr int REP = HMODE == HIST_SMEM_STRIPED ? POOL_MAP_REP : 1; /* the striped variant owns the SM: room for map copies */
   extern __shared__ __align__(16) double smem[];
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   MCI_VIEW(P, Pp);
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
+  constexpr int WD = IntegrandWD<FID>::value; /* doubles per value: 2 = complex (re, im) */
   constexpr int NWARP = THREADS / 32;
   extern __shared__ __align__(16) double smem[];
   double *smaps = smem;
@@ -416,25 +418,28 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
       const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
       const bool active = s < A.neval_per_block;
       if (!__any_sync(0xffffffffu, active)) break;
-      double x[MAX_DRAW], tprob[MAX_DRAW], w[NI], pad[NI], jac;
+      double x[MAX_DRAW], tprob[MAX_DRAW], w[NI * WD], pad[NI], jac;
       int bin[MAX_DRAW];
       vegas_sample_generic<FID>(P, maps, K, s, block, x, bin, tprob, jac, w, pad);
       bool finite = true;
 #pragma unroll
-      for (int i = 0; i < NI; ++i) finite = finite && isfinite(w[i]);
+      for (int i = 0; i < NI * WD; ++i) finite = finite && isfinite(w[i]);
       if (active && !finite) bad++;
       const bool meas = active && (P.measurefreq == 1 || ((s + 1) % (uint64_t)P.measurefreq) == 0);
       if (meas) {
         if (P.measure_kind == MCI_MEASURE_DEFAULT) {
 #pragma unroll
-          for (int i = 0; i < NI; ++i) acc[P.obs_off[i]] += w[i] * pad[i] * jac;
+          for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int c = 0; c < WD; ++c) acc[P.obs_off[i] + c] += w[WD * i + c] * pad[i] * jac;
         } else if (P.measure_kind == MCI_MEASURE_BIN_BY_DISCRETE) {
           /* obs[0][Ext - lower] += relw[0]; the binning leaf is the last leaf, slot 1 (example/bubble.jl:81-84) */
-          acc[P.obs_off[0] + bin[P.leaf[P.nleaf - 1].base]] += w[0] * pad[0] * jac;
-        } else { /* the caller's measure(x, obs, relw, config) (main.jl:35-37), compiled from source */
-          double relw[NI];
 #pragma unroll
-          for (int i = 0; i < NI; ++i) relw[i] = w[i] * pad[i] * jac;
+          for (int c = 0; c < WD; ++c) acc[P.obs_off[0] + WD * bin[P.leaf[P.nleaf - 1].base] + c] += w[c] * pad[0] * jac;
+        } else { /* the caller's measure(x, obs, relw, config) (main.jl:35-37), compiled from source */
+          double relw[NI * WD];
+#pragma unroll
+          for (int i = 0; i < NI * WD; ++i) relw[i] = w[i] * pad[i / WD] * jac;
           FlatX X{x, &P};
           UserMeasureT<0>::call(X, acc, relw, P.userdata);
         }
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
         for (int v = 0; v < P.nv; ++v)
           MCI_UNROLL_LAYOUT
           for (int i = 0; i < NI; ++i) {
-            const double a = fabs(w[i]) * jac;
+            const double a = wabs<WD>(w, i) * jac;
             const double w2 = a * a;
             MCI_UNROLL_LAYOUT
             for (int p = 0; p < P.dof[i * P.nv + v]; ++p)
@@ -498,12 +503,13 @@ __global__ void vegas_trace_kernel(const __grid_constant__ DevProblem Pp, const 
   if (t >= count) return;
   PhiloxKey K;
   philox_expand_key(P.seed, iter, K);
-  double x[MAX_DRAW], tprob[MAX_DRAW], w[Integrand<FID>::NI], pad[Integrand<FID>::NI], jac;
+  constexpr int WD = IntegrandWD<FID>::value;
+  double x[MAX_DRAW], tprob[MAX_DRAW], w[Integrand<FID>::NI * WD], pad[Integrand<FID>::NI], jac;
   int bin[MAX_DRAW];
   vegas_sample_generic<FID>(P, gmaps, K, first + t, block, x, bin, tprob, jac, w, pad);
   for (int k = 0; k < P.n_draw; ++k) { xo[(size_t)t * P.n_draw + k] = x[k]; bo[(size_t)t * P.n_draw + k] = bin[k]; }
   jo[t] = jac;
-  for (int i = 0; i < P.ni; ++i) wo[(size_t)t * P.ni + i] = w[i];
+  for (int i = 0; i < P.ni * WD; ++i) wo[(size_t)t * P.ni * WD + i] = w[i]; /* complex: (re, im) interleaved */
 }
 
 }  // namespace mci

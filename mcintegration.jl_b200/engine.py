@@ -169,6 +169,28 @@ class CudaEngine(HandleEngine):
         self._check(self.lib.mci_stats_device_ptr(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def nonfinite_count(self) -> int:
+        """non-finite integrand values met by the last fetched iteration (the reference's debug warnings)"""
+        n = C.c_uint64()
+        self._check(self.lib.mci_nonfinite_count(self.h, C.byref(n)))
+        return n.value
+
+    def run_iterations(self, first_iter: int, niter: int, *, gamma=1.0, goal=None, do_reweight=False, do_refine=True):
+        """niter whole iterations (fill -> statistics -> doReweight! -> train!) in ONE library call, no host round
+        trip in between (mci_run_iterations); returns the IterationStats of every iteration."""
+        outs = (_abi.IterationOut * niter)()
+        keep = []
+        for k in range(niter):
+            st, out, nev = self._alloc_out()
+            outs[k] = out
+            keep.append((st, nev))
+        g = None if goal is None else np.ascontiguousarray(goal, dtype=np.float64)
+        self._check(self.lib.mci_run_iterations(self.h, int(first_iter), int(niter), float(gamma), _dp(g),
+                                                1 if do_reweight else 0, 1 if do_refine else 0, outs))
+        for st, nev in keep:
+            st.neval = nev.value
+        return [st for st, _ in keep]
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         self._check(self.lib.mci_launch_count(self.h, C.byref(n)))

@@ -21,20 +21,25 @@ class Integrand:
     userdata: tuple = ()
     doc: str = ""
     source: str | None = None  # CUDA C++ source of a user integrand (id == F_USER)
+    complex: bool = False      # ComplexF64 values: the device function writes (re, im) pairs
 
     def with_userdata(self, data: Sequence[float]) -> "Integrand":
-        return Integrand(self.name, self.id, self.n_integrand, tuple(float(x) for x in data), self.doc, self.source)
+        return Integrand(self.name, self.id, self.n_integrand, tuple(float(x) for x in data), self.doc, self.source,
+                         self.complex)
 
 
-def user_integrand(source: str, n_integrand: int = 1, userdata: Sequence[float] = (), name: str = "user") -> Integrand:
+def user_integrand(source: str, n_integrand: int = 1, userdata: Sequence[float] = (), name: str = "user",
+                   complex: bool = False) -> Integrand:
     """The reference takes any closure f(x, c) (main.jl:25-33); here the integrand is CUDA C++ source compiled by NVRTC
     at engine creation into a kernel specialised to the problem.  `source` must define
 
         template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w);
 
     X(leaf, pos): value of pool slot `pos` (1-based, the reference's x[pos]) of leaf variable `leaf` (0-based, top-level
-    order then leaf order); w[0..n_integrand-1] receives the values."""
-    return Integrand(name, _abi.F_USER, int(n_integrand), tuple(float(x) for x in userdata), "user source (NVRTC)", source)
+    order then leaf order); w[0..n_integrand-1] receives the values.  complex=True (with Configuration(type=complex)):
+    w[2i], w[2i+1] = real and imaginary part of integrand i."""
+    return Integrand(name, _abi.F_USER, int(n_integrand), tuple(float(x) for x in userdata), "user source (NVRTC)", source,
+                     bool(complex))
 
 
 @dataclass(frozen=True)
@@ -63,6 +68,9 @@ lattice_comp = Integrand("lattice_comp", _abi.F_LATTICE_COMP, 1, doc="same on Co
 hypersphere3 = Integrand("hypersphere3", _abi.F_HYPERSPHERE3, 3, doc="nested unit balls d=2,3,4 (test/montecarlo.jl:200-216, N=3)")
 poly3 = Integrand("poly3", _abi.F_POLY3, 3, doc="(x, x², x³) (test/thread.jl)")
 x2_plus_y2 = Integrand("x2_plus_y2", _abi.F_X2_PLUS_Y2, 1, doc="x₁²+x₂² (main.jl:64)")
+complex1 = Integrand("complex1", _abi.F_COMPLEX1, 1, doc="x + x² im (test/montecarlo.jl:166-170, TestComplex1)", complex=True)
+complex2 = Integrand("complex2", _abi.F_COMPLEX2, 2, doc="(x, x² im), dof=[[1],[1]] (test/montecarlo.jl:172-198, TestComplex2)",
+                     complex=True)
 
 
 def genz_corner_peak(d: int, layout: str = "pool", csum: float = 1.85) -> Integrand:
@@ -169,7 +177,7 @@ def bubble_fermik(para: BubblePara | None = None) -> Integrand:
 REGISTRY = {
     f.name: f
     for f in (gauss_nd, log_over_sqrt, sphere1, sphere2, discrete_x, discrete2_const, lattice_pool, lattice_comp,
-              hypersphere3, poly3, x2_plus_y2)
+              hypersphere3, poly3, x2_plus_y2, complex1, complex2)
 }
 
 

@@ -27,6 +27,11 @@ def average(means, stds, init=1, max_=None):
         max_ = len(means)
     if max_ <= init:
         return means[0], stds[0], np.zeros_like(means[0])
+    if np.iscomplexobj(np.asarray(means[-1])):  # real and imaginary parts are averaged separately (statistics.jl:208-215)
+        part = lambda f, xs: [f(np.asarray(x)) for x in xs]
+        mr, er, cr = average(part(np.real, means), part(np.real, stds), init, max_)
+        mi, ei, ci = average(part(np.imag, means), part(np.imag, stds), init, max_)
+        return mr + 1j * mi, er + 1j * ei, cr + 1j * ci
     data = [np.asarray(means[i]) for i in range(init - 1, max_)]
     weight = [1.0 / (np.asarray(stds[i]) + 1.0e-10) ** 2 for i in range(init - 1, max_)]
     wsum = sum(weight)

@@ -321,8 +321,15 @@ typedef struct oconfig {
   uint64_t neval;
   orng rng;
   int shift_mode;
+  int wd;       /* doubles per integrand value: 1 real, 2 complex (re, im) — Configuration(type=ComplexF64) */
+  int counting; /* 0 during the extra burn-in steps of mci_problem_t.chain_burnin: they touch no statistic */
   void *mem; /* single allocation backing the arrays */
 } oconfig;
+
+/* abs(weights[i]): Julia's abs(::Complex) is hypot(re, im) */
+static inline double wabs(const oconfig *c, const double *w, int i) {
+  return c->wd == 1 ? fabs(w[i]) : hypot(w[2 * i], w[2 * i + 1]);
+}
 
 /* create!(::Continuous): sampler.jl:293-305 */
 static double cont_create(oleaf *T, int idx, orng *rng) {
@@ -600,7 +607,7 @@ static double volume_inverse(int d) {
   return pow(d / (2 * PI * euler), d / 2.0) * sqrt((double)d) * sqrt(PI);
 }
 
-/* evaluate all integrands (vegas / vegasmc convention f(x, c)); w has ni entries */
+/* evaluate all integrands (vegas / vegasmc convention f(x, c)); w has ni entries ((re, im) pairs when complex) */
 static void eval_all(const oconfig *c, int id, double *w) {
   const double *ud = c->userdata;
   switch (id) {
@@ -702,16 +709,24 @@ static void eval_all(const oconfig *c, int id, double *w) {
     double a = X(c, 0, 1), b = X(c, 0, 2);
     w[0] = a * a + b * b;
     break; }
+  case MCI_F_COMPLEX1: { /* test/montecarlo.jl:166-170: x + x^2 im */
+    double x = X(c, 0, 1);
+    w[0] = x; w[1] = x * x;
+    break; }
+  case MCI_F_COMPLEX2: { /* test/montecarlo.jl:172-198: (x, x^2 im) */
+    double x = X(c, 0, 1);
+    w[0] = x; w[1] = 0.0; w[2] = 0.0; w[3] = x * x;
+    break; }
   default:
-    for (int i = 0; i < c->ni; ++i) w[i] = NAN;
+    for (int i = 0; i < c->ni * c->wd; ++i) w[i] = NAN;
   }
 }
 
-/* mcmc convention f(idx, x, c): the reference's tests define it as the idx-th component */
-static double eval_one(const oconfig *c, int id, int idx /*0-based*/) {
-  double w[MCI_MAX_INTEGRAND];
+/* mcmc convention f(idx, x, c): the reference's tests define it as the idx-th component; out has wd entries */
+static void eval_one(const oconfig *c, int id, int idx /*0-based*/, double *out) {
+  double w[2 * MCI_MAX_INTEGRAND];
   eval_all(c, id, w);
-  return w[idx];
+  for (int k = 0; k < c->wd; ++k) out[k] = w[c->wd * idx + k];
 }
 
 /* ------------------------------------------------------------------------- */
@@ -730,6 +745,7 @@ struct orc_handle {
   int leaf_grid_off[MCI_MAX_LEAF], leaf_disc_off[MCI_MAX_LEAF], leaf_accum_off[MCI_MAX_LEAF], leaf_hist_off[MCI_MAX_LEAF];
   double *grids, *disc_dist, *disc_accum, *reweight;
   int rank, world, shift_mode;
+  int wd, start_idx; /* doubles per value (weight_kind); mcmc start integrand, 0-based */
   double *packed; int64_t packed_len;
   int off_hist, off_obs, off_cnt, off_visited, off_propose, off_accept, off_neval;
   char err[256];
@@ -772,8 +788,10 @@ int orc_create(const mci_problem_t *p, orc_handle **out) {
     for (int v = 0; v < h->nv; ++v) h->dof[i * h->nv + v] = p->dof[i * h->nv + v];
   for (int v = 0; v < h->nv; ++v) h->dof[h->ni * h->nv + v] = 0; /* configuration.jl:153 */
   orc_maxdof(h->dof, h->nd, h->nv, h->maxdof);
-  h->obs_total = 0;
-  for (int i = 0; i < h->ni; ++i) { h->obs_len[i] = p->obs_len ? p->obs_len[i] : 1; h->obs_off[i] = h->obs_total; h->obs_total += h->obs_len[i]; }
+  h->wd = p->weight_kind == MCI_WEIGHT_COMPLEX ? 2 : 1;
+  h->start_idx = p->mcmc_start_idx > 0 ? p->mcmc_start_idx - 1 : 0; /* `idx` of MCMC.montecarlo, mcmc/montecarlo.jl:76 */
+  h->obs_total = 0; /* in doubles: a complex entry is (re, im) */
+  for (int i = 0; i < h->ni; ++i) { h->obs_len[i] = (p->obs_len ? p->obs_len[i] : 1) * h->wd; h->obs_off[i] = h->obs_total; h->obs_total += h->obs_len[i]; }
   /* neighbor: configuration.jl:201-209 default chain, or the given CSR */
   if (p->neighbor_ptr) {
     for (int d = 0; d <= h->nd; ++d) h->nb_ptr[d] = p->neighbor_ptr[d];
@@ -896,6 +914,7 @@ static oconfig *config_new(const orc_handle *h) {
   c->h = h; c->ni = h->ni; c->nd = h->nd; c->nv = h->nv; c->nleaf = h->nleaf;
   c->dof = h->dof; c->maxdof = h->maxdof; c->reweight = h->reweight; c->userdata = h->userdata;
   c->shift_mode = h->shift_mode;
+  c->wd = h->wd; c->counting = 1;
   size_t nd = 0;
   int len[MCI_MAX_TOPVAR];
   for (int v = 0; v < h->nv; ++v) { len[v] = h->maxdof[v] + h->topvar_offset[v] + 2; nd += (size_t)len[v] * (1 + 3 * h->topvar_nleaf[v]); }
@@ -943,23 +962,26 @@ static void config_free(oconfig *c) { free(c->mem); free(c); }
 /* measure: default obs[i] += relw (vegas/montecarlo.jl:151-153) or the bubble rule (example/bubble.jl:81-84) */
 static void do_measure_all(oconfig *c, const double *relw) {
   const orc_handle *h = c->h;
+  const int wd = c->wd;
   if (h->p.measure_kind == MCI_MEASURE_DEFAULT) {
-    for (int i = 0; i < c->ni; ++i) c->obs[h->obs_off[i]] += relw[i];
+    for (int i = 0; i < c->ni; ++i)
+      for (int k = 0; k < wd; ++k) c->obs[h->obs_off[i] + k] += relw[wd * i + k];
   } else {
     const oleaf *E = &c->leaf[c->nleaf - 1];
     int off = c->top[c->nv - 1].offset;
     int e = (int)E->data[1 + off - 1] - E->lower_i;
-    c->obs[h->obs_off[0] + e] += relw[0];
+    for (int k = 0; k < wd; ++k) c->obs[h->obs_off[0] + wd * e + k] += relw[k];
   }
 }
-static void do_measure_one(oconfig *c, int curr, double relw) {
+static void do_measure_one(oconfig *c, int curr, const double *relw) {
   const orc_handle *h = c->h;
-  if (h->p.measure_kind == MCI_MEASURE_DEFAULT) c->obs[h->obs_off[curr]] += relw;
+  const int wd = c->wd;
+  if (h->p.measure_kind == MCI_MEASURE_DEFAULT) { for (int k = 0; k < wd; ++k) c->obs[h->obs_off[curr] + k] += relw[k]; }
   else {
     const oleaf *E = &c->leaf[c->nleaf - 1];
     int off = c->top[c->nv - 1].offset;
     int e = (int)E->data[1 + off - 1] - E->lower_i;
-    c->obs[h->obs_off[0] + e] += relw;
+    for (int k = 0; k < wd; ++k) c->obs[h->obs_off[0] + wd * e + k] += relw[k];
   }
 }
 
@@ -996,17 +1018,18 @@ static void vegas_sample(oconfig *c, uint64_t ne /*1-based*/, double *weights, d
   }
   eval_all(c, id, weights);                       /* :140-144 */
   c->neval += 1;
-  if (tr) { tr->jac[trow] = jac; for (int i = 0; i < c->ni; ++i) tr->w[trow * c->ni + i] = weights[i]; }
+  const int wd = c->wd;
+  if (tr) { tr->jac[trow] = jac; for (int i = 0; i < c->ni * wd; ++i) tr->w[trow * c->ni * wd + i] = weights[i]; }
   if (ne % (uint64_t)h->p.measurefreq == 0) {     /* :148-165 */
-    double relw[MCI_MAX_INTEGRAND];
-    for (int i = 0; i < c->ni; ++i) relw[i] = weights[i] * pad[i] * jac;
+    double relw[2 * MCI_MAX_INTEGRAND];
+    for (int i = 0; i < c->ni * wd; ++i) relw[i] = weights[i] * pad[i / wd] * jac;
     do_measure_all(c, relw);
     c->normalization += 1.0;
   }
   for (int vi = 0; vi < c->nv; ++vi) {            /* :170-185 */
     int offset = c->top[vi].offset;
     for (int i = 0; i < c->ni; ++i) {
-      double w2 = fabs(weights[i]);
+      double w2 = wabs(c, weights, i);
       double j2 = jac;
       for (int pos = 1; pos <= c->dof[i * c->nv + vi]; ++pos) var_accumulate(c, vi, pos + offset, (w2 * j2) * (w2 * j2));
     }
@@ -1015,7 +1038,7 @@ static void vegas_sample(oconfig *c, uint64_t ne /*1-based*/, double *weights, d
 
 static void vegas_block(oconfig *c, uint64_t iter, int block) {
   const orc_handle *h = c->h;
-  double weights[MCI_MAX_INTEGRAND], pad[MCI_MAX_INTEGRAND];
+  double weights[2 * MCI_MAX_INTEGRAND], pad[MCI_MAX_INTEGRAND];
   if (c->shift_mode == 1) { /* Dist.initialize! :108-110, on a stream no sample uses */
     orng_init(&c->rng, h->p.seed, iter, (uint32_t)block, ~(uint64_t)0);
     for (int vi = 0; vi < c->nv; ++vi) var_initialize(c, vi);
@@ -1045,15 +1068,15 @@ static double vegasmc_change_variable(oconfig *c, double currProbability, double
   double prop = var_shift(c, vi, idx);                     /* :60 */
   if (prop <= EPS0) return currProbability;                /* :62-64 */
   eval_all(c, h->p.integrand_id, _weights);                /* :66-74 */
-  c->neval += 1;
+  if (c->counting) c->neval += 1;
   for (int i = 0; i < N + 1; ++i) _pad[i] = padding_probability(c, i); /* :79-81 */
   double newProbability = c->reweight[N] * _pad[N];        /* :82 */
-  for (int i = 0; i < N; ++i) newProbability += fabs(_weights[i]) * c->reweight[i] * _pad[i];
+  for (int i = 0; i < N; ++i) newProbability += wabs(c, _weights, i) * c->reweight[i] * _pad[i];
   double R = prop * newProbability / currProbability;      /* :88 */
-  c->propose[PA(c, 1, 0, vi)] += 1.0;                      /* :90 propose[2,1,vi] */
+  if (c->counting) c->propose[PA(c, 1, 0, vi)] += 1.0;     /* :90 propose[2,1,vi] */
   if (orng_rand(&c->rng) < R) {
-    c->accept[PA(c, 1, 0, vi)] += 1.0;
-    for (int i = 0; i < N; ++i) weights[i] = _weights[i];
+    if (c->counting) c->accept[PA(c, 1, 0, vi)] += 1.0;
+    for (int i = 0; i < N * c->wd; ++i) weights[i] = _weights[i];
     for (int i = 0; i < N + 1; ++i) pad[i] = _pad[i];
     return newProbability;
   } else {
@@ -1065,19 +1088,22 @@ static double vegasmc_change_variable(oconfig *c, double currProbability, double
 static void vegasmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker, uint64_t neval) {
   const orc_handle *h = c->h;
   int N = c->ni;
-  double weights[MCI_MAX_INTEGRAND], _weights[MCI_MAX_INTEGRAND], relw[MCI_MAX_INTEGRAND];
-  double pad[MCI_MAX_INTEGRAND + 1], _pad[MCI_MAX_INTEGRAND + 1];
+  const int wd = c->wd;
+  double weights[2 * MCI_MAX_INTEGRAND], _weights[2 * MCI_MAX_INTEGRAND], relw[2 * MCI_MAX_INTEGRAND];
+  double pad[MCI_MAX_INTEGRAND + 1] = {0.0}, _pad[MCI_MAX_INTEGRAND + 1] = {0.0};
   orng_init(&c->rng, h->p.seed, iter, (uint32_t)block, walker);
   for (int vi = 0; vi < c->nv; ++vi) var_initialize(c, vi);        /* montecarlo.jl:151-153 */
   eval_all(c, h->p.integrand_id, _weights);                         /* :155-159 */
   for (int i = 0; i < N + 1; ++i) pad[i] = padding_probability(c, i); /* :161 */
   double probability_ = c->reweight[N] * pad[N];                    /* :162 */
-  for (int i = 0; i < N; ++i) { weights[i] = _weights[i]; probability_ += fabs(_weights[i]) * c->reweight[i] * pad[i]; }
+  for (int i = 0; i < N * wd; ++i) weights[i] = _weights[i];
+  for (int i = 0; i < N; ++i) probability_ += wabs(c, _weights, i) * c->reweight[i] * pad[i];
   for (int64_t ne = 1 - (int64_t)h->p.chain_burnin; ne <= (int64_t)neval; ++ne) { /* :184; ne <= 0: extra burn-in (mcib200.h) */
+    c->counting = ne >= 1;
     probability_ = vegasmc_change_variable(c, probability_, weights, _weights, pad, _pad); /* :186-188; single update */
     if (ne < 1) continue;
     for (int i = 0; i < N; ++i) {                                   /* :198-211 */
-      double f2 = fabs(weights[i]) * fabs(weights[i]) / probability(c, i);
+      double f2 = wabs(c, weights, i) * wabs(c, weights, i) / probability(c, i);
       double wf2 = f2 * pad[i] / probability_;
       for (int vi = 0; vi < c->nv; ++vi) {
         int offset = c->top[vi].offset;
@@ -1086,8 +1112,10 @@ static void vegasmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker
     }
     if ((uint64_t)ne % (uint64_t)h->p.measurefreq == 0 && (double)ne >= (double)neval / 100) { /* :213 */
       for (int i = 0; i < N; ++i) {
-        c->visited[i] += fabs(weights[i] * pad[i] * c->reweight[i]) / probability_;
-        relw[i] = weights[i] * pad[i] / probability_;
+        double wpr[2];
+        for (int k = 0; k < wd; ++k) wpr[k] = weights[wd * i + k] * pad[i] * c->reweight[i];
+        c->visited[i] += wabs(c, wpr, 0) / probability_;
+        for (int k = 0; k < wd; ++k) relw[wd * i + k] = weights[wd * i + k] * pad[i] / probability_;
       }
       do_measure_all(c, relw);
       c->normalization += 1.0 * pad[N] / probability_;                /* :229 */
@@ -1099,14 +1127,14 @@ static void vegasmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker
 /* ------------------------------------------------------------------------- */
 /* MCMC.montecarlo: mcmc/montecarlo.jl:72-205, updates.jl:1-147               */
 /* ------------------------------------------------------------------------- */
-typedef struct { int curr; double weight; double probability; } ostate;
+typedef struct { int curr; double weight[2]; double probability; } ostate; /* weight: (re, im) when complex */
 
 static void mcmc_initialize(oconfig *c, ostate *s) { /* montecarlo.jl:190-205 */
   for (int vi = 0; vi < c->nv; ++vi) var_initialize(c, vi);
   if (s->curr != c->ni) {
-    s->weight = eval_one(c, c->h->p.integrand_id, s->curr);
-    s->probability = fabs(s->weight) * c->reweight[s->curr];
-  } else { s->weight = 0.0; s->probability = c->reweight[s->curr]; }
+    eval_one(c, c->h->p.integrand_id, s->curr, s->weight);
+    s->probability = wabs(c, s->weight, 0) * c->reweight[s->curr];
+  } else { s->weight[0] = s->weight[1] = 0.0; s->probability = c->reweight[s->curr]; }
 }
 
 static void mcmc_change_integrand(oconfig *c, ostate *s) { /* updates.jl:1-70 */
@@ -1123,14 +1151,15 @@ static void mcmc_change_integrand(oconfig *c, ostate *s) { /* updates.jl:1-70 */
     else if (currdof[vi] > newdof[vi]) { for (int pos = newdof[vi] + 1; pos <= currdof[vi]; ++pos) prop *= var_remove(c, vi, pos + offset); }
   }
   if (prop <= EPS0) return;                                  /* :29-31 */
-  double newWeight = (new_ == c->ni) ? 0.0 : eval_one(c, h->p.integrand_id, new_); /* :35-38 */
-  c->neval += 1;
-  double newProbability = (new_ == c->ni) ? c->reweight[new_] : fabs(newWeight) * c->reweight[new_];
+  double newWeight[2] = {0.0, 0.0};
+  if (new_ != c->ni) eval_one(c, h->p.integrand_id, new_, newWeight); /* :35-38 */
+  if (c->counting) c->neval += 1;
+  double newProbability = (new_ == c->ni) ? c->reweight[new_] : wabs(c, newWeight, 0) * c->reweight[new_];
   double R = prop * newProbability / s->probability;         /* :46 */
-  c->propose[PA(c, 0, curr, new_)] += 1.0;
+  if (c->counting) c->propose[PA(c, 0, curr, new_)] += 1.0;
   if (orng_rand(&c->rng) < R) {
-    c->accept[PA(c, 0, curr, new_)] += 1.0;
-    s->curr = new_; s->weight = newWeight; s->probability = newProbability;
+    if (c->counting) c->accept[PA(c, 0, curr, new_)] += 1.0;
+    s->curr = new_; s->weight[0] = newWeight[0]; s->weight[1] = newWeight[1]; s->probability = newProbability;
   } /* createRollback!/removeRollback! are no-ops: sampler.jl:24,43,306,324 */
 }
 
@@ -1144,13 +1173,16 @@ static void mcmc_change_variable(oconfig *c, ostate *s) { /* updates.jl:72-109 *
   int idx = c->top[vi].offset + orng_int(&c->rng, currdof[vi]); /* :84 */
   double prop = var_shift(c, vi, idx);
   if (prop <= EPS0) return;
-  double weight = eval_one(c, c->h->p.integrand_id, curr);
-  c->neval += 1;
-  double newProbability = fabs(weight) * c->reweight[curr];
+  double weight[2] = {0.0, 0.0};
+  eval_one(c, c->h->p.integrand_id, curr, weight);
+  if (c->counting) c->neval += 1;
+  double newProbability = wabs(c, weight, 0) * c->reweight[curr];
   double R = prop * newProbability / s->probability;
-  c->propose[PA(c, 1, curr, vi)] += 1.0;
-  if (orng_rand(&c->rng) < R) { c->accept[PA(c, 1, curr, vi)] += 1.0; s->weight = weight; s->probability = newProbability; }
-  else var_shift_rollback(c, vi, idx);
+  if (c->counting) c->propose[PA(c, 1, curr, vi)] += 1.0;
+  if (orng_rand(&c->rng) < R) {
+    if (c->counting) c->accept[PA(c, 1, curr, vi)] += 1.0;
+    s->weight[0] = weight[0]; s->weight[1] = weight[1]; s->probability = newProbability;
+  } else var_shift_rollback(c, vi, idx);
 }
 
 static void mcmc_swap_variable(oconfig *c, ostate *s) { /* updates.jl:111-147 */
@@ -1164,20 +1196,23 @@ static void mcmc_swap_variable(oconfig *c, ostate *s) { /* updates.jl:111-147 */
   if (idx1 == idx2) return;
   double prop = var_swap(c, vi, idx1, idx2);
   if (prop <= EPS0) return;
-  double weight = eval_one(c, c->h->p.integrand_id, curr);
-  c->neval += 1;
-  double newProbability = fabs(weight) * c->reweight[curr];
+  double weight[2] = {0.0, 0.0};
+  eval_one(c, c->h->p.integrand_id, curr, weight);
+  if (c->counting) c->neval += 1;
+  double newProbability = wabs(c, weight, 0) * c->reweight[curr];
   double R = prop * newProbability / s->probability;
-  c->propose[PA(c, 2, curr, vi)] += 1.0;
-  if (orng_rand(&c->rng) < R) { c->accept[PA(c, 2, curr, vi)] += 1.0; s->weight = weight; s->probability = newProbability; }
-  else var_swap_rollback(c, vi, idx1, idx2);
+  if (c->counting) c->propose[PA(c, 2, curr, vi)] += 1.0;
+  if (orng_rand(&c->rng) < R) {
+    if (c->counting) c->accept[PA(c, 2, curr, vi)] += 1.0;
+    s->weight[0] = weight[0]; s->weight[1] = weight[1]; s->probability = newProbability;
+  } else var_swap_rollback(c, vi, idx1, idx2);
 }
 
 /* returns 0 ok, MCI_ERR_MCMC_START when no start point exists (montecarlo.jl:109-110) */
 static int mcmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker, uint64_t neval) {
   const orc_handle *h = c->h;
   orng_init(&c->rng, h->p.seed, iter, (uint32_t)block, walker);
-  ostate s = {0, 0.0, 1.0}; /* idx=1 */
+  ostate s = {h->start_idx, {0.0, 0.0}, 1.0}; /* `idx`: the integral to start with (:76), default 1 */
   for (int i = 0; i < 10000; ++i) {                          /* :103-108 */
     mcmc_initialize(c, &s);
     if (s.curr == c->ni || s.probability > TINY) break;
@@ -1186,6 +1221,7 @@ static int mcmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker, ui
   int nupdates = 2 * c->nv + 2;                              /* :117-120 */
   uint64_t nburnin = (uint64_t)floor((double)neval * h->p.thermal_ratio); /* :133 */
   for (int64_t i = 1 - (int64_t)h->p.chain_burnin; i <= (int64_t)(neval + nburnin); ++i) { /* :134; i <= 0: extra burn-in */
+    c->counting = i >= 1;
     if (i >= 1) c->visited[s.curr] += 1;
     int u = orng_int(&c->rng, nupdates);                     /* :138 */
     if (u == 1) mcmc_change_integrand(c, &s);
@@ -1198,7 +1234,10 @@ static int mcmc_walker(oconfig *c, uint64_t iter, int block, uint64_t walker, ui
           for (int pos = 1; pos <= c->dof[s.curr * c->nv + vi]; ++pos) var_accumulate(c, vi, pos + offset, 1.0);
         }
       if (s.curr == c->ni) c->normalization += 1.0 / c->reweight[c->ni]; /* :158-159 */
-      else do_measure_one(c, s.curr, s.weight / s.probability);          /* :161-169 */
+      else { /* :161-169 */
+        double relw[2] = {s.weight[0] / s.probability, s.weight[1] / s.probability};
+        do_measure_one(c, s.curr, relw);
+      }
     }
   }
   return 0;
@@ -1252,7 +1291,7 @@ int orc_run_iteration(orc_handle *h, uint64_t iter, int32_t nthreads) {
     config_free(c);
   }
   free(cfg);
-  if (status) { snprintf(h->err, sizeof h->err, "mcmc: cannot find variables that make integrand #1 nonzero"); return status; }
+  if (status) { snprintf(h->err, sizeof h->err, "Cannot find the variables that makes the #%d integrand nonzero!", h->start_idx + 1); return status; }
   return MCI_OK;
 }
 
@@ -1315,7 +1354,7 @@ int orc_trace_samples(orc_handle *h, uint64_t iter, int32_t block, uint64_t firs
   int n_draw = 0;
   for (int vi = 0; vi < h->nv; ++vi) n_draw += h->maxdof[vi] * h->topvar_nleaf[vi];
   otrace tr = {x, bins, jac, weights, n_draw};
-  double w[MCI_MAX_INTEGRAND], pad[MCI_MAX_INTEGRAND];
+  double w[2 * MCI_MAX_INTEGRAND], pad[MCI_MAX_INTEGRAND];
   for (int32_t s = 0; s < count; ++s) {
     orng_init(&c->rng, h->p.seed, iter, (uint32_t)block, first + s);
     vegas_sample(c, first + s + 1, w, pad, &tr, s);

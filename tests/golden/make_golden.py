@@ -969,6 +969,23 @@ def main():
                              vegasmc=dict(steps=300, measurefreq=1,
                                           out=loop_vegasmc_vars(mkb, fb, bdof, brw, 5150, 4, 2, 300, 1, nbins_obs=4)))
 
+    # complex integrands (Configuration(type=ComplexF64)): TestComplex2 of test/montecarlo.jl:172-198, f = (x, x^2 im),
+    # dof = [[1], [1]], through the same three loops — Python's complex arithmetic plays Julia's: abs(z) = hypot(re, im),
+    # z * real and z / real component by component.  Stored as (re, im) pairs in the library's observable layout
+    # [block][integrand][re, im] (include/mcib200.h, MCI_WEIGHT_COMPLEX)
+    QC = Prob(lambda: Pool(lgrid, 1), lambda x: [x[1] + 0j, x[1] * x[1] * 1j], [1, 1, 0], [[3, 2], [1], [1]])
+    crw = [0.4, 0.35, 0.25]
+
+    def split(o):
+        o = dict(o)
+        o["obs"] = [[c for z in blk for c in (complex(z).real, complex(z).imag)] for blk in o["obs"]]
+        return o
+
+    G["loops_complex"] = dict(grid=lgrid, reweight=crw, seed=1618, iter=5, n_block=2,
+                              vegas=dict(npb=64, measurefreq=1, out=split(loop_vegas(QC, 1618, 5, 2, 64, 1))),
+                              vegasmc=dict(steps=300, measurefreq=1, out=split(loop_vegasmc(QC, crw, 1618, 5, 2, 300, 1))),
+                              mcmc=dict(steps=300, measurefreq=1, thermal_ratio=0.1, out=split(loop_mcmc(QC, crw, 1618, 5, 2, 300, 1, 0.1))))
+
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(out, "w") as f:
         json.dump(G, f)

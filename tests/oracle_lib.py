@@ -94,7 +94,7 @@ class OracleEngine(HandleEngine):
 
 def oracle_integrate(integrand, *, solver="vegas", config=None, neval=1e4, niter=10, block=16, gamma=1.0, adapt=True,
                      reweight_goal=None, ignore=None, measure=None, measurefreq=1, thermal_ratio=0.1, walkers=1,
-                     shift_mode=0, nthreads=None, chain_burnin=None, **kwargs):
+                     shift_mode=0, nthreads=None, chain_burnin=None, idx=1, **kwargs):
     """integrate() with the oracle as engine: same host driver (mcintegration_jl_b200.main.drive)."""
     from mcintegration_jl_b200.main import _MEASURES, _SOLVERS, _standardize_block, default_chain_burnin, drive
     from mcintegration_jl_b200.integrands import resolve
@@ -107,7 +107,8 @@ def oracle_integrate(integrand, *, solver="vegas", config=None, neval=1e4, niter
     nevalperblock = (nevalperblock // W) * W
     spec = mci.problem_from_config(config, f, solver=_SOLVERS[solver], measure_kind=_MEASURES[measure], n_block=block,
                                    neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
-                                   thermal_ratio=thermal_ratio, chain_burnin=default_chain_burnin(W, chain_burnin))
+                                   thermal_ratio=thermal_ratio, chain_burnin=default_chain_burnin(W, chain_burnin),
+                                   seed=config.next_seed(), mcmc_start_idx=int(idx))  # main.jl:136, like integrate()
     eng = OracleEngine(spec, nthreads=nthreads, shift_mode=shift_mode)
     try:
         eng.set_maps(*mci.maps_from_config(config))
