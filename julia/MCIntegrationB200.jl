@@ -28,6 +28,8 @@ struct MciProblem
     measurefreq::Int32; walkers_per_block::Int32; thermal_ratio::Float64; device::Int32; hist_policy::Int32
     jit::Int32; reserved_::Int32; user_source::Cstring       # ABI v2: NVRTC specialisation / user integrand source
     chain_burnin::UInt64                                       # extra unmeasured steps per chain (0 = reference)
+    mcmc_start_idx::Int32                                      # ABI v3: `idx` of MCMC.montecarlo (mcmc/montecarlo.jl:76), 1-based
+    weight_kind::Int32                                         # ABI v3: 0 = Float64, 1 = ComplexF64 values and observables
 end
 
 struct MciIterationOut
@@ -50,16 +52,21 @@ leafdesc(v::Continuous) = MciLeaf(0, length(v.grid) - 1, v.adapt, 0, v.lower, v.
 leafdesc(v::Discrete) = MciLeaf(1, v.upper - v.lower + 1, v.adapt, v.lower, 0.0, 0.0, v.alpha)
 
 """
-    integrate_b200(integrand::Union{Integer,AbstractString}; userdata=Float64[], measure_kind=0, walkers=0, device=0, jit=0, chain_burnin=1024, kwargs...)
+    integrate_b200(integrand::Union{Integer,AbstractString}; userdata=Float64[], measure_kind=0, walkers=0, device=0, jit=0,
+                   chain_burnin=1024, comm=nothing, idx=1, debug=false, kwargs...)
 
 Same keyword surface as `MCIntegration.integrate` (src/main.jl:71-90): `solver, config, neval, niter, block, gamma,
-adapt, reweight_goal, ignore, measurefreq, thermal_ratio` plus the `Configuration` kwargs (`var, dof, obs, reweight,
-seed, neighbor`).  The integrand is a built-in device function (`enum mci_integrand_id`) or CUDA C++ source instead of a
-closure.
+adapt, debug, reweight_goal, ignore, measurefreq, thermal_ratio` plus the `Configuration` kwargs (`var, dof, type, obs,
+reweight, seed, neighbor`).  The integrand is a built-in device function (`enum mci_integrand_id`) or CUDA C++ source
+instead of a closure.  `comm` = an `MPI.Comm` (one process per GPU, like the reference's MPI mode, main.jl:113-122): the
+128-byte NCCL id travels over it once, afterwards the library's own all-reduce replaces MPIreduce / MPIbcast.  `idx` =
+the integrand an :mcmc chain starts in (mcmc/montecarlo.jl:76).  `type=ComplexF64` (configuration.jl:108) selects
+complex integrand values; the source then writes (re, im) pairs.
 """
 function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, niter=10, block=16,
-    gamma=1.0, adapt=true, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
-    userdata=Float64[], measure_kind=0, walkers=0, device=0, hist_policy=0, jit=0, chain_burnin=1024, kwargs...)
+    gamma=1.0, adapt=true, debug=false, reweight_goal=nothing, ignore::Int=adapt ? 1 : 0, measurefreq=1, thermal_ratio=0.1,
+    userdata=Float64[], measure_kind=0, walkers=0, device=0, hist_policy=0, jit=0, chain_burnin=1024, comm=nothing, idx::Int=1,
+    kwargs...)
     # `integrand` is a built-in id (enum mci_integrand_id) or a String holding CUDA C++ source that defines
     # `template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w)`
     # (MCI_F_USER = 100, compiled by NVRTC inside mci_create) — the device-side equivalent of the closure f(x, c).
@@ -67,7 +74,11 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
     source = integrand isa AbstractString ? String(integrand) : ""
     haskey(SOLVER, solver) || error("Solver $solver is not supported!")            # main.jl:263
     config = isnothing(config) ? Configuration(; kwargs...) : config                # main.jl:95-97
-    nevalperblock, block = MCIntegration._standardize_block(neval, block)          # main.jl:121
+    nevalperblock, block = MCIntegration._standardize_block(neval, block)          # main.jl:121 (pads block up to nprocs)
+    nprocs = isnothing(comm) ? 1 : _mpi().Comm_size(comm)
+    @assert block % nprocs == 0                                                      # main.jl:122
+    T = eltype(config.observable) <: AbstractArray ? eltype(eltype(config.observable)) : eltype(config.observable)
+    cplx = T <: Complex                                                              # Configuration(type=ComplexF64)
     # walkers = 0: the library fills the GPU with whole CTAs of chains of >= 512 steps (mci_chain_info); walkers = 1 and
     # chain_burnin = 0 reproduce the reference's one-chain-per-block decomposition (DESIGN.md 5.3)
     W = solver == :vegas ? 1 : walkers
@@ -79,7 +90,8 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
     desc = MciLeaf[leafdesc(l) for l in lv]
     N, Nv = config.N, length(config.var)
     dof = Int32[config.dof[i][v] for i in 1:N for v in 1:Nv]                        # row-major [Ni][Nv]
-    obslen = Int32[length(o) for o in config.observable]
+    obslen = Int32[length(o) for o in config.observable]                          # in (complex) entries
+    goalbuf = isnothing(reweight_goal) ? Float64[] : Float64.(reweight_goal)        # rooted for the whole call
     nbptr = Int32[0]; nbidx = Int32[]
     for nb in config.neighbor
         append!(nbidx, Int32.(nb .- 1)); push!(nbptr, length(nbidx))
@@ -92,12 +104,14 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
         prob = MciProblem(SOLVER[solver], integrand_id, measure_kind, N, Nv, length(lv), pointer(topn), pointer(topoff),
             pointer(desc), pointer(dof), pointer(obslen), pointer(nbptr), pointer(nbidx), pointer(ud), length(ud), block,
             nevalperblock, seed, measurefreq, W, thermal_ratio, device, hist_policy, jit, 0,
-            isempty(source) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, source), UInt64(chain_burnin))
+            isempty(source) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, source), UInt64(chain_burnin),
+            Int32(idx), Int32(cplx ? 1 : 0))
         rc = ccall((:mci_create, LIB), Cint, (Ref{MciProblem}, Ref{Ptr{Cvoid}}), prob, h)
         rc == 0 || throw(MciError(rc, unsafe_string(ccall((:mci_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
     end
     handle = h[]
     try
+        isnothing(comm) || comm_init!(handle, comm)   # blocks b mod nprocs == rank; one ncclAllReduce per iteration
         # warm restart: push the grids of `config` (main.jl:95-97, docs/src/index.md:129-150)
         grids = vcat((l.grid for l in lv if l isa Continuous)..., Float64[])
         dist = vcat((l.distribution for l in lv if l isa Discrete)..., Float64[])
@@ -106,7 +120,7 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
             handle, grids, dist, accum, config.reweight))
 
         Nd = N + 1
-        obstot = sum(obslen)
+        obstot = sum(obslen) * (cplx ? 2 : 1)       # doubles per block: a complex entry is (re, im)
         histlen = sum(d.nbins for d in desc)
         pa = max(Nd, Nv)
         block_obs = zeros(obstot, block)          # C row-major [block][obstot] == Julia column-major (obstot, block)
@@ -123,14 +137,34 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
             config.neval = nev[]; config.visited .= visited
             config.propose .= permutedims(propose, (3, 2, 1)); config.accept .= permutedims(accept, (3, 2, 1))
             config.normalization = sum(block_norm)
+            if debug                                                               # vegas/montecarlo.jl:176-178 etc.
+                bad = Ref{UInt64}(0)
+                ccall((:mci_nonfinite_count, LIB), Cint, (Ptr{Cvoid}, Ref{UInt64}), handle, bad)
+                bad[] > 0 && @warn("integrand is not finite at $(bad[]) evaluation(s) of iteration $iter")
+            end
             if solver != :vegas                                                    # main.jl:183
-                goal = isnothing(reweight_goal) ? C_NULL : pointer(Float64.(reweight_goal))
-                check(handle, ccall((:mci_reweight, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), handle, gamma, goal))
+                GC.@preserve goalbuf begin
+                    goal = isempty(goalbuf) ? Ptr{Float64}(C_NULL) : pointer(goalbuf)
+                    check(handle, ccall((:mci_reweight, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), handle, gamma, goal))
+                end
             end
             adapt && check(handle, ccall((:mci_refine, LIB), Cint, (Ptr{Cvoid},), handle))   # main.jl:193-198
             # per-block means -> _mean_std (main.jl:275-287, 296-320)
             m = block_obs ./ reshape(block_norm, 1, :)
-            obsSum = vec(sum(m, dims=2)); obsSq = vec(sum(m .^ 2, dims=2))
+            if cplx     # (re, im) doubles -> ComplexF64; squares of the two parts kept separately (main.jl:281,285)
+                mc = m[1:2:end, :] .+ m[2:2:end, :] .* im
+                sq = real.(mc) .^ 2 .+ (imag.(mc) .^ 2) .* im
+                flatSum = vec(sum(mc, dims=2)); flatSq = vec(sum(sq, dims=2))
+            else
+                flatSum = vec(sum(m, dims=2)); flatSq = vec(sum(m .^ 2, dims=2))
+            end
+            # regroup the flat entries per integrand like config.observable (scalar or vector observables)
+            obsSum = Any[]; obsSq = Any[]; o = 0
+            for (i, ob) in enumerate(config.observable)
+                n = length(ob)
+                push!(obsSum, ob isa AbstractArray ? flatSum[o+1:o+n] : flatSum[o+1])
+                push!(obsSq, ob isa AbstractArray ? flatSq[o+1:o+n] : flatSq[o+1]); o += n
+            end
             mean, std = MCIntegration._mean_std(obsSum, obsSq, block)
             push!(results, (mean, std, config))
         end
@@ -152,9 +186,11 @@ function integrate_b200(integrand; solver=:vegasmc, config=nothing, neval=1e4, n
     end
 end
 
+_mpi() = Base.require(Base.PkgId(Base.UUID("da04e1cc-30fd-572f-bb4f-1f8673147195"), "MPI"))
+
 "Attach an NCCL communicator: rank 0 creates the id, MPI carries the 128 bytes (replaces src/utility/parallel.jl)."
 function comm_init!(handle, comm)
-    MPI = Base.require(Base.PkgId(Base.UUID("da04e1cc-30fd-572f-bb4f-1f8673147195"), "MPI"))
+    MPI = _mpi()
     id = zeros(UInt8, 128)
     MPI.Comm_rank(comm) == 0 && ccall((:mci_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
     MPI.Bcast!(id, 0, comm)

@@ -174,6 +174,56 @@ def bubble_fermik(para: BubblePara | None = None) -> Integrand:
     return Integrand("bubble_fermik", _abi.F_BUBBLE_FERMIK, 1, tuple(ud))
 
 
+CUBA11_SOURCE = r"""
+// the 11 test integrands of the Cuba demo on the unit cube — the workload of the reference's own timing comparison,
+// example/benchmark/cuba/benchmark.jl:35-46 (t1 .. t11) evaluated together like its test2 / test3 (:62-89)
+template <class XA> __device__ void mci_user_integrand(const XA &X, const double *userdata, double *w) {
+  const double x = X(0, 1), y = X(0, 2), z = X(0, 3);
+  const double rsq = x * x + y * y + z * z, xyz = x * y * z;
+  w[0] = sin(x) * cos(y) * exp(z);
+  w[1] = 1.0 / ((x + y) * (x + y) + 0.003) * cos(y) * exp(z);
+  w[2] = 1.0 / (3.75 - cospi(x) - cospi(y) - cospi(z));
+  w[3] = fabs(rsq - 0.125);
+  w[4] = exp(-rsq);
+  w[5] = 1.0 / (1.0 - xyz + 1e-10);
+  w[6] = sqrt(fabs(x - y - z));
+  w[7] = exp(-xyz);
+  w[8] = x * x / (cos(x + y + z + 1.0) + 5.0);
+  w[9] = (x > 0.5) ? 1.0 / sqrt(xyz + 1e-5) : sqrt(xyz);
+  w[10] = (rsq < 1.0) ? 1.0 : 0.0;
+}
+"""
+# what the reference prints for this workload (comments of example/benchmark/cuba/benchmark.jl:121-131,148-158; Cuba's own
+# Vegas at 1e6 evaluations :104-114): (estimate, error)
+CUBA11_REFERENCE = {
+    "vegas": [(0.6662389036758806, 0.0009370223870430191), (5.256465932385138, 0.007319608002109763),
+              (0.3075345398612458, 0.00024117145696156536), (0.8788561548719585, 0.001217419754053441),
+              (0.4161189703927425, 0.00038591698396624104), (1.2031224696691054, 0.0014223459029237325),
+              (0.7100206908822683, 0.0007923510194941002), (0.8912870247582633, 0.0007501319218471907),
+              (0.08030537560622107, 0.00013380714402722626), (2.396395164639421, 0.0035658664551599913),
+              (0.5228992089675735, 0.0008064389576126581)],
+    "vegasmc": [(0.6636210504918344, 0.0020729178999968614), (5.242919616854019, 0.02260128007562855),
+                (0.30681239353464046, 0.0007850307152916456), (0.8780127497538999, 0.0027696019511458045),
+                (0.4144658711129951, 0.0011614492930177123), (1.2002718763309468, 0.003387144818775182),
+                (0.7095634473688555, 0.002250824818469535), (0.8880588065576488, 0.0022868326414642133),
+                (0.08033351807552817, 0.0002957920163406668), (2.417025425999495, 0.011011866855686713),
+                (0.5200202669127822, 0.0016844693189224066)],
+    "cuba_vegas_1e6": [(0.6646695631037952, 0.0005192264010635556), (5.268641443643625, 0.00937817147924112),
+                       (0.30780794363958314, 0.00016915694878023873), (0.8773127802819499, 0.0007272020591230047),
+                       (0.4165412720874263, 0.00026445560918383573), (1.2020166963125194, 0.0007653098425722113),
+                       (0.7096235523946715, 0.000489330660608438), (0.8912187300170151, 0.00040985374702141484),
+                       (0.08018533940010736, 8.303642721037487e-5), (2.3963590312091303, 0.0032631645439722893),
+                       (0.5236360284653482, 0.0005842099358276612)],
+    "wall_s": {"vegas": 0.246125, "vegasmc": 0.495360},  # @time of integrate(...; neval=1e5) — 10 iterations, one CPU thread
+}
+
+
+def cuba11() -> Integrand:
+    """The 11-integrand Cuba demo set of example/benchmark/cuba/benchmark.jl — the one workload the reference itself
+    publishes a wall time for — as a user-source integrand: var = Continuous(0, 1), dof = [[3]] * 11."""
+    return user_integrand(CUBA11_SOURCE, n_integrand=11, name="cuba11")
+
+
 REGISTRY = {
     f.name: f
     for f in (gauss_nd, log_over_sqrt, sphere1, sphere2, discrete_x, discrete2_const, lattice_pool, lattice_comp,

@@ -56,6 +56,11 @@ def case(name):
         "poly3": dict(f=I.poly3, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[1], [1], [1]]),
                       expect=[1 / 2, 1 / 3, 1 / 4]),
         "x2y2": dict(f=I.x2_plus_y2, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[2]]), expect=[2 / 3]),
+        # test/montecarlo.jl:166-198 (TestComplex1 / TestComplex2): Configuration(type=ComplexF64)
+        "complex1": dict(f=I.complex1, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[1]], type=complex),
+                         expect=[0.5 + 1j / 3]),
+        "complex2": dict(f=I.complex2, cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[1], [1]], type=complex),
+                         expect=[0.5 + 0j, 1j / 3]),
         # BASELINE C5 integrand
         "product4": dict(f=I.product4(), cfg=lambda: dict(var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4),
                          expect=[1.0, 1.0, 1.0, 1.0]),

@@ -101,6 +101,70 @@ def test_invalid_problems_are_rejected_before_touching_the_device(lib):
     assert e.value.code == _abi.ERR_UNSUPPORTED
 
 
+def test_round2_validation_rules(lib):
+    """describe_problem rejects, before any device is touched: a userdata blob shorter than the integrand reads (it would
+    be zero-filled silently), a NULL / oversized blob, a real/complex mismatch, the bin-by-Discrete measure with several
+    integrands under a chain solver (bins would be dropped), an mcmc start index that is no integrand."""
+    from mcintegration_jl_b200.engine import MCIError
+
+    def err(spec):
+        with pytest.raises(MCIError) as e:
+            mci.CudaEngine(spec)
+        return e.value
+
+    spec, _ = make_spec("bubble", "vegasmc")
+    spec.userdata = spec.userdata[:7]
+    e = err(spec)
+    assert e.code == _abi.ERR_INVALID and "userdata" in str(e)
+    spec, _ = make_spec("genz16_pool", "vegas")
+    spec.userdata = spec.userdata[:10]
+    assert err(spec).code == _abi.ERR_INVALID
+    spec, _ = make_spec("product4", "vegas")
+    spec.userdata = list(spec.userdata) + [0.0] * 100  # > MCI_MAX_USERDATA
+    assert err(spec).code == _abi.ERR_INVALID
+    spec, _ = make_spec("gauss10", "vegas")
+    spec.weight_kind = _abi.WEIGHT_COMPLEX
+    e = err(spec)
+    assert e.code == _abi.ERR_INVALID and "real" in str(e)
+    spec, _ = make_spec("complex2", "mcmc")
+    spec.weight_kind = _abi.WEIGHT_REAL
+    assert err(spec).code == _abi.ERR_INVALID
+    spec, _ = make_spec("sphere2", "mcmc")
+    spec.mcmc_start_idx = 5
+    assert err(spec).code == _abi.ERR_INVALID
+    # bin-by-Discrete with two integrands: fine under :vegas (no device here, so it fails LATER, with NO_DEVICE or not
+    # at all), refused under the chain solvers
+    import mcintegration_jl_b200 as M
+    cfg = M.Configuration(var=(M.Continuous(0.0, 1.0), M.Discrete(1, 4, adapt=False)), dof=[[2, 1], [3, 1]], obs=[[0.0] * 4, 0.0])
+    spec = M.problem_from_config(cfg, M.integrands.sphere2, solver=_abi.SOLVER_VEGASMC, measure_kind=_abi.MEASURE_BIN_BY_DISCRETE,
+                                 n_block=2, neval_per_block=100)
+    e = err(spec)
+    assert e.code == _abi.ERR_UNSUPPORTED and "one integrand" in str(e)
+
+
+def test_sixteen_integrands_are_accepted(lib):
+    """MCI_MAX_INTEGRAND = 16, the reference's own bound (MaxOrder, src/distribution/distribution.jl:59): a 16-integrand
+    user problem passes validation and compiles (NVRTC, no device needed); 17 are refused."""
+    import ctypes as C
+    src = """template <class XA> __device__ void mci_user_integrand(const XA &X, const double *ud, double *w) {
+      for (int i = 0; i < %d; ++i) w[i] = X(0, 1) * (i + 1); }"""
+    for n, ok in ((16, True), (17, False)):
+        cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[1]] * n) if ok else None
+        if ok:
+            f = mci.integrands.user_integrand(src % n, n_integrand=n)
+            spec = mci.problem_from_config(cfg, f, solver=_abi.SOLVER_VEGAS, measure_kind=0, n_block=2, neval_per_block=100)
+            p, keep = spec.to_ctypes()
+            log = C.create_string_buffer(4096)
+            rc = lib.mci_jit_check(C.byref(p), log, 4096)
+            assert rc == 0 or b"nvrtc" in log.value.lower(), log.value  # NVRTC may be absent on a CPU-only box
+        else:
+            spec, _ = make_spec("gauss10", "vegas")
+            spec.n_integrand = n
+            from mcintegration_jl_b200.engine import MCIError
+            with pytest.raises(MCIError):
+                mci.CudaEngine(spec)
+
+
 def test_no_device_means_no_fallback(lib):
     """Without a GPU mci_create must fail with MCI_ERR_NO_DEVICE — never compute on the CPU."""
     import torch

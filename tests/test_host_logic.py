@@ -182,3 +182,45 @@ def test_report_config_tables():
     out = buf.getvalue()
     assert "ChangeIntegrand" in out and "SwapVariable" in out and "Norm ->" in out and "0.400000" in out
     assert "Integrand evaluation = 1000" in out and "Discrete" in out
+
+
+def test_successive_calls_draw_fresh_samples():
+    """main.jl:136: every integrate() call seeds its solver streams with rand(config.rng, 1:10^6), so two calls on one
+    Configuration — a warm restart, or a plain repeat — use independent samples.  (The host driver is shared with the
+    oracle engine, which stands in for the GPU here.)"""
+    from oracle_lib import oracle_integrate
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[2]], seed=42)
+    a = oracle_integrate(integrands.sphere1, solver="vegas", neval=2000, niter=2, adapt=False, config=cfg)
+    b = oracle_integrate(integrands.sphere1, solver="vegas", neval=2000, niter=2, adapt=False, config=cfg)
+    assert a.mean[0] != b.mean[0]
+    # the sequence of seeds is itself reproducible from Configuration(seed=...)
+    cfg2 = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[2]], seed=42)
+    a2 = oracle_integrate(integrands.sphere1, solver="vegas", neval=2000, niter=2, adapt=False, config=cfg2)
+    assert a2.mean[0] == a.mean[0]
+
+
+def test_complex_block_statistics_and_average():
+    """main.jl:281,285,305-308 and statistics.jl:208-215: real and imaginary parts are squared, square-rooted and
+    averaged separately; std = r_std + i_std im"""
+    from mcintegration_jl_b200.engine import IterationStats
+    from mcintegration_jl_b200.statistics import average, mean_std
+    rng = np.random.default_rng(3)
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0), dof=[[1], [1]], type=complex)
+    B = 8
+    z = rng.normal(size=(B, 2)) + 1j * rng.normal(size=(B, 2))
+    norm = np.full(B, 100.0)
+    flat = np.empty((B, 4))
+    flat[:, 0::2], flat[:, 1::2] = (z * 100.0).real, (z * 100.0).imag
+    st = IterationStats(flat, norm, np.zeros(0), np.zeros(3), np.zeros((3, 3, 3)), np.zeros((3, 3, 3)), 0)
+    mean, std = block_statistics(st, cfg, B)
+    for o in range(2):
+        assert np.isclose(mean[o], z[:, o].mean())
+        mr, sr = mean_std(z[:, o].real.sum(), (z[:, o].real ** 2).sum(), B)
+        mi, si = mean_std(z[:, o].imag.sum(), (z[:, o].imag ** 2).sum(), B)
+        assert np.isclose(std[o].real, sr) and np.isclose(std[o].imag, si)
+    means = [complex(1 + 0.01 * k, 2 - 0.01 * k) for k in range(5)]
+    stds = [complex(0.1, 0.2)] * 5
+    m, e, c2 = average(means, stds, init=2)
+    mr, er, cr = average([x.real for x in means], [x.real for x in stds], init=2)
+    mi, ei, ci = average([x.imag for x in means], [x.imag for x in stds], init=2)
+    assert np.isclose(m, mr + 1j * mi) and np.isclose(e, er + 1j * ei) and np.isclose(c2, cr + 1j * ci)

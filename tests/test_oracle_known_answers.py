@@ -50,6 +50,24 @@ def test_mcmc_known_answers(name):
     check(res, c["expect"])
 
 
+def check_complex(res, expect, ratio=7.0):
+    """test/runtests.jl:11-21: real and imaginary parts are held to 7 sigma separately"""
+    for o, ex in enumerate(expect):
+        m, s = complex(res.mean[o]), complex(res.stdev[o])
+        assert abs(m.real - ex.real) < ratio * s.real + 1e-300, (o, m, s, ex)
+        assert abs(m.imag - ex.imag) < ratio * s.imag + 1e-300, (o, m, s, ex)
+
+
+@pytest.mark.parametrize("solver,neval", [("vegas", 2e5), ("vegasmc", 1e5), ("mcmc", 1e5)])
+@pytest.mark.parametrize("name", ["complex1", "complex2"])
+def test_complex_known_answers(name, solver, neval):
+    """test/montecarlo.jl:292-296, 325-330, 370-374: TestComplex1 -> 0.5 + i/3, TestComplex2 -> (0.5, i/3)"""
+    c = case(name)
+    res = oracle_integrate(c["f"], solver=solver, neval=neval, niter=10, seed=1234, **c["cfg"]())
+    check_complex(res, c["expect"])
+    assert all(np.iscomplexobj(np.asarray(m)) for m in res.mean)
+
+
 @pytest.mark.parametrize("solver", ["vegasmc", "mcmc"])
 def test_many_short_chains_with_burnin(solver):
     """The GPU decomposition — many short chains per block — on the oracle: 64 chains x 97 measured steps each with

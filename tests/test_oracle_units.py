@@ -455,3 +455,66 @@ def test_binned_measure_loops_against_independent_restatement(solver_name):
             assert st.neval == want["neval"]
     finally:
         eng.close()
+
+
+# ---- complex integrands (Configuration(type=ComplexF64), main.jl:276-286): the three loops on TestComplex2 -------------
+def _complex_loop_engine(solver, npb, measurefreq, thermal=0.1):
+    import mcintegration_jl_b200 as mci
+    from mcintegration_jl_b200 import integrands
+    from oracle_lib import OracleEngine
+    L = GOLD["loops_complex"]
+    cfg = mci.Configuration(var=mci.Continuous(0.0, 1.0, grid=L["grid"]), dof=[[1], [1]], seed=L["seed"], type=complex)
+    spec = mci.problem_from_config(cfg, integrands.complex2, solver=solver, measure_kind=0, n_block=L["n_block"],
+                                   neval_per_block=npb, measurefreq=measurefreq, walkers_per_block=1, thermal_ratio=thermal)
+    eng = OracleEngine(spec, nthreads=1)
+    eng.set_maps(grids=arr(L["grid"]), reweight=arr(L["reweight"]))
+    return eng, L
+
+
+@pytest.mark.parametrize("solver_name", ["vegas", "vegasmc", "mcmc"])
+def test_complex_loops_against_independent_restatement(solver_name):
+    """golden.json["loops_complex"]: f = (x, x^2 im) (test/montecarlo.jl:172-198) through the three whole loops, restated
+    in pure Python with Python's complex arithmetic (abs = hypot; complex x real component-wise, like Julia).  The
+    observables cross the boundary as (re, im) pairs: [block][integrand][2]."""
+    from mcintegration_jl_b200 import _abi
+    sid = {"vegas": _abi.SOLVER_VEGAS, "vegasmc": _abi.SOLVER_VEGASMC, "mcmc": _abi.SOLVER_MCMC}[solver_name]
+    L0 = GOLD["loops_complex"][solver_name]
+    eng, L = _complex_loop_engine(sid, L0.get("npb", L0.get("steps")), L0["measurefreq"], L0.get("thermal_ratio", 0.1))
+    try:
+        assert eng.obs_total == 4  # two complex observables = four doubles
+        eng.run_local(L["iter"])
+        got, want = _unpack(eng, eng.packed()), L0["out"]
+        np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(got["cnt"], want["norm"], rtol=1e-13)
+        np.testing.assert_allclose(got["hist"], want["hist"], rtol=1e-13)
+        if solver_name != "vegas":
+            np.testing.assert_allclose(got["visited"], want["visited"], rtol=1e-13)
+            assert int(got["neval"][0]) == want["neval"]
+        if solver_name == "mcmc":
+            np.testing.assert_array_equal(got["propose"], np.array(want["propose"]))
+            np.testing.assert_array_equal(got["accept"], np.array(want["accept"]))
+    finally:
+        eng.close()
+
+
+def test_mcmc_start_integrand_and_burnin_counters():
+    """`idx`, the integrand an :mcmc chain starts in (mcmc/montecarlo.jl:76): starting in the normalisation integrand needs
+    no evaluation and is always a valid start.  Extra burn-in steps (mci_problem_t.chain_burnin) touch no statistic:
+    propose / accept / neval count the reference's loop only."""
+    from cases import make_spec
+    from oracle_lib import OracleEngine
+    stats = {}
+    for start, burn in ((0, 0), (3, 0), (0, 500)):
+        spec, _ = make_spec("sphere2", "mcmc", n_block=2, neval_per_block=400, walkers=1, chain_burnin=burn, seed=9)
+        spec.mcmc_start_idx = start
+        eng = OracleEngine(spec, nthreads=1)
+        try:
+            stats[(start, burn)] = eng.run_iteration(0)
+        finally:
+            eng.close()
+    a, b, c = stats[(0, 0)], stats[(3, 0)], stats[(0, 500)]
+    assert not np.array_equal(a.visited, b.visited)  # a different start, a different chain
+    total = 2 * (400 + 40)                            # neval + nburnin steps per block, every one counted in visited
+    for st in (a, b, c):
+        assert abs(st.visited.sum() - 3 * 3e-8 - total) < 1e-6
+        assert (st.propose - 3e-8).sum() <= total + 1e-6 and st.neval <= total  # burn-in steps add nothing
