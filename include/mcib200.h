@@ -194,8 +194,15 @@ enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };
  *   SMEM_ATOMIC  one fp64 copy per CTA in shared memory, red.shared.add.f64
  *   GLOBAL_RED   RED.E.ADD.F64 into a few L2-resident copies (layouts whose histograms do not fit in shared memory)
  *   WARP_PRIVATE one copy per warp, MATCH.ANY conflict ranking, no atomics (generic VEGAS kernel only; kept for study)
- *   SMEM_STRIPED 16 bank-striped copies per CTA, one 1024-thread CTA per SM (single-pool VEGAS kernel; AUTO picks it) */
-enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4 };
+ *   SMEM_STRIPED 16 bank-striped copies per CTA, one 1024-thread CTA per SM (single-pool VEGAS kernel; AUTO picks it)
+ *   SMEM_FIXED   (single-pool VEGAS kernel, opt-in) the striped copies as 64-bit FIXED-POINT cells of two u32 limbs updated
+ *                with the native shared-memory integer add (sm_100a has no native shared fp64 add: every fp64 update is a
+ *                load + add + compare-and-swap).  A sample's weight is scaled by a power of two chosen on the device from
+ *                the previous iteration's histogram, rounded to nearest once and added exactly: the sums are
+ *                order-independent, i.e. bit-reproducible.  The first iteration of a handle (no scale yet) runs SMEM_STRIPED;
+ *                a weight beyond the fixed-point range makes mci_fetch_iteration fail with MCI_ERR_NUMERIC. */
+enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4,
+       MCI_HIST_SMEM_FIXED = 5 };
 
 /*
  * Per-iteration statistics handed back to the host: what `_block!` +

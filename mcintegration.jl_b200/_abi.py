@@ -31,7 +31,7 @@ LEAF_CONTINUOUS, LEAF_DISCRETE, LEAF_FERMIK = 0, 1, 2
 MEASURE_DEFAULT, MEASURE_BIN_BY_DISCRETE, MEASURE_USER = 0, 1, 2
 JIT_AUTO, JIT_ON, JIT_OFF = 0, 1, 2
 WEIGHT_REAL, WEIGHT_COMPLEX = 0, 1
-HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED = 0, 1, 2, 3, 4
+HIST_AUTO, HIST_SMEM_ATOMIC, HIST_GLOBAL_RED, HIST_WARP_PRIVATE, HIST_SMEM_STRIPED, HIST_SMEM_FIXED = 0, 1, 2, 3, 4, 5
 
 # enum mci_integrand_id
 F_GAUSS_ND = 1

@@ -93,8 +93,8 @@ struct mci_handle_t {
   double *d_alpha = nullptr, *d_gmaps = nullptr;
   int *d_leaf_grid_off = nullptr, *d_leaf_dist_off = nullptr, *d_leaf_acc_off = nullptr;
   double *d_tile_obs = nullptr, *d_tile_cnt = nullptr, *d_cta_hist = nullptr, *d_cta_stats = nullptr, *d_packed = nullptr;
-  unsigned long long *d_flags = nullptr;
-  int *d_err = nullptr;
+  unsigned long long *d_flags = nullptr; /* [4]: non-finite weights, mcmc walkers without a start, fixed-point range, spare */
+  int *d_err = nullptr, *d_fixed_exp = nullptr;
   /* the buffers above are carved out of three allocations (cudaMalloc / cudaFree / cudaMallocHost cost 0.1-1 ms each
    * and synchronise the device: a job of the reference's default size, neval = 1e4, is over in 4 ms):
    * the fixed state, the per-launch partials (re-planned by mci_set_partition) and the pinned host mirrors */
@@ -109,6 +109,8 @@ struct mci_handle_t {
   int *h_err = nullptr;
   /* launch plan */
   const void *kernel = nullptr;
+  const void *kernel_first = nullptr; /* HIST_SMEM_FIXED: the fp64 striped kernel that runs while no scale exists yet */
+  bool fixed_scale_ready = false;
   const char *kernel_name = "";
   bool is_pool = false;
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
@@ -264,7 +266,7 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   char name[160];
   switch (kind) {
     case 0:
-      if (mode == HIST_SMEM_STRIPED && P.maxdof[0] > 20) return nullptr; /* 1024 threads x 64 registers */
+      if ((mode == HIST_SMEM_STRIPED || mode == HIST_SMEM_FIXED) && P.maxdof[0] > 20) return nullptr; /* 1024 threads x 64 registers */
       snprintf(name, sizeof name, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0], mode, threads, exact ? "true" : "false");
       break;
     case 1: snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, GENERIC_THREADS); break;
@@ -272,7 +274,8 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
     default: snprintf(name, sizeof name, "mci::mcmc_kernel<%d>", P.fid); break;
   }
   std::vector<std::string> exprs{name};
-  if (kind <= 1) { char t[64]; snprintf(t, sizeof t, "mci::vegas_trace_kernel<%d>", P.fid); exprs.push_back(t); }
+  if (kind == 0) { char t[80]; snprintf(t, sizeof t, "mci::vegas_pool_trace_kernel<%d, %d>", P.fid, P.maxdof[0]); exprs.push_back(t); }
+  if (kind == 1) { char t[64]; snprintf(t, sizeof t, "mci::vegas_trace_kernel<%d>", P.fid); exprs.push_back(t); }
   std::vector<const void *> ks;
   std::string err;
   int rc = jit_compile(P, h->user_source.c_str(), exprs, ks, err);
@@ -344,14 +347,25 @@ int plan(mci_handle_t *h) {
       /* 16 bank-striped copies of the histogram, one 1024-thread CTA per SM, when they fit */
       const size_t red_s = (size_t)(POOL_THREADS_STRIPED / 32) * (P.ni + 1) * 8;
       const bool striped_fits = (size_t)POOL_MAP_REP * map_bytes + (size_t)STRIPE * hist_bytes + red_s <= SMEM_MAX;
-      if (P.any_adapt && striped_fits && (p.hist_policy == MCI_HIST_SMEM_STRIPED || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_STRIPED))) {
-        mode = HIST_SMEM_STRIPED; threads = POOL_THREADS_STRIPED; nwarp = threads / 32; red = red_s;
+      /* fixed-point cells: built-in integrands with an ahead-of-time instantiation only (two kernels per handle) */
+      const bool want_fixed = p.hist_policy == MCI_HIST_SMEM_FIXED && P.fid != MCI_F_USER && P.maxdof[0] <= 20 &&
+                              lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_FIXED, nullptr) != nullptr;
+      if (P.any_adapt && striped_fits && (p.hist_policy == MCI_HIST_SMEM_STRIPED || want_fixed || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_STRIPED))) {
+        mode = want_fixed ? HIST_SMEM_FIXED : HIST_SMEM_STRIPED; threads = POOL_THREADS_STRIPED; nwarp = threads / 32; red = red_s;
         hs = (size_t)STRIPE * hist_bytes + (size_t)(POOL_MAP_REP - 1) * map_bytes; h->maps_in_smem = 1;
       }
       if (h->maps_in_smem) {
-        const void *k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
-        if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
-        if (!k && mode == HIST_SMEM_STRIPED) { /* no striped instantiation for this many slots: one shared copy */
+        const void *k = nullptr;
+        if (mode == HIST_SMEM_FIXED) { /* iterations without a scale yet run the fp64 striped kernel of the same shape */
+          k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_FIXED, &h->kernel_name);
+          h->kernel_first = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_STRIPED, nullptr);
+          if (!h->kernel_first) k = nullptr;
+          if (k) h->use_jit = false;
+        } else {
+          k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
+          if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
+        }
+        if (!k && (mode == HIST_SMEM_STRIPED || mode == HIST_SMEM_FIXED)) { /* no striped instantiation for this many slots: one shared copy */
           threads = POOL_THREADS; nwarp = threads / 32; red = (size_t)nwarp * (P.ni + 1) * 8;
           mode = pick_hist(nwarp, red, false); hs = hist_smem(mode, nwarp);
           if (h->maps_in_smem) k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
@@ -439,6 +453,7 @@ int plan(mci_handle_t *h) {
     h->maps_in_smem = best_mis;
   }
   CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  if (h->hist_mode == HIST_SMEM_FIXED) CU(h, cudaFuncSetAttribute(h->kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   int occ = 0;
   CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->threads, h->smem));
   if (occ < 1) return fail(h, MCI_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", h->kernel_name, h->smem);
@@ -780,21 +795,23 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
     const size_t o_rw = D.reserve<double>(nd), o_goal = D.reserve<double>(nd), o_alpha = D.reserve<double>(nleaf);
     const size_t o_gmaps = D.reserve<double>(mo + 2);
     const size_t o_lg = D.reserve<int>(nleaf), o_ld = D.reserve<int>(nleaf), o_la = D.reserve<int>(nleaf);
-    const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(2), o_err = D.reserve<int>(1);
+    const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(4), o_err = D.reserve<int>(1);
+    const size_t o_fx = D.reserve<int>(1);
     TRY(arena_device(h, D, &h->d_state_arena, &h->state_cap, false));
     h->d_grids = D.at<double>(o_grids); h->d_dist = D.at<double>(o_dist); h->d_accum = D.at<double>(o_accum);
     h->d_reweight = D.at<double>(o_rw); h->d_goal = D.at<double>(o_goal); h->d_alpha = D.at<double>(o_alpha);
     h->d_gmaps = D.at<double>(o_gmaps);
     h->d_leaf_grid_off = D.at<int>(o_lg); h->d_leaf_dist_off = D.at<int>(o_ld); h->d_leaf_acc_off = D.at<int>(o_la);
     h->d_packed = D.at<double>(o_packed); h->d_flags = D.at<unsigned long long>(o_flags); h->d_err = D.at<int>(o_err);
+    h->d_fixed_exp = D.at<int>(o_fx);
     Arena H;
-    const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(2), ho_err = H.reserve<int>(1);
+    const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(4), ho_err = H.reserve<int>(1);
     const size_t ho_init = H.reserve<char>(D.total); /* staging image of the device state */
     CUT(g_blocks.get(true, 0, H.total, &h->h_arena, &h->host_cap));
     H.base = static_cast<char *>(h->h_arena);
     h->h_packed = H.at<double>(ho_packed); h->h_flags = H.at<unsigned long long>(ho_flags); h->h_err = H.at<int>(ho_err);
     memset(h->h_packed, 0, Y.len * sizeof(double));
-    h->h_flags[0] = h->h_flags[1] = 0; *h->h_err = 0;
+    h->h_flags[0] = h->h_flags[1] = h->h_flags[2] = h->h_flags[3] = 0; *h->h_err = 0;
     char *img = H.at<char>(ho_init);
     memset(img, 0, D.total);
     auto at = [&](size_t off) { return img + off; };
@@ -821,6 +838,7 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
       }
     }
     for (int d = 0; d < nd; ++d) rw[d] = 1.0 / nd;
+    *reinterpret_cast<int *>(at(o_fx)) = FIXED_EXP_INVALID;
     CUT(cudaMemcpyAsync(h->d_state_arena, img, D.total, cudaMemcpyHostToDevice, h->stream));
     /* the staging image lives in the pinned block until the handle dies, so the copy needs no synchronisation here */
   }
@@ -882,7 +900,7 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   const int n_local = p.n_block / h->world;
   CU(h, cudaEventRecord(h->ev_iter0, h->stream));
   if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
-  CU(h, cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned long long), h->stream));
+  CU(h, cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(unsigned long long), h->stream));
   if (h->hist_mode == HIST_GLOBAL_RED)
     CU(h, cudaMemsetAsync(h->d_cta_hist, 0, (size_t)h->n_hist_copies * h->hist_len * sizeof(double), h->stream));
   void *args[2];
@@ -890,7 +908,7 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   ChainArgs CA;
   if (p.solver == MCI_SOLVER_VEGAS) {
     FA.gmaps = h->d_gmaps; FA.tile_obs = h->d_tile_obs; FA.tile_cnt = h->d_tile_cnt; FA.cta_hist = h->d_cta_hist;
-    FA.flags = h->d_flags; FA.iter = iter; FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
+    FA.flags = h->d_flags; FA.fixed_exp = h->d_fixed_exp; FA.iter = iter; FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
     FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
     FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
     args[0] = &h->dp; args[1] = &FA;
@@ -905,7 +923,11 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);
   if (!h->ev_fill0[slot]) { CU(h, cudaEventCreate(&h->ev_fill0[slot])); CU(h, cudaEventCreate(&h->ev_fill1[slot])); }
   CU(h, cudaEventRecord(h->ev_fill0[slot], h->stream));
-  CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
+  /* fixed-point histogram: the scale of an iteration comes from the one before it; the first runs the fp64 striped kernel */
+  const bool fixed_now = h->hist_mode == HIST_SMEM_FIXED && h->fixed_scale_ready;
+  if (h->hist_mode == HIST_SMEM_FIXED) FA.hist_mode = fixed_now ? HIST_SMEM_FIXED : HIST_SMEM_STRIPED;
+  CU(h, cudaLaunchKernel(h->hist_mode == HIST_SMEM_FIXED && !fixed_now ? h->kernel_first : h->kernel, dim3(h->grid), dim3(h->threads), args,
+                         h->smem, h->stream));
   CU(h, cudaEventRecord(h->ev_fill1[slot], h->stream));
   h->n_iterations++;
   h->launches++;
@@ -928,9 +950,15 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
     int rc = g_nccl.AllReduce(h->d_packed, h->d_packed, (size_t)h->Y.len, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream);
     if (rc != 0) return fail(h, MCI_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   }
+  if (h->hist_mode == HIST_SMEM_FIXED) { /* the scale of the next iteration, from the (all-reduced) statistics of this one */
+    fixed_scale_kernel<<<1, 256, 0, h->stream>>>(h->Y, h->d_packed, h->dp.maxdof[0], h->d_fixed_exp);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    h->fixed_scale_ready = true;
+  }
   if (with_d2h) {
     CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_flags, h->d_flags, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   }
   CU(h, cudaEventRecord(h->ev_iter1, h->stream));
   h->have_iteration = true;
@@ -953,6 +981,9 @@ static int unpack_iteration(mci_handle_t *h, const double *pk, const unsigned lo
   if (out->accept) for (int i = 0; i < Y.pa_len; ++i) out->accept[i] = B1 * 1.0e-10 + pk[Y.off_accept + i];
   if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
   h->nonfinite = flags[0];
+  if (flags[2])
+    return fail(h, MCI_ERR_NUMERIC, "fixed-point histogram (MCI_HIST_SMEM_FIXED): a weight or a CTA total left the 64-bit range "
+                                    "(the scale follows the previous iteration's mean weight); use another hist_policy");
   if (flags[1]) /* mcmc/montecarlo.jl:109-113 */
     return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #%d integrand nonzero!", h->dp.start_idx + 1);
   for (int b = 0; b < nb; ++b)
@@ -1043,7 +1074,7 @@ int mci_run_iterations(mci_handle_t *h, uint64_t first_iter, int32_t niter, doub
   if (!h || niter < 1) return MCI_ERR_INVALID;
   CU(h, cudaSetDevice(h->device));
   const PackedLayout &Y = h->Y;
-  const size_t rec = (size_t)Y.len + 2; /* packed statistics + the two flag words, in 8-byte slots */
+  const size_t rec = (size_t)Y.len + 4; /* packed statistics + the four flag words, in 8-byte slots */
   const size_t bytes = rec * (size_t)niter * sizeof(double);
   if (h->history_cap < bytes) {
     g_blocks.put(false, h->device, h->d_history, h->history_cap);
@@ -1086,7 +1117,7 @@ int mci_run_iterations(mci_handle_t *h, uint64_t first_iter, int32_t niter, doub
   CU(h, cudaStreamSynchronize(h->stream));
   /* leave the handle as after a fetch of the last iteration */
   memcpy(h->h_packed, hh + rec * (niter - 1), Y.len * sizeof(double));
-  memcpy(h->h_flags, hh + rec * (niter - 1) + Y.len, 2 * sizeof(unsigned long long));
+  memcpy(h->h_flags, hh + rec * (niter - 1) + Y.len, 4 * sizeof(unsigned long long));
   {
     const int slot = (int)((h->n_iterations - 1) % mci_handle_t::FILL_RING);
     cudaEventElapsedTime(&h->fill_ms, h->ev_fill0[slot], h->ev_fill1[slot]);
@@ -1156,7 +1187,10 @@ int mci_trace_samples(mci_handle_t *h, uint64_t iter, int32_t block, uint64_t fi
   if (h->p.solver != MCI_SOLVER_VEGAS) return fail(h, MCI_ERR_UNSUPPORTED, "mci_trace_samples: VEGAS sampler only");
   if (count == 0) return MCI_OK;
   CU(h, cudaSetDevice(h->device));
-  const void *k = h->use_jit ? h->trace_kernel : lookup_vegas_trace(h->dp.fid);
+  /* a handle whose fill kernel is the pool kernel is probed through the pool kernel's own draw code */
+  const void *k = h->trace_kernel; /* set when the fill kernel is an NVRTC build */
+  if (!k && h->is_pool) k = lookup_vegas_pool_trace(h->dp.fid, h->dp.maxdof[0]);
+  if (!k) k = lookup_vegas_trace(h->dp.fid);
   if (!k) return fail(h, MCI_ERR_UNSUPPORTED, "no trace kernel for integrand %d", h->dp.fid);
   if (h->maps_dirty) { int rc = enqueue_build_maps(h); if (rc) return rc; }
   const int nd = h->dp.n_draw, ni = h->ni * h->dp.wdim;
@@ -1208,7 +1242,8 @@ int mci_jit_check(const mci_problem_t *p, char *log, int32_t log_cap) {
       snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, GENERIC_THREADS);
     }
     exprs.push_back(name);
-    snprintf(name, sizeof name, "mci::vegas_trace_kernel<%d>", P.fid);
+    if (pool) snprintf(name, sizeof name, "mci::vegas_pool_trace_kernel<%d, %d>", P.fid, P.maxdof[0]);
+    else snprintf(name, sizeof name, "mci::vegas_trace_kernel<%d>", P.fid);
     exprs.push_back(name);
   } else {
     snprintf(name, sizeof name, p->solver == MCI_SOLVER_VEGASMC ? "mci::vegasmc_kernel<%d>" : "mci::mcmc_kernel<%d>", P.fid);

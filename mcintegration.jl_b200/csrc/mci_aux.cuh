@@ -297,11 +297,33 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
   if (threadIdx.x == 0 && s_bad) atomicOr(err, 1);
 }
 
+/* HIST_SMEM_FIXED: exponent of the next iteration's fixed-point scale from this iteration's (all-reduced) statistics.
+ * mean weight per histogram add = sum(hist) / (measured samples x slots); E = FIXED_TARGET_LOG2 - ceil(log2(mean)) */
+__global__ void fixed_scale_kernel(PackedLayout Y, const double *__restrict__ packed, int slots, int *__restrict__ fixed_exp) {
+  __shared__ double s_red[32];
+  double h = 0.0, n = 0.0;
+  for (int i = threadIdx.x; i < Y.hist_len; i += blockDim.x) h += packed[Y.off_hist + i];
+  for (int i = threadIdx.x; i < Y.n_block; i += blockDim.x) n += packed[Y.off_cnt + i];
+  h = cta_allsum(h, s_red);
+  n = cta_allsum(n, s_red);
+  if (threadIdx.x == 0) {
+    const double mean = h / (n * (double)slots);
+    int e = FIXED_EXP_INVALID;
+    if (isfinite(mean) && mean > 0.0) {
+      int ex;
+      frexp(mean, &ex); /* mean = f 2^ex, f in [0.5, 1) */
+      e = FIXED_TARGET_LOG2 - ex;
+      if (e > 1000 || e < -1000) e = FIXED_EXP_INVALID;
+    }
+    *fixed_exp = e;
+  }
+}
+
 /* mci_run_iterations: keep this iteration's packed statistics and flags in the per-call history (one launch) */
 __global__ void snapshot_kernel(const double *__restrict__ packed, int len, const unsigned long long *__restrict__ flags,
                                 double *__restrict__ rec) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) rec[i] = packed[i];
-  if (blockIdx.x == 0 && threadIdx.x < 2) reinterpret_cast<unsigned long long *>(rec + len)[threadIdx.x] = flags[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < 4) reinterpret_cast<unsigned long long *>(rec + len)[threadIdx.x] = flags[threadIdx.x];
 }
 
 /* doReweight!: main.jl:322-346; goal may be NULL */

@@ -35,8 +35,19 @@ constexpr int HIST_WARP_PRIVATE = 3; /* one private histogram per warp, conflict
 constexpr int HIST_SMEM_STRIPED = 4; /* CTA-shared fp64 histogram in 16 bank-striped copies: lane l updates copy l%16, which
                                         lives in bank pair l%16, so neither the LDS.64 nor the CAS of a random-bin scatter
                                         ever has a bank conflict (2 wavefronts per instruction instead of ~10)           */
-constexpr int STRIPE_LOG2 = 4;
+constexpr int HIST_SMEM_FIXED = 5;   /* the striped copies as 64-bit fixed-point cells (two u32 limbs, native ATOMS.ADD) */
+#ifndef MCI_STRIPE_LOG2
+#define MCI_STRIPE_LOG2 4
+#endif
+constexpr int STRIPE_LOG2 = MCI_STRIPE_LOG2;
 constexpr int STRIPE = 1 << STRIPE_LOG2;
+/* fixed-point histogram: a weight w2 is added as round(w2 * 2^E); E is chosen so that the MEAN weight of the previous
+ * iteration maps to 2^FIXED_TARGET_LOG2 = 2^30: a bin that collects n adds of typical size carries a rounding error of
+ * ~0.5 sqrt(n) units on n 2^30, i.e. 1.5e-13 relative for the 1e7 adds of a BASELINE-size iteration.  Range: every cell
+ * of a CTA is bounded by the sum of all weights the CTA adds (~2^53 for 7e6 samples of mean weight), which the kernel
+ * checks against 2^63 — the mean may grow 2^10-fold between two iterations, a single weight may be 2^32 times the mean */
+constexpr int FIXED_TARGET_LOG2 = 30;
+constexpr int FIXED_EXP_INVALID = -100000;
 #ifndef MCI_POOL_MAP_REP
 #define MCI_POOL_MAP_REP 4
 #endif
@@ -286,6 +297,22 @@ __device__ __forceinline__ void map_index(int nbins, double nbins_d, double u, i
   double fl = __dsub_rn(f, MAGIC);
   dy = __dsub_rn(t, fl);
   iy = min(i, nbins - 1);
+}
+
+/* The pool kernel's form of the same draw, two instructions shorter and bit-identical (tests: pool trace == oracle):
+ *  - the uniform is u = m - 1 with m in [1, 2) built from the top 52 bits of the Philox words (u52 without its
+ *    subtraction).  m - 1 is exact, so t = RN(u * N) = RN(m * N - N) = fma(m, N, -N): one DFMA replaces DADD + DMUL;
+ *  - no clamp of the increment: u <= 1 - 2^-52, so the exact product is <= N - N 2^-52 <= N - ulp(N) (ulp(N) = 2^(e-52)
+ *    <= N 2^-52 for 2^e <= N), which is representable or rounds to a value below N: floor(RN(u N)) <= N - 1 for every N. */
+__device__ __forceinline__ double m52(uint32_t hi, uint32_t lo) { /* 1 + k 2^-52, k = top 52 bits of (hi:lo) */
+  return __hiloint2double((int)((hi >> 12) | 0x3FF00000u), (int)__funnelshift_r(lo, hi, 12));
+}
+__device__ __forceinline__ void map_index_m(double nbins_d, double neg_nbins_d, double m, int &iy, double &dy) {
+  const double MAGIC = 4503599627370496.0;
+  const double t = __fma_rn(m, nbins_d, neg_nbins_d);
+  const double f = __dadd_rd(t, MAGIC);
+  iy = __double2loint(f);
+  dy = __dsub_rn(t, __dsub_rn(f, MAGIC));
 }
 
 /* locate (common.jl:8-36) clamped into the table instead of throwing; returns 0-based index g

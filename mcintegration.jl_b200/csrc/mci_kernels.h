@@ -15,6 +15,8 @@ const void *lookup_vegas_pool(int fid, int d, bool exact, int hist_mode, const c
 /* vegas, any layout */
 const void *lookup_vegas_generic(int fid, const char **name);
 const void *lookup_vegas_trace(int fid);
+/* the same probe through the pool kernel's own draw code (NULL: this integrand has no pool instantiation) */
+const void *lookup_vegas_pool_trace(int fid, int d);
 /* Markov-chain solvers */
 const void *lookup_vegasmc(int fid, const char **name);
 const void *lookup_mcmc(int fid, const char **name);

@@ -21,6 +21,15 @@
 #pragma once
 #include "mci_integrands.cuh"
 
+/* updates of one sample issued together (loads / adds back to back, then the dependent halves) */
+#ifndef MCI_HIST_BATCH
+#define MCI_HIST_BATCH 5
+#endif
+/* fixed-point cells: add the high limb unconditionally (1) or only when it is non-zero (0) */
+#ifndef MCI_FIXED_HI_ALWAYS
+#define MCI_FIXED_HI_ALWAYS 1
+#endif
+
 namespace mci {
 
 struct FillArgs {
@@ -28,7 +37,8 @@ struct FillArgs {
   double *tile_obs;      /* [n_tiles_total][obs_total]                                             */
   double *tile_cnt;      /* [n_tiles_total] measured samples of the tile                            */
   double *cta_hist;      /* [n_hist_copies][hist_len] partial histograms (zeroed before launch)     */
-  unsigned long long *flags; /* [0] = number of non-finite weights seen                            */
+  unsigned long long *flags; /* [0] = number of non-finite weights seen, [2] = fixed-point histogram range exceeded */
+  const int *fixed_exp;  /* HIST_SMEM_FIXED: the exponent E of this iteration's scale 2^E (device memory)      */
   uint64_t iter;
   uint64_t neval_per_block;
   int n_local_blocks, rank, world; /* this rank runs blocks b = rank + k*world                      */
@@ -76,11 +86,12 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
       const unsigned long long nw = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[q]) + v);
       asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(got[q]) : "r"(a[q]), "l"(old[q]), "l"(nw) : "memory");
     }
-  bool lost = false;
+  /* did any of the B swaps lose?  OR of the XORs: two LOP3 per update (the 64-bit compares cost 3.6 ISETP each) */
+  unsigned long long diff = 0;
 #pragma unroll
   for (int q = 0; q < B; ++q)
-    if (p0 + q < MAXD && (EXACT || p0 + q < n)) lost = lost || (got[q] != old[q]);
-  if (lost) {
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) diff |= got[q] ^ old[q];
+  if (diff != 0) {
 #pragma unroll
     for (int q = 0; q < B; ++q)
       if (p0 + q < MAXD && (EXACT || p0 + q < n))
@@ -88,9 +99,37 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
   }
 }
 
-#ifndef MCI_HIST_BATCH
-#define MCI_HIST_BATCH 5
+/* HIST_SMEM_FIXED: hist[bin] += X on a 64-bit fixed-point cell of two u32 limbs (lo at saddr, hi at saddr + 4).  The
+ * low limb is added with the returning form of the native shared-memory integer add; its carry — (old + lo) wrapped —
+ * joins the high limb, which a second, non-returning add applies.  Integer adds commute: the cell ends up with the
+ * exact sum whatever the interleaving of threads, so the histogram is bit-reproducible. */
+template <int B, int MAXD, bool EXACT>
+__device__ __forceinline__ void fixed_batch(uint32_t hist_saddr, const int *bin, int p0, int n, uint32_t xlo, uint32_t xhi) {
+  uint32_t a[B], old[B];
+#pragma unroll
+  for (int q = 0; q < B; ++q) /* the B low-limb adds go out back to back: their return values are independent */
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) {
+      a[q] = hist_saddr + (8u * STRIPE) * (uint32_t)bin[p0 + q];
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[q]) : "r"(a[q]), "r"(xlo) : "memory");
+    }
+#pragma unroll
+  for (int q = 0; q < B; ++q) /* carry + high limb */
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) {
+#if MCI_FIXED_HI_ALWAYS
+      /* unconditional: 5 instructions per update (address, add, carry, high word, add).  ptxas turns a predicated
+       * shared-memory atomic into a branch around it (+4 instructions), which costs more than the add it skips */
+      asm volatile("{\n\t.reg .u32 t, h;\n\tadd.cc.u32 t, %0, %1;\n\taddc.u32 h, %2, 0;\n\t"
+                   "red.shared.add.u32 [%3+4], h;\n\t}"
+                   ::"r"(old[q]), "r"(xlo), "r"(xhi), "r"(a[q]) : "memory");
+#else
+      asm volatile("{\n\t.reg .u32 t, h;\n\t.reg .pred q;\n\tadd.cc.u32 t, %0, %1;\n\taddc.u32 h, %2, 0;\n\t"
+                   "setp.ne.u32 q, h, 0;\n\t@q red.shared.add.u32 [%3+4], h;\n\t}"
+                   ::"r"(old[q]), "r"(xlo), "r"(xhi), "r"(a[q]) : "memory");
 #endif
+    }
+}
+
+
 
 /* The pool's map in shared memory.
  *   REP == 1: one table of (edge, width) pairs, one LDS.128 per draw.  32 lanes at random increments conflict on the 8
@@ -111,42 +150,72 @@ struct PoolMap {
   }
 };
 
-template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD, int REP>
-__device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M,
-                                            uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
-                                            bool active, double *acc, int &cnt, unsigned long long &bad) {
-  using F = Integrand<FID>;
-  constexpr int NI = F::NI;
-  constexpr bool CAN_PAD = NI > 1 && !EXACT; /* one integrand, or EXACT: dof == maxdof by construction */
-  const int nbins = P.leaf[0].nbins;
-  const double nbins_d = P.leaf[0].nbins_d;
+/* jac = prod_p N dx_p accumulated as (N^h dx_1 ... dx_h) (N^(d-h) dx_(h+1) ... dx_d), h = ceil(d / 2): one DMUL per
+ * slot instead of two (N dx, then jac *= it).  The powers of N enter in two halves so that the partial products stay
+ * as far from the over- / underflow thresholds as the per-slot products N dx themselves (N^12 ~ 1e36 at most for the
+ * largest pool); the association differs from the reference's prod 1/prob by a few ulp (L0: jac rtol 1e-13). */
+template <int MAXD, bool EXACT>
+struct PoolJac {
+  double n_lo, n_hi; /* N^h, N^(d-h) */
+  int h;
+  __device__ __forceinline__ void init(double nbins_d, int d) {
+    h = (d + 1) >> 1;
+    n_lo = n_hi = 1.0;
+#pragma unroll
+    for (int p = 0; p < (MAXD + 1) / 2; ++p) {
+      if (p < h) n_lo *= nbins_d;
+      if (p < d - h) n_hi *= nbins_d;
+    }
+  }
+};
+
+/* the draws of one sample on the pool: slots 1..d from Philox calls (s, j, block), two slots per call
+ * (vegas/montecarlo.jl:122-131).  Shared by the fill kernel and by the pool-path trace kernel (L0 parity probe). */
+template <int MAXD, bool EXACT, bool CAN_PAD, int REP>
+__device__ __forceinline__ void pool_draw(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M, const PoolJac<MAXD, EXACT> &J,
+                                          uint64_t s, uint32_t block, PoolX<MAXD> &X, int *bin, double *prob, double &jac) {
+  const double nbins_d = P.leaf[0].nbins_d, neg_nbins_d = -nbins_d;
   const int d = EXACT ? MAXD : P.maxdof[0];
-  PoolX<MAXD> X;
-  int bin[MAXD];
-  double prob[CAN_PAD ? MAXD : 1]; /* only live when P.need_pad */
-  double jac = 1.0;
+  jac = J.n_lo;
 #pragma unroll
   for (int j = 0; j < (MAXD + 1) / 2; ++j) {
     if (2 * j < d) {
       uint32_t o0, o1, o2, o3;
       philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
       double dx, dy, g;
-      map_index(nbins, nbins_d, u52(o0, o1), bin[2 * j], dy);
+      map_index_m(nbins_d, neg_nbins_d, m52(o0, o1), bin[2 * j], dy);
       M.lookup(bin[2 * j], g, dx);
       X.v[2 * j] = __dadd_rn(g, __dmul_rn(dy, dx));
-      double ndx = __dmul_rn(nbins_d, dx);
-      jac *= ndx;
-      if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / ndx;
+      if (2 * j == J.h) jac *= J.n_hi;
+      jac *= dx;
+      if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / __dmul_rn(nbins_d, dx);
       if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
-        map_index(nbins, nbins_d, u52(o2, o3), bin[2 * j + 1], dy);
+        map_index_m(nbins_d, neg_nbins_d, m52(o2, o3), bin[2 * j + 1], dy);
         M.lookup(bin[2 * j + 1], g, dx);
         X.v[2 * j + 1] = __dadd_rn(g, __dmul_rn(dy, dx));
-        ndx = __dmul_rn(nbins_d, dx);
-        jac *= ndx;
-        if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / ndx;
+        if (2 * j + 1 == J.h) jac *= J.n_hi;
+        jac *= dx;
+        if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / __dmul_rn(nbins_d, dx);
       }
     }
   }
+  if (J.h >= d) jac *= J.n_hi; /* d == 1: the second half is empty (n_hi = 1) */
+}
+
+template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD, int REP>
+__device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M, const PoolJac<MAXD, EXACT> &J,
+                                            uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
+                                            bool active, double *acc, int &cnt, unsigned long long &bad, double fx_scale,
+                                            double &fx_total) {
+  using F = Integrand<FID>;
+  constexpr int NI = F::NI;
+  constexpr bool CAN_PAD = NI > 1 && !EXACT; /* one integrand, or EXACT: dof == maxdof by construction */
+  const int d = EXACT ? MAXD : P.maxdof[0];
+  PoolX<MAXD> X;
+  int bin[MAXD];
+  double prob[CAN_PAD ? MAXD : 1]; /* only live when P.need_pad */
+  double jac;
+  pool_draw<MAXD, EXACT, CAN_PAD, REP>(P, K, M, J, s, block, X, bin, prob, jac);
   double w[NI];
   F::template eval<MAXD, PoolX<MAXD>, EXACT>(X, P, w);
   double pad[NI];
@@ -185,7 +254,16 @@ __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K
         w2 = a * a;
       }
       const int di = EXACT ? MAXD : P.dof[i * P.nv];
-      if constexpr (HMODE == HIST_SMEM_STRIPED && MCI_HIST_BATCH > 1) {
+      if constexpr (HMODE == HIST_SMEM_FIXED) {
+        /* one conversion per (sample, pass): X = round-to-nearest(w2 2^E); every slot then adds the same integer */
+        const double xs = w2 * fx_scale;
+        fx_total += xs; /* range check at CTA exit: no cell can exceed the sum of everything this CTA added */
+        const unsigned long long Xi = xs < 4.6e18 ? __double2ull_rn(xs) : 0ull;
+        if (!(xs < 4.6e18)) fx_total = 1.0e300; /* a single weight beyond 2^62 (or NaN): trip the check */
+        const uint32_t xlo = (uint32_t)Xi, xhi = (uint32_t)(Xi >> 32);
+#pragma unroll
+        for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) fixed_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, xlo, xhi);
+      } else if constexpr (HMODE == HIST_SMEM_STRIPED && MCI_HIST_BATCH > 1) {
 #pragma unroll
         for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) hist_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, w2);
       } else {
@@ -212,11 +290,12 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
-  static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED,
-                "pool kernel histogram modes");
+  static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED ||
+                    HMODE == HIST_SMEM_FIXED, "pool kernel histogram modes");
   static_assert(IntegrandWD<FID>::value == 1, "complex integrands run on the generic kernel");
-  constexpr int NCOPY = HMODE == HIST_SMEM_STRIPED ? STRIPE : (HMODE == HIST_SMEM_ATOMIC ? 1 : 0);
-  constexpr int REP = HMODE == HIST_SMEM_STRIPED ? POOL_MAP_REP : 1; /* the striped variant owns the SM: room for map copies */
+  constexpr bool STRIPED = HMODE == HIST_SMEM_STRIPED || HMODE == HIST_SMEM_FIXED;
+  constexpr int NCOPY = STRIPED ? STRIPE : (HMODE == HIST_SMEM_ATOMIC ? 1 : 0);
+  constexpr int REP = STRIPED ? POOL_MAP_REP : 1; /* the striped variants own the SM: room for map copies */
   extern __shared__ __align__(16) double smem[];
   double *smaps = smem;                                 /* REP * P.map_doubles                    */
   double *shist = smem + REP * P.map_doubles;           /* the CTA's histogram: [bin][copy]       */
@@ -238,12 +317,22 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   }
   for (int i = tid; i < NCOPY * P.hist_len; i += THREADS) shist[i] = 0.0;
   __syncthreads();
-  const uint32_t hist_saddr = (uint32_t)__cvta_generic_to_shared(shist) + (HMODE == HIST_SMEM_STRIPED ? 8u * (lane & (STRIPE - 1)) : 0u);
+  const uint32_t hist_saddr = (uint32_t)__cvta_generic_to_shared(shist) + (STRIPED ? 8u * (lane & (STRIPE - 1)) : 0u);
+  /* fixed-point cells: scale 2^E of this iteration, chosen on the device after the previous one (fixed_scale_kernel) */
+  int fx_exp = 0;
+  double fx_scale = 1.0, fx_total = 0.0;
+  if (HMODE == HIST_SMEM_FIXED) {
+    fx_exp = *A.fixed_exp;
+    if (fx_exp == FIXED_EXP_INVALID) { fx_exp = 0; fx_total = 1.0e300; } /* no usable scale: report it */
+    fx_scale = scalbn(1.0, fx_exp);
+  }
   double *ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
 
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
   unsigned long long bad = 0;
+  PoolJac<MAXD, EXACT> J;
+  J.init(P.leaf[0].nbins_d, EXACT ? MAXD : P.maxdof[0]);
 
   const int n_tiles = A.n_local_blocks * A.tiles_per_block;
   const uint64_t tile_samples = (uint64_t)THREADS * A.spt;
@@ -259,19 +348,19 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
     if (s0 + tile_samples <= A.neval_per_block) { /* full tile: no per-lane guards anywhere */
       if (adapt) {
         for (int k = 0; k < A.spt; ++k)
-          pool_sample<FID, MAXD, HMODE, EXACT, false, REP>(P, K, M, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
-                                                       true, acc, cnt, bad);
+          pool_sample<FID, MAXD, HMODE, EXACT, false, REP>(P, K, M, J, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
+                                                       true, acc, cnt, bad, fx_scale, fx_total);
       } else {
         for (int k = 0; k < A.spt; ++k)
-          pool_sample<FID, MAXD, HIST_NONE, EXACT, false, REP>(P, K, M, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
-                                                           block, true, acc, cnt, bad);
+          pool_sample<FID, MAXD, HIST_NONE, EXACT, false, REP>(P, K, M, J, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
+                                                           block, true, acc, cnt, bad, fx_scale, fx_total);
       }
     } else { /* ragged last tile of a block */
       for (int k = 0; k < A.spt; ++k) {
         const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
         const bool active = s < A.neval_per_block;
-        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true, REP>(P, K, M, hist_saddr, ghist, s, block, active, acc, cnt, bad);
-        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true, REP>(P, K, M, hist_saddr, ghist, s, block, active, acc, cnt, bad);
+        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_total);
+        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_total);
       }
     }
     /* tile flush: warp shuffle -> shared -> one thread sums the warps in order */
@@ -298,15 +387,31 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
     }
   }
   if (bad) atomicAdd(A.flags, bad);
+  if (HMODE == HIST_SMEM_FIXED) { /* range check: every cell <= the sum of all weights this CTA added, which must stay below
+                                     2^63: each of the <= 32 warps below 2^58 */
+    const double t = warp_sum(fx_total);
+    if (lane == 0 && !(t < 2.8e17)) atomicAdd(A.flags + 2, 1ull);
+  }
   /* histogram flush: one global partial per CTA (stripes summed in a fixed order) */
   if (NCOPY > 0) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
-    for (int i = tid; i < P.hist_len; i += THREADS) {
-      double t = 0.0;
+    if (HMODE == HIST_SMEM_FIXED) { /* integer sum of the stripes (exact), one conversion, one exact power-of-two scaling */
+      const unsigned long long *cells = reinterpret_cast<const unsigned long long *>(shist); /* lo limb first: little endian */
+      const double inv = scalbn(1.0, -fx_exp);
+      for (int i = tid; i < P.hist_len; i += THREADS) {
+        unsigned long long t = 0ull;
 #pragma unroll
-      for (int c = 0; c < NCOPY; ++c) t += shist[i * NCOPY + c];
-      out[i] = t;
+        for (int c = 0; c < NCOPY; ++c) t += cells[i * NCOPY + c];
+        out[i] = (double)t * inv;
+      }
+    } else {
+      for (int i = tid; i < P.hist_len; i += THREADS) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCOPY; ++c) t += shist[i * NCOPY + c];
+        out[i] = t;
+      }
     }
   }
 }
@@ -510,6 +615,36 @@ __global__ void vegas_trace_kernel(const __grid_constant__ DevProblem Pp, const 
   for (int k = 0; k < P.n_draw; ++k) { xo[(size_t)t * P.n_draw + k] = x[k]; bo[(size_t)t * P.n_draw + k] = bin[k]; }
   jo[t] = jac;
   for (int i = 0; i < P.ni * WD; ++i) wo[(size_t)t * P.ni * WD + i] = w[i]; /* complex: (re, im) interleaved */
+}
+
+/* L0 parity probe of the POOL path: the very draw code of vegas_pool_kernel (pool_draw: fma map index, unclamped
+ * increment, halved Jacobian products) on the staged map image in global memory, plus the integrand */
+template <int FID, int MAXD>
+__global__ void vegas_pool_trace_kernel(const __grid_constant__ DevProblem Pp, const double *gmaps, uint64_t iter, uint32_t block,
+                                        uint64_t first, int count, double *xo, int *bo, double *jo, double *wo) {
+  MCI_VIEW(P, Pp);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  constexpr int NI = Integrand<FID>::NI;
+  PhiloxKey K;
+  philox_expand_key(P.seed, iter, K);
+  PoolMap<1> M;
+  M.pair = reinterpret_cast<const double2 *>(gmaps);
+  PoolJac<MAXD, false> J;
+  J.init(P.leaf[0].nbins_d, P.maxdof[0]);
+  PoolX<MAXD> X;
+  int bin[MAXD];
+  double prob[1], jac, w[NI];
+#pragma unroll
+  for (int p = 0; p < MAXD; ++p) { X.v[p] = 0.0; bin[p] = 0; }
+  pool_draw<MAXD, false, false, 1>(P, K, M, J, first + t, block, X, bin, prob, jac);
+  Integrand<FID>::template eval<MAXD, PoolX<MAXD>, false>(X, P, w);
+  const int d = P.maxdof[0];
+#pragma unroll
+  for (int p = 0; p < MAXD; ++p)
+    if (p < d) { xo[(size_t)t * d + p] = X.v[p]; bo[(size_t)t * d + p] = bin[p]; }
+  jo[t] = jac;
+  for (int i = 0; i < NI; ++i) wo[(size_t)t * NI + i] = w[i];
 }
 
 }  // namespace mci

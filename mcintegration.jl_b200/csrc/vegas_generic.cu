@@ -22,6 +22,18 @@ const void *lookup_vegas_generic(int fid, const char **name) {
   return nullptr;
 }
 
+/* L0 probe of the pool path (pool_draw), for every integrand that has pool instantiations */
+const void *lookup_vegas_pool_trace(int fid, int d) {
+  if (d > MCI_MAX_SLOT) return nullptr;
+  switch (fid) {
+#define MP(FID) case FID: return (const void *)vegas_pool_trace_kernel<FID, MCI_MAX_SLOT>;
+    MP(MCI_F_GAUSS_ND) MP(MCI_F_GENZ_CORNER_POOL) MP(MCI_F_PRODUCT_4) MP(MCI_F_LOG_OVER_SQRT) MP(MCI_F_SPHERE1) MP(MCI_F_SPHERE2)
+    MP(MCI_F_LATTICE_POOL) MP(MCI_F_HYPERSPHERE3) MP(MCI_F_POLY3) MP(MCI_F_X2_PLUS_Y2)
+#undef MP
+  }
+  return nullptr;
+}
+
 const void *lookup_vegas_trace(int fid) {
   switch (fid) {
 #define M(FID) case FID: return (const void *)vegas_trace_kernel<FID>;

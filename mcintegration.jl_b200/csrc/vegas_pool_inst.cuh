@@ -11,6 +11,9 @@
     case mci::HIST_SMEM_STRIPED:                                                                                                 \
       if (MAXD <= 20) return (const void *)mci::vegas_pool_kernel<FID, (MAXD <= 20 ? MAXD : 1), mci::HIST_SMEM_STRIPED, mci::POOL_THREADS_STRIPED, EXACT>; \
       return nullptr; /* 1024 threads x 64 registers cannot hold more than 20 slots without spilling */                           \
+    case mci::HIST_SMEM_FIXED:                                                                                                   \
+      if (MAXD <= 20) return (const void *)mci::vegas_pool_kernel<FID, (MAXD <= 20 ? MAXD : 1), mci::HIST_SMEM_FIXED, mci::POOL_THREADS_STRIPED, EXACT>; \
+      return nullptr;                                                                                                            \
   }
 
 /* run-time dof <= MAXD, predicated */

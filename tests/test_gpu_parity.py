@@ -202,10 +202,14 @@ def test_chain_burnin_parity(name, solver):
         _assert_stats(a, b, obs_rtol=1e-9, hist_rtol=1e-9, counts_exact=False)
         np.testing.assert_allclose(a.visited, b.visited, rtol=1e-9)
         assert np.array_equal(np.round(a.propose - b.propose, 6), np.zeros_like(a.propose))
-        # the measured part is unchanged in length: same normalisation count scale as without burn-in, more evaluations
+        # burn-in steps touch no statistic — not the evaluation / proposal counters either (report(config) must describe
+        # the reference's loop, not the warm-up): the counts stay within the measured loop's budget, the chains differ
         g0, c0, _ = _pair(name, solver, n_block=4, neval_per_block=96 * 100, walkers=96)
         try:
-            assert g0.run_iteration(0).neval < a.neval
+            plain = g0.run_iteration(0)
+            steps = 4 * 96 * 100 * (1.1 if solver == "mcmc" else 1.0)
+            assert a.neval <= steps and plain.neval <= steps and (a.propose - 5e-8).sum() <= steps + 1e-3
+            assert not np.array_equal(a.block_obs, plain.block_obs)
         finally:
             g0.close(); c0.close()
     finally:

@@ -369,3 +369,50 @@ def test_cuba_demo_set_against_the_reference_published_values(solver):
     # closed forms where they exist: t5 = (sqrt(pi)/2 erf(1))^3, t11 = pi/6
     assert abs(res.mean[4] - (math.sqrt(math.pi) / 2 * math.erf(1)) ** 3) < 7 * res.stdev[4]
     assert abs(res.mean[10] - math.pi / 6) < 7 * res.stdev[10]
+
+
+# ---- fixed-point histogram cells (hist_policy = MCI_HIST_SMEM_FIXED) ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["gauss10", "genz16_pool", "product4"])
+def test_fixed_point_histogram_policy(name):
+    """The striped shared-memory histogram as 64-bit fixed-point cells updated with native integer adds.
+    Parity: against the oracle's fp64 histogram rtol 1e-10 on every bin above 2^-20 of the largest, absolute 2^-40 of the
+    largest below that (a weight is rounded once to 2^-30 of the previous iteration's mean weight); block sums untouched
+    (rtol 1e-11); the refined grid agrees to 1e-9; and — integer adds commute — two runs are bit-identical."""
+    spec, _ = make_spec(name, "vegas", n_block=16, neval_per_block=20000, hist_policy=_abi.HIST_SMEM_FIXED)
+    gpu, cpu = mci.CudaEngine(spec), OracleEngine(spec)
+    twin = mci.CudaEngine(spec)
+    try:
+        assert gpu.launch_info()["hist_mode"] == _abi.HIST_SMEM_FIXED
+        for it in range(4):  # iteration 0 has no scale yet and runs the fp64 striped kernel
+            a, b, t = gpu.run_iteration(it), cpu.run_iteration(it), twin.run_iteration(it)
+            scale = np.abs(b.block_obs).max()
+            np.testing.assert_allclose(a.block_obs, b.block_obs, rtol=1e-11, atol=1e-11 * scale)
+            assert np.array_equal(a.block_norm, b.block_norm)
+            big = b.hist > b.hist.max() * 2.0 ** -20
+            np.testing.assert_allclose(a.hist[big], b.hist[big], rtol=1e-10)
+            np.testing.assert_allclose(a.hist, b.hist, rtol=1e-10, atol=b.hist.max() * 2.0 ** -40)
+            if it >= 1:
+                assert np.array_equal(a.hist, t.hist)  # bit-reproducible
+            gpu.refine(); cpu.refine(); twin.refine()
+            np.testing.assert_allclose(gpu.get_maps()[0], cpu.get_maps()[0], rtol=1e-9, atol=1e-12)
+            gpu.set_maps(*cpu.get_maps()); twin.set_maps(*cpu.get_maps())
+    finally:
+        gpu.close(); cpu.close(); twin.close()
+
+
+def test_fixed_point_histogram_range_is_checked():
+    """a weight far beyond the scale the previous iteration set must be reported, not wrapped around"""
+    cfg = mci.Configuration(var=mci.Continuous(-5.0, 5.0), dof=[[10]], seed=5)
+    spec = mci.problem_from_config(cfg, integrands.gauss_nd, solver=_abi.SOLVER_VEGAS, measure_kind=0, n_block=4,
+                                   neval_per_block=1 << 14, hist_policy=_abi.HIST_SMEM_FIXED)
+    eng = mci.CudaEngine(spec)
+    try:
+        eng.run_iteration(0)  # sets the scale from a uniform grid ...
+        grids = eng.get_maps()[0]
+        # ... then a map squeezed onto a corner of the domain: the Jacobian, hence every weight, jumps by ~(1e6)^10
+        squeezed = np.concatenate([np.linspace(-5.0, -5.0 + 1e-5, len(grids) - 1), [5.0]])
+        eng.set_maps(grids=squeezed)
+        with pytest.raises(mci.MCIError, match="fixed-point"):
+            eng.run_iteration(1)
+    finally:
+        eng.close()

@@ -15,7 +15,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "gauss10"
 solver = sys.argv[2] if len(sys.argv) > 2 else "vegas"
 lg = int(sys.argv[3]) if len(sys.argv) > 3 else 24
 walkers = int(sys.argv[4]) if len(sys.argv) > 4 else 8192
-ALL = {"0": (0, True), "1": (1, True), "2": (2, True), "3": (3, True), "4": (4, True), "n": (0, False)}
+ALL = {"0": (0, True), "1": (1, True), "2": (2, True), "3": (3, True), "4": (4, True), "5": (5, True), "n": (0, False)}
 sel = sys.argv[5].split(",") if len(sys.argv) > 5 else list(ALL)
 niter = int(sys.argv[6]) if len(sys.argv) > 6 else 8
 rows = []
@@ -41,7 +41,7 @@ for policy, adapt in (ALL[k] for k in sel):
     info = eng.launch_info()
     ms = sorted(t)[len(t) // 2]
     n = spec.n_block * spec.neval_per_block
-    rows.append(dict(case=name, solver=solver, policy=policy, adapt=adapt, hist_mode=info["hist_mode"], grid=info["grid"],
+    rows.append(dict(lib=os.path.basename(os.environ.get("MCIB200_LIB", "libmcib200.so")), case=name, solver=solver, policy=policy, adapt=adapt, hist_mode=info["hist_mode"], grid=info["grid"],
                      threads=info["threads"], smem=info["smem_bytes"], fill_ms=ms, gsamples_per_s=n / ms / 1e6,
                      kernel=info["kernel"]))
     print(json.dumps(rows[-1]), flush=True)
