@@ -71,6 +71,11 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 thread_local char g_err[256];
 /* auto policy of the pool kernel = 16 bank-striped shared copies: measured 39.8 vs 28.0 G samples/s (one shared copy) on C2, profiles/r1_hist_policy_sweeps.jsonl */
 constexpr bool MCI_AUTO_STRIPED = true;
+/* auto policy of the generic kernel where the fp64 histogram would have to live in L2: fixed-point cells in shared memory */
+#ifndef MCI_AUTO_FIXED_GENERIC_DEFAULT
+#define MCI_AUTO_FIXED_GENERIC_DEFAULT 0
+#endif
+constexpr bool MCI_AUTO_FIXED_GENERIC = MCI_AUTO_FIXED_GENERIC_DEFAULT != 0;
 }  // namespace
 
 struct mci_handle_t {
@@ -95,6 +100,7 @@ struct mci_handle_t {
   double *d_tile_obs = nullptr, *d_tile_cnt = nullptr, *d_cta_hist = nullptr, *d_cta_stats = nullptr, *d_packed = nullptr;
   unsigned long long *d_flags = nullptr; /* [4]: non-finite weights, mcmc walkers without a start, fixed-point range, spare */
   int *d_err = nullptr, *d_fixed_exp = nullptr;
+  double *d_fixed_state = nullptr; /* largest histogram bin of the previous iteration (fixed_scale_kernel) */
   /* the buffers above are carved out of three allocations (cudaMalloc / cudaFree / cudaMallocHost cost 0.1-1 ms each
    * and synchronise the device: a job of the reference's default size, neval = 1e4, is over in 4 ms):
    * the fixed state, the per-launch partials (re-planned by mci_set_partition) and the pinned host mirrors */
@@ -110,7 +116,6 @@ struct mci_handle_t {
   /* launch plan */
   const void *kernel = nullptr;
   const void *kernel_first = nullptr; /* HIST_SMEM_FIXED: the fp64 striped kernel that runs while no scale exists yet */
-  bool fixed_scale_ready = false;
   const char *kernel_name = "";
   bool is_pool = false;
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
@@ -253,7 +258,7 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   if (!h->use_jit) {
     switch (kind) {
       case 0: return lookup_vegas_pool(P.fid, P.maxdof[0], exact, mode, &h->kernel_name);
-      case 1: return lookup_vegas_generic(P.fid, &h->kernel_name);
+      case 1: return lookup_vegas_generic(P.fid, &h->kernel_name, threads);
       case 2: return lookup_vegasmc(P.fid, &h->kernel_name);
       default: return lookup_mcmc(P.fid, &h->kernel_name);
     }
@@ -269,7 +274,7 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
       if ((mode == HIST_SMEM_STRIPED || mode == HIST_SMEM_FIXED) && P.maxdof[0] > 20) return nullptr; /* 1024 threads x 64 registers */
       snprintf(name, sizeof name, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0], mode, threads, exact ? "true" : "false");
       break;
-    case 1: snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, GENERIC_THREADS); break;
+    case 1: snprintf(name, sizeof name, "mci::vegas_generic_kernel<%d, %d>", P.fid, threads); break;
     case 2: snprintf(name, sizeof name, "mci::vegasmc_kernel<%d>", P.fid); break;
     default: snprintf(name, sizeof name, "mci::mcmc_kernel<%d>", P.fid); break;
   }
@@ -378,14 +383,27 @@ int plan(mci_handle_t *h) {
       }
     }
     if (!h->is_pool) {
-      const int nwarp = GENERIC_THREADS / 32;
-      const size_t red = (size_t)nwarp * (P.obs_total + 1) * 8;
+      int gthreads = GENERIC_THREADS;
+      int nwarp = gthreads / 32;
+      size_t red = (size_t)nwarp * (P.obs_total + 1) * 8;
       int mode = pick_hist(nwarp, red, true);
-      h->kernel = resolve_kernel(h, 1, mode, GENERIC_THREADS, false);
+      /* fixed-point cells: ONE shared copy of every leaf's histogram per CTA, updated with native integer adds.  Asked for
+       * explicitly, or chosen when the fp64 alternative is the L2 reductions (histograms too large to share an SM with a
+       * second CTA).  Large histograms take one 1024-thread CTA per SM; the maps then stay in global memory (L1 / L2 hits)
+       * unless they fit beside the cells */
+      const bool fixed_ok = P.any_adapt && hist_bytes + (size_t)(GENERIC_THREADS_BIG / 32) * (P.obs_total + 1) * 8 + 1024 <= SMEM_MAX;
+      if (fixed_ok && (p.hist_policy == MCI_HIST_SMEM_FIXED || (p.hist_policy == MCI_HIST_AUTO && mode == HIST_GLOBAL_RED && MCI_AUTO_FIXED_GENERIC))) {
+        mode = HIST_SMEM_FIXED;
+        if (hist_bytes > SMEM_MAX / 4) gthreads = GENERIC_THREADS_BIG;
+        nwarp = gthreads / 32;
+        red = (size_t)nwarp * (P.obs_total + 1) * 8;
+        h->maps_in_smem = map_bytes + hist_bytes + red <= SMEM_MAX ? 1 : 0;
+      }
+      h->kernel = resolve_kernel(h, 1, mode, gthreads, false);
       if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
       if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no vegas kernel", P.fid);
-      h->threads = GENERIC_THREADS; h->hist_mode = mode;
-      h->smem = (h->maps_in_smem ? map_bytes : 0) + hist_smem(mode, nwarp) + red;
+      h->threads = gthreads; h->hist_mode = mode;
+      h->smem = (h->maps_in_smem ? map_bytes : 0) + (mode == HIST_SMEM_FIXED ? hist_bytes : hist_smem(mode, nwarp)) + red;
     }
   } else {
     /* chain solvers: walker state in shared memory rows [row][thread]; pick the CTA size that keeps most walkers
@@ -395,7 +413,7 @@ int plan(mci_handle_t *h) {
     if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no chain kernel", P.fid);
     int max_nl = 1;
     for (int v = 0; v < P.nv; ++v) max_nl = std::max(max_nl, P.top_nleaf[v]);
-    h->chain_rows = P.n_draw + max_nl;
+    h->chain_rows = P.n_draw + (max_nl > 1 ? max_nl : 0); /* single-leaf variables keep shift!'s rollback cache in registers */
     { /* largest number of (slot, leaf) items one changeIntegrand creates or removes, over the neighbour graph */
       int worst = 0;
       for (int a = 0; a < P.nd; ++a)
@@ -408,7 +426,7 @@ int plan(mci_handle_t *h) {
       if (const char *e = getenv("MCIB200_COOP_MIN")) coop_min = atoi(e);
       h->coop_ci = worst >= coop_min && !h->has_fermik;
     }
-    const size_t row_bytes = (size_t)h->chain_rows * (8 + 4 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0));
+    const size_t row_bytes = (size_t)h->chain_rows * (8 + 2 + (p.solver == MCI_SOLVER_VEGASMC ? 8 : 0)); /* x, u16 bin[, prob] */
     const size_t fixed = 32 * 8 + (((size_t)2 * h->pa_len + 1) / 2) * 8;
     CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     int best_score = -1, best_occ = 1;
@@ -453,7 +471,7 @@ int plan(mci_handle_t *h) {
     h->maps_in_smem = best_mis;
   }
   CU(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-  if (h->hist_mode == HIST_SMEM_FIXED) CU(h, cudaFuncSetAttribute(h->kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  if (h->hist_mode == HIST_SMEM_FIXED && h->is_pool) CU(h, cudaFuncSetAttribute(h->kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   int occ = 0;
   CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->threads, h->smem));
   if (occ < 1) return fail(h, MCI_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", h->kernel_name, h->smem);
@@ -482,7 +500,9 @@ int plan(mci_handle_t *h) {
      * variable, slot(s), acceptance) plus one per leaf it redraws — every slot of the largest integrand when an mcmc
      * changeIntegrand creates them all, three per FermiK proposal.  Refuse chains that would wrap it and replay */
     {
-      const double per_step = 4.0 + (p.solver == MCI_SOLVER_MCMC ? (double)P.n_draw + 3.0 : (double)(h->chain_rows - P.n_draw));
+      int max_nl = 1;
+      for (int v = 0; v < P.nv; ++v) max_nl = std::max(max_nl, P.top_nleaf[v]);
+      const double per_step = 4.0 + (p.solver == MCI_SOLVER_MCMC ? (double)P.n_draw + 3.0 : (double)max_nl);
       const double total_steps = (double)h->steps * (1.0 + (p.solver == MCI_SOLVER_MCMC ? P.thermal_ratio : 0.0)) + (double)p.chain_burnin + 1.0;
       if (per_step * total_steps + 10000.0 * (double)P.n_draw >= 4294967296.0)
         return fail(h, MCI_ERR_UNSUPPORTED, "%llu steps per chain exhaust the 2^32 uniforms of a walker's stream: cut the block into more chains (walkers_per_block)",
@@ -660,6 +680,8 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
         continue;
       }
       if (S.nbins < 1) BAIL(MCI_ERR_INVALID, "leaf %d has no bins", l);
+      if (p->solver != MCI_SOLVER_VEGAS && S.nbins > 65535)
+        BAIL(MCI_ERR_UNSUPPORTED, "leaf %d has %d bins: the chain solvers keep bin indices in 16 bits (at most 65535)", l, S.nbins);
       L.kind = S.kind; L.nbins = S.nbins; L.adapt = S.adapt ? 1 : 0; L.lower_i = S.lower_i; L.nbins_d = (double)S.nbins;
       L.top = v; L.base = P.top_base[v] + k; L.stride = P.top_nleaf[v];
       L.hist_off = ho; ho += S.nbins;
@@ -733,6 +755,12 @@ static int describe_problem(const mci_problem_t *p, mci_handle_t *h) {
     if (P.fid == MCI_F_BUBBLE_FERMIK) P.fconst[0] = 1.0 / pow(2 * pi, (double)P.top_nleaf[1]); /* phase = 1/(2pi)^dim, test/bubble_FermiK.jl:71 */
     if (P.fid == MCI_F_HYPERSPHERE3) for (int i = 1; i <= 3; ++i) P.fconst[i - 1] = volume_inverse(i + 1);
   }
+  { /* halves of N^d for the pool kernel's Jacobian (PoolJac, mci_vegas.cuh) */
+    const int d = P.maxdof[0], hh = (d + 1) >> 1;
+    P.pool_npow[0] = P.pool_npow[1] = 1.0;
+    for (int k = 0; k < hh; ++k) P.pool_npow[0] *= P.leaf[0].nbins_d;
+    for (int k = 0; k < d - hh; ++k) P.pool_npow[1] *= P.leaf[0].nbins_d;
+  }
   P.pa_dim = std::max(nd, nv);
   h->pa_len = 3 * nd * P.pa_dim;
   PackedLayout &Y = h->Y;
@@ -796,14 +824,14 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
     const size_t o_gmaps = D.reserve<double>(mo + 2);
     const size_t o_lg = D.reserve<int>(nleaf), o_ld = D.reserve<int>(nleaf), o_la = D.reserve<int>(nleaf);
     const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(4), o_err = D.reserve<int>(1);
-    const size_t o_fx = D.reserve<int>(1);
+    const size_t o_fx = D.reserve<int>(1), o_fxs = D.reserve<double>(1);
     TRY(arena_device(h, D, &h->d_state_arena, &h->state_cap, false));
     h->d_grids = D.at<double>(o_grids); h->d_dist = D.at<double>(o_dist); h->d_accum = D.at<double>(o_accum);
     h->d_reweight = D.at<double>(o_rw); h->d_goal = D.at<double>(o_goal); h->d_alpha = D.at<double>(o_alpha);
     h->d_gmaps = D.at<double>(o_gmaps);
     h->d_leaf_grid_off = D.at<int>(o_lg); h->d_leaf_dist_off = D.at<int>(o_ld); h->d_leaf_acc_off = D.at<int>(o_la);
     h->d_packed = D.at<double>(o_packed); h->d_flags = D.at<unsigned long long>(o_flags); h->d_err = D.at<int>(o_err);
-    h->d_fixed_exp = D.at<int>(o_fx);
+    h->d_fixed_exp = D.at<int>(o_fx); h->d_fixed_state = D.at<double>(o_fxs);
     Arena H;
     const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(4), ho_err = H.reserve<int>(1);
     const size_t ho_init = H.reserve<char>(D.total); /* staging image of the device state */
@@ -867,6 +895,13 @@ int mci_set_maps(mci_handle_t *h, const double *grids, const double *dist, const
   if (dist && h->disc_len) CU(h, cudaMemcpyAsync(h->d_dist, dist, h->disc_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (accum && h->accum_len) CU(h, cudaMemcpyAsync(h->d_accum, accum, h->accum_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (rw) CU(h, cudaMemcpyAsync(h->d_reweight, rw, h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (grids && h->hist_mode == HIST_SMEM_FIXED) {
+    /* maps replaced from outside: the fixed-point scale learnt from the old map's histogram says nothing about the
+     * new one — forget it, the fp64 kernel runs until the histogram has settled again */
+    static const int invalid = FIXED_EXP_INVALID;
+    CU(h, cudaMemcpyAsync(h->d_fixed_exp, &invalid, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->d_fixed_state, 0, sizeof(double), h->stream));
+  }
   CU(h, cudaStreamSynchronize(h->stream)); /* the caller may reuse its buffers */
   h->maps_dirty = true;
   return MCI_OK;
@@ -908,7 +943,9 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   ChainArgs CA;
   if (p.solver == MCI_SOLVER_VEGAS) {
     FA.gmaps = h->d_gmaps; FA.tile_obs = h->d_tile_obs; FA.tile_cnt = h->d_tile_cnt; FA.cta_hist = h->d_cta_hist;
-    FA.flags = h->d_flags; FA.fixed_exp = h->d_fixed_exp; FA.iter = iter; FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
+    FA.flags = h->d_flags; FA.fixed_exp = h->hist_mode == HIST_SMEM_FIXED ? h->d_fixed_exp : nullptr; FA.iter = iter;
+    FA.fixed_bias = 0;
+    if (const char *e = getenv("MCIB200_FIXED_EXP_BIAS")) FA.fixed_bias = atoi(e); /* test hook: shrink the headroom */ FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
     FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
     FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
     args[0] = &h->dp; args[1] = &FA;
@@ -923,11 +960,12 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   const int slot = (int)(h->n_iterations % mci_handle_t::FILL_RING);
   if (!h->ev_fill0[slot]) { CU(h, cudaEventCreate(&h->ev_fill0[slot])); CU(h, cudaEventCreate(&h->ev_fill1[slot])); }
   CU(h, cudaEventRecord(h->ev_fill0[slot], h->stream));
-  /* fixed-point histogram: the scale of an iteration comes from the one before it; the first runs the fp64 striped kernel */
-  const bool fixed_now = h->hist_mode == HIST_SMEM_FIXED && h->fixed_scale_ready;
-  if (h->hist_mode == HIST_SMEM_FIXED) FA.hist_mode = fixed_now ? HIST_SMEM_FIXED : HIST_SMEM_STRIPED;
-  CU(h, cudaLaunchKernel(h->hist_mode == HIST_SMEM_FIXED && !fixed_now ? h->kernel_first : h->kernel, dim3(h->grid), dim3(h->threads), args,
-                         h->smem, h->stream));
+  CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
+  if (h->hist_mode == HIST_SMEM_FIXED && h->is_pool) { /* ... and its fp64 twin: the device-side scale decides which of the two works
+                                                           (mci_vegas.cuh); the generic kernel switches inside one launch */
+    CU(h, cudaLaunchKernel(h->kernel_first, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
+    h->launches++;
+  }
   CU(h, cudaEventRecord(h->ev_fill1[slot], h->stream));
   h->n_iterations++;
   h->launches++;
@@ -951,10 +989,9 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
     if (rc != 0) return fail(h, MCI_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   }
   if (h->hist_mode == HIST_SMEM_FIXED) { /* the scale of the next iteration, from the (all-reduced) statistics of this one */
-    fixed_scale_kernel<<<1, 256, 0, h->stream>>>(h->Y, h->d_packed, h->dp.maxdof[0], h->d_fixed_exp);
+    fixed_scale_kernel<<<1, 256, 0, h->stream>>>(h->Y, h->d_packed, h->d_fixed_exp, h->d_fixed_state);
     CU(h, cudaGetLastError());
     h->launches++;
-    h->fixed_scale_ready = true;
   }
   if (with_d2h) {
     CU(h, cudaMemcpyAsync(h->h_packed, h->d_packed, h->Y.len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -982,8 +1019,8 @@ static int unpack_iteration(mci_handle_t *h, const double *pk, const unsigned lo
   if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
   h->nonfinite = flags[0];
   if (flags[2])
-    return fail(h, MCI_ERR_NUMERIC, "fixed-point histogram (MCI_HIST_SMEM_FIXED): a weight or a CTA total left the 64-bit range "
-                                    "(the scale follows the previous iteration's mean weight); use another hist_policy");
+    return fail(h, MCI_ERR_NUMERIC, "fixed-point histogram (MCI_HIST_SMEM_FIXED): a bin outgrew the largest bin of the previous "
+                                    "iteration by more than 2^6 and left the 64-bit range; use another hist_policy");
   if (flags[1]) /* mcmc/montecarlo.jl:109-113 */
     return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #%d integrand nonzero!", h->dp.start_idx + 1);
   for (int b = 0; b < nb; ++b)

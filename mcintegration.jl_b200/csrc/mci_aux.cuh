@@ -297,25 +297,37 @@ __global__ void refine_kernel(const __grid_constant__ DevProblem P, PackedLayout
   if (threadIdx.x == 0 && s_bad) atomicOr(err, 1);
 }
 
-/* HIST_SMEM_FIXED: exponent of the next iteration's fixed-point scale from this iteration's (all-reduced) statistics.
- * mean weight per histogram add = sum(hist) / (measured samples x slots); E = FIXED_TARGET_LOG2 - ceil(log2(mean)) */
-__global__ void fixed_scale_kernel(PackedLayout Y, const double *__restrict__ packed, int slots, int *__restrict__ fixed_exp) {
+/* HIST_SMEM_FIXED: exponent of the next iteration's fixed-point scale from this iteration's (all-reduced) histogram:
+ * 2^E M = 2^FIXED_CAP_LOG2 with M the largest bin; invalid (-> the fp64 kernel runs) while M is not settled within
+ * 2^FIXED_STABLE_LOG2 of the iteration before.  state[0] = M of the previous call. */
+__global__ void fixed_scale_kernel(PackedLayout Y, const double *__restrict__ packed, int *__restrict__ fixed_exp,
+                                   double *__restrict__ state) {
   __shared__ double s_red[32];
-  double h = 0.0, n = 0.0;
-  for (int i = threadIdx.x; i < Y.hist_len; i += blockDim.x) h += packed[Y.off_hist + i];
-  for (int i = threadIdx.x; i < Y.n_block; i += blockDim.x) n += packed[Y.off_cnt + i];
-  h = cta_allsum(h, s_red);
-  n = cta_allsum(n, s_red);
+  double m = 0.0;
+  bool finite = true;
+  for (int i = threadIdx.x; i < Y.hist_len; i += blockDim.x) {
+    const double h = packed[Y.off_hist + i];
+    finite = finite && isfinite(h);
+    m = fmax(m, h);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int bad = __syncthreads_or(!finite);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const double mean = h / (n * (double)slots);
+    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmax(m, s_red[w]);
+    const double prev = state[0];
+    const double band = scalbn(1.0, FIXED_STABLE_LOG2);
     int e = FIXED_EXP_INVALID;
-    if (isfinite(mean) && mean > 0.0) {
+    if (!bad && m > 0.0 && prev > 0.0 && m <= prev * band && prev <= m * band) {
       int ex;
-      frexp(mean, &ex); /* mean = f 2^ex, f in [0.5, 1) */
-      e = FIXED_TARGET_LOG2 - ex;
-      if (e > 1000 || e < -1000) e = FIXED_EXP_INVALID;
+      frexp(m, &ex); /* m = f 2^ex, f in [0.5, 1) */
+      e = FIXED_CAP_LOG2 - ex;
+      if (e > 900 || e < -900) e = FIXED_EXP_INVALID;
     }
     *fixed_exp = e;
+    state[0] = bad ? 0.0 : m;
   }
 }
 

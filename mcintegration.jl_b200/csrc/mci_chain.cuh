@@ -43,19 +43,30 @@ struct ChainArgs {
   int walkers_per_block, ctas_per_block;
   int n_local_blocks, rank, world;
   int hist_mode, n_hist_copies, maps_in_smem;
-  int rows;               /* walker rows in shared memory = n_draw + max leaves of one variable  */
+  int rows;               /* walker rows in shared memory = n_draw (+ the leaves of the widest variable when some
+                             variable has several: the rollback rows of shift!)                    */
   long long burnin;       /* extra unmeasured steps before the reference's loop (mci_problem_t.chain_burnin) */
   int coop_ci;            /* mcmc: changeIntegrand creates/removes enough slots for the warp-cooperative path */
 };
 
 /* a walker's columns of the shared state; T = row stride (threads per CTA) */
+/* bin indices are kept as 16-bit values (mci_create refuses chain problems with more than 65535 bins in a leaf; the
+ * reference's default is 999): 10 bytes per (slot, walker) instead of 12, which for BASELINE C5 (20 slots) is the
+ * difference between 512 and 1024 resident walkers per SM */
+typedef unsigned short gidx_t;
+
 template <bool HAS_PROB>
 struct Walker {
   double *data;
   double *prob; /* HAS_PROB only */
-  int *gidx;    /* 0-based bin: grid increment (Continuous) / value - lower (Discrete) */
+  gidx_t *gidx; /* 0-based bin: grid increment (Continuous) / value - lower (Discrete) */
   int T;
-  int bk0;      /* first backup row */
+  int bk0;      /* first backup row (problems with a multi-leaf variable only) */
+  /* rollback cache of shift! (sampler.jl:338-340): in registers when every variable is a single leaf — the common case,
+   * and one shared-memory row per walker less — else one backup row per leaf of the variable */
+  bool bk_regs;
+  double bk_x, bk_p;
+  int bk_g;
 };
 
 template <class RNG, bool FK = false>
@@ -89,7 +100,7 @@ __device__ __forceinline__ double leaf_create(CTX &C, Walker<HP> &W, const DevLe
     int iy;
     double dx;
     W.data[f] = map_continuous(reinterpret_cast<const double2 *>(C.maps + L.smem_off), L.nbins, L.nbins_d, u, iy, dx);
-    W.gidx[f] = iy;
+    W.gidx[f] = (gidx_t)iy;
     if (!HP) return __dmul_rn(L.nbins_d, dx); /* 1/prob = N dx (the reference's 1/(1/(N dx)) to 1 ulp) */
     const double pr = __ddiv_rn(1.0, __dmul_rn(L.nbins_d, dx));
     W.prob[f] = pr;
@@ -98,7 +109,7 @@ __device__ __forceinline__ double leaf_create(CTX &C, Walker<HP> &W, const DevLe
     const double *dist = C.maps + L.smem_off;
     const int g = locate_clamped(dist + L.nbins, L.nbins, u);
     W.data[f] = (double)(L.lower_i + g);
-    W.gidx[f] = g;
+    W.gidx[f] = (gidx_t)g;
     if (HP) W.prob[f] = dist[g];
     return __ddiv_rn(1.0, dist[g]);
   }
@@ -120,11 +131,16 @@ __device__ __forceinline__ double leaf_remove(CTX &C, Walker<HP> &W, const DevLe
 template <bool HP, class CTX>
 __device__ __forceinline__ double leaf_shift(CTX &C, Walker<HP> &W, const DevLeaf &L, int pos, int k) {
   const int f = frow(L, pos) * W.T;
-  const int b = (W.bk0 + k) * W.T;
-  W.data[b] = W.data[f];
   const int curr = W.gidx[f];
-  W.gidx[b] = curr;
-  if (HP) W.prob[b] = W.prob[f];
+  if (W.bk_regs) {
+    W.bk_x = W.data[f]; W.bk_g = curr;
+    if (HP) W.bk_p = W.prob[f];
+  } else {
+    const int b = (W.bk0 + k) * W.T;
+    W.data[b] = W.data[f];
+    W.gidx[b] = (gidx_t)curr;
+    if (HP) W.prob[b] = W.prob[f];
+  }
   const double u = C.rng.rand(C.K);
   double ratio;
   if (L.kind == MCI_LEAF_CONTINUOUS) {
@@ -132,13 +148,13 @@ __device__ __forceinline__ double leaf_shift(CTX &C, Walker<HP> &W, const DevLea
     int iy;
     double dx;
     W.data[f] = map_continuous(pair, L.nbins, L.nbins_d, u, iy, dx);
-    W.gidx[f] = iy;
+    W.gidx[f] = (gidx_t)iy;
     ratio = __ddiv_rn(pair[curr].y, dx);
   } else {
     const double *dist = C.maps + L.smem_off;
     const int g = locate_clamped(dist + L.nbins, L.nbins, u);
     W.data[f] = (double)(L.lower_i + g);
-    W.gidx[f] = g;
+    W.gidx[f] = (gidx_t)g;
     ratio = __ddiv_rn(dist[g], dist[curr]);
   }
   if (HP) W.prob[f] = __dmul_rn(W.prob[f], ratio);
@@ -296,6 +312,12 @@ __device__ __forceinline__ double var_shift(CTX &C, Walker<HP> &W, int v, int po
 template <bool HP>
 __device__ __forceinline__ void var_shift_rollback(const Problem &P, Walker<HP> &W, int v, int pos) {
   const int nl = P.top_nleaf[v];
+  if (W.bk_regs) { /* single-leaf variables only */
+    const int f = frow(P.leaf[P.top_first[v]], pos) * W.T;
+    W.data[f] = W.bk_x; W.gidx[f] = (gidx_t)W.bk_g;
+    if (HP) W.prob[f] = W.bk_p;
+    return;
+  }
   for (int k = 0; k < nl; ++k) {
     const int f = frow(P.leaf[P.top_first[v] + k], pos) * W.T;
     const int b = (W.bk0 + k) * W.T;
@@ -312,7 +334,7 @@ __device__ __forceinline__ void var_swap(const Problem &P, Walker<HP> &W, int v,
     const DevLeaf &L = P.leaf[P.top_first[v] + k];
     const int a = frow(L, p1) * W.T, b = frow(L, p2) * W.T;
     double t = W.data[a]; W.data[a] = W.data[b]; W.data[b] = t;
-    int g = W.gidx[a]; W.gidx[a] = W.gidx[b]; W.gidx[b] = g;
+    gidx_t g = W.gidx[a]; W.gidx[a] = W.gidx[b]; W.gidx[b] = g;
     if (HP) { t = W.prob[a]; W.prob[a] = W.prob[b]; W.prob[b] = t; }
   }
 }
@@ -367,7 +389,7 @@ __device__ __forceinline__ double cta_sum(double v, double *sred) {
 
 /* shared-memory carve-up of the chain kernels:
  *   [maps (if they fit)] [histogram (HIST_SMEM_ATOMIC)] [reduction scratch: 32 doubles] [mcmc: 2*pa_len u32 counters]
- *   [walker data rows*T doubles] [walker prob rows*T doubles (VegasMC)] [walker gidx rows*T ints]                  */
+ *   [walker data rows*T doubles] [walker prob rows*T doubles (VegasMC)] [walker gidx rows*T u16]                   */
 struct ChainSmem {
   const double *maps;
   double *shist, *sred;
@@ -389,9 +411,11 @@ __device__ __forceinline__ ChainSmem chain_setup(const Problem &P, const ChainAr
   double *wbase = S.sred + 32 + ((n_count + 1) >> 1);
   W.T = T;
   W.bk0 = P.n_draw;
+  W.bk_regs = A.rows == P.n_draw; /* no backup rows were reserved: every variable is a single leaf */
+  W.bk_x = W.bk_p = 0.0; W.bk_g = 0;
   W.data = wbase + tid;
   W.prob = HP ? wbase + (size_t)A.rows * T + tid : nullptr;
-  W.gidx = reinterpret_cast<int *>(wbase + (size_t)(HP ? 2 : 1) * A.rows * T) + tid;
+  W.gidx = reinterpret_cast<gidx_t *>(wbase + (size_t)(HP ? 2 : 1) * A.rows * T) + tid;
   if (A.maps_in_smem) stage_maps(P, maps_s, A.gmaps);
   for (int i = tid; i < nsh; i += T) S.shist[i] = 0.0;
   for (int i = tid; i < n_count; i += T) S.scount[i] = 0u;
@@ -660,12 +684,12 @@ __device__ __forceinline__ void eval_one(const Problem &P, const XA &X, int idx,
  * own rounding).  Returns the product on every lane; advances *q past the draws it consumed and leaves in
  * *b_out the buffered half when the new position is odd. */
 __device__ __forceinline__ double coop_change_dof(const Problem &P, const double *maps, const PhiloxKey &K, double *wdata0,
-                                                  int *wgidx0, int T, int src_tid, int curr, int nw, uint32_t c0, uint32_t c1,
+                                                  gidx_t *wgidx0, int T, int src_tid, int curr, int nw, uint32_t c0, uint32_t c1,
                                                   uint32_t c3, uint32_t *q, double *b_out) {
   const int lane = threadIdx.x & 31;
   double prop = 1.0;
   double *data = wdata0 + src_tid;
-  int *gidx = wgidx0 + src_tid;
+  gidx_t *gidx = wgidx0 + src_tid;
   for (int v = 0; v < P.nv; ++v) {
     const int cd = P.dof[curr * P.nv + v], nd_ = P.dof[nw * P.nv + v];
     if (cd == nd_) continue;
@@ -685,13 +709,13 @@ __device__ __forceinline__ double coop_change_dof(const Problem &P, const double
             int iy;
             double dx;
             data[f] = map_continuous(reinterpret_cast<const double2 *>(maps + L.smem_off), L.nbins, L.nbins_d, u, iy, dx);
-            gidx[f] = iy;
+            gidx[f] = (gidx_t)iy;
             term = __dmul_rn(L.nbins_d, dx);
           } else {
             const double *dist = maps + L.smem_off;
             const int g = locate_clamped(dist + L.nbins, L.nbins, u);
             data[f] = (double)(L.lower_i + g);
-            gidx[f] = g;
+            gidx[f] = (gidx_t)g;
             term = __ddiv_rn(1.0, dist[g]);
           }
         } else { /* remove! */

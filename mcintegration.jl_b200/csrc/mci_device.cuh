@@ -41,12 +41,17 @@ constexpr int HIST_SMEM_FIXED = 5;   /* the striped copies as 64-bit fixed-point
 #endif
 constexpr int STRIPE_LOG2 = MCI_STRIPE_LOG2;
 constexpr int STRIPE = 1 << STRIPE_LOG2;
-/* fixed-point histogram: a weight w2 is added as round(w2 * 2^E); E is chosen so that the MEAN weight of the previous
- * iteration maps to 2^FIXED_TARGET_LOG2 = 2^30: a bin that collects n adds of typical size carries a rounding error of
- * ~0.5 sqrt(n) units on n 2^30, i.e. 1.5e-13 relative for the 1e7 adds of a BASELINE-size iteration.  Range: every cell
- * of a CTA is bounded by the sum of all weights the CTA adds (~2^53 for 7e6 samples of mean weight), which the kernel
- * checks against 2^63 — the mean may grow 2^10-fold between two iterations, a single weight may be 2^32 times the mean */
-constexpr int FIXED_TARGET_LOG2 = 30;
+/* fixed-point histogram: a weight w2 is added as round(w2 * 2^E) into a 64-bit cell.  E is chosen on the device after
+ * every iteration from M = the largest bin of that iteration's (all-reduced) histogram: 2^E M = 2^FIXED_CAP_LOG2 = 2^58.
+ * A cell holds part of ONE bin, so it cannot overflow unless a bin grows beyond 2^6 M — and an overflow of the high limb
+ * is detected exactly, at the add that causes it.  One unit is 2^-58 M: the n adds of a bin lose at most n/2 units
+ * (typically 0.02 n, the bias of rounding a decreasing density), 2^-40 M for the 1e7 adds per bin of a BASELINE-size
+ * iteration — 1e-12 of a bin of a trained map, whose bins are within a small factor of each other; fp64 accumulation
+ * itself is no better than n 2^-53.  The scale is only USED when the histogram is settled: if M moved by more than
+ * 2^FIXED_STABLE_LOG2 against the iteration before (the first two iterations of an untrained map, normally), E is
+ * marked invalid and the fp64 kernel runs that iteration instead (both are launched; the device-side flag picks). */
+constexpr int FIXED_CAP_LOG2 = 58;
+constexpr int FIXED_STABLE_LOG2 = 8;
 constexpr int FIXED_EXP_INVALID = -100000;
 #ifndef MCI_POOL_MAP_REP
 #define MCI_POOL_MAP_REP 4
@@ -90,6 +95,8 @@ struct DevProblem {
   DevLeaf leaf[MCI_MAX_LEAF];
   double userdata[MCI_MAX_USERDATA];
   double fconst[4]; /* integrand constants evaluated on the host with the C library              */
+  double pool_npow[2]; /* single-pool layout: N^h and N^(d-h), N = increments of the pool's grid, d = maxdof, h = ceil(d/2):
+                          the two halves of N^d that PoolJac multiplies into the Jacobian (constant-bank operands)  */
   double thermal_ratio;
   uint64_t seed;
   __host__ __device__ int pa_len_() const { return 3 * nd * pa_dim; }

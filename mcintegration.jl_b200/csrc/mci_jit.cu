@@ -133,8 +133,8 @@ std::string jit_problem_header(const DevProblem &P) {
   o += buf;
   o += members;
   o += "  struct T_leaf { __device__ __forceinline__ const DevLeaf &operator[](int i) const { return jit_tab::leaf[i]; } } leaf;\n";
-  o += "  const double *userdata, *fconst; double thermal_ratio; uint64_t seed;\n"
-       "  __device__ __forceinline__ JitProblem(const DevProblem &p) : userdata(p.userdata), fconst(p.fconst), "
+  o += "  const double *userdata, *fconst, *pool_npow; double thermal_ratio; uint64_t seed;\n"
+       "  __device__ __forceinline__ JitProblem(const DevProblem &p) : userdata(p.userdata), fconst(p.fconst), pool_npow(p.pool_npow), "
        "thermal_ratio(p.thermal_ratio), seed(p.seed) {}\n"
        "  __device__ static constexpr int pa_len_() { return 3 * nd * pa_dim; }\n};\n}  // namespace mci\n";
   return o;

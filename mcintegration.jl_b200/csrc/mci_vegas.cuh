@@ -25,6 +25,17 @@
 #ifndef MCI_HIST_BATCH
 #define MCI_HIST_BATCH 5
 #endif
+/* pool draws: t = fma(m, N, -N) without clamp (1) or the generic map_index (0); Jacobian as N^d prod dx (1) or prod N dx (0) */
+#ifndef MCI_POOL_FMA_INDEX
+#define MCI_POOL_FMA_INDEX 1
+#endif
+#ifndef MCI_POOL_HALF_JAC
+#define MCI_POOL_HALF_JAC 1
+#endif
+/* lost-race check of a batch of compare-and-swaps: OR of XORs (1) or a chain of 64-bit compares (0) */
+#ifndef MCI_LOST_LOP3
+#define MCI_LOST_LOP3 1
+#endif
 /* fixed-point cells: add the high limb unconditionally (1) or only when it is non-zero (0) */
 #ifndef MCI_FIXED_HI_ALWAYS
 #define MCI_FIXED_HI_ALWAYS 1
@@ -39,6 +50,7 @@ struct FillArgs {
   double *cta_hist;      /* [n_hist_copies][hist_len] partial histograms (zeroed before launch)     */
   unsigned long long *flags; /* [0] = number of non-finite weights seen, [2] = fixed-point histogram range exceeded */
   const int *fixed_exp;  /* HIST_SMEM_FIXED: the exponent E of this iteration's scale 2^E (device memory)      */
+  int fixed_bias;        /* added to E (0; the tests raise it through MCIB200_FIXED_EXP_BIAS to provoke the overflow report) */
   uint64_t iter;
   uint64_t neval_per_block;
   int n_local_blocks, rank, world; /* this rank runs blocks b = rank + k*world                      */
@@ -86,12 +98,20 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
       const unsigned long long nw = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[q]) + v);
       asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(got[q]) : "r"(a[q]), "l"(old[q]), "l"(nw) : "memory");
     }
+#if MCI_LOST_LOP3
   /* did any of the B swaps lose?  OR of the XORs: two LOP3 per update (the 64-bit compares cost 3.6 ISETP each) */
   unsigned long long diff = 0;
 #pragma unroll
   for (int q = 0; q < B; ++q)
     if (p0 + q < MAXD && (EXACT || p0 + q < n)) diff |= got[q] ^ old[q];
-  if (diff != 0) {
+  const bool lost = diff != 0;
+#else
+  bool lost = false;
+#pragma unroll
+  for (int q = 0; q < B; ++q)
+    if (p0 + q < MAXD && (EXACT || p0 + q < n)) lost = lost || (got[q] != old[q]);
+#endif
+  if (lost) {
 #pragma unroll
     for (int q = 0; q < B; ++q)
       if (p0 + q < MAXD && (EXACT || p0 + q < n))
@@ -103,8 +123,17 @@ __device__ __forceinline__ void hist_batch(uint32_t hist_saddr, const int *bin, 
  * low limb is added with the returning form of the native shared-memory integer add; its carry — (old + lo) wrapped —
  * joins the high limb, which a second, non-returning add applies.  Integer adds commute: the cell ends up with the
  * exact sum whatever the interleaving of threads, so the histogram is bit-reproducible. */
+/* one such update (the generic kernel: bins of different leaves, run-time layout) */
+__device__ __forceinline__ void fixed_add1(uint32_t saddr, uint32_t xlo, uint32_t xhi, uint32_t &ovf) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(xlo) : "memory");
+  asm volatile("{\n\t.reg .u32 t, h, oh;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 h, %3, 0;\n\t"
+               "atom.shared.add.u32 oh, [%4+4], h;\n\tadd.cc.u32 t, oh, h;\n\taddc.u32 %0, %0, 0;\n\t}"
+               : "+r"(ovf) : "r"(old), "r"(xlo), "r"(xhi), "r"(saddr) : "memory");
+}
+
 template <int B, int MAXD, bool EXACT>
-__device__ __forceinline__ void fixed_batch(uint32_t hist_saddr, const int *bin, int p0, int n, uint32_t xlo, uint32_t xhi) {
+__device__ __forceinline__ void fixed_batch(uint32_t hist_saddr, const int *bin, int p0, int n, uint32_t xlo, uint32_t xhi, uint32_t &ovf) {
   uint32_t a[B], old[B];
 #pragma unroll
   for (int q = 0; q < B; ++q) /* the B low-limb adds go out back to back: their return values are independent */
@@ -116,11 +145,12 @@ __device__ __forceinline__ void fixed_batch(uint32_t hist_saddr, const int *bin,
   for (int q = 0; q < B; ++q) /* carry + high limb */
     if (p0 + q < MAXD && (EXACT || p0 + q < n)) {
 #if MCI_FIXED_HI_ALWAYS
-      /* unconditional: 5 instructions per update (address, add, carry, high word, add).  ptxas turns a predicated
-       * shared-memory atomic into a branch around it (+4 instructions), which costs more than the add it skips */
-      asm volatile("{\n\t.reg .u32 t, h;\n\tadd.cc.u32 t, %0, %1;\n\taddc.u32 h, %2, 0;\n\t"
-                   "red.shared.add.u32 [%3+4], h;\n\t}"
-                   ::"r"(old[q]), "r"(xlo), "r"(xhi), "r"(a[q]) : "memory");
+      /* unconditional (ptxas turns a predicated shared-memory atomic into a branch around it, +4 instructions, which
+       * costs more than the add it skips); the returning form, so that an overflow of the cell — the high limb wrapping —
+       * is seen by the add that causes it: 7 instructions per update */
+      asm volatile("{\n\t.reg .u32 t, h, oh;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 h, %3, 0;\n\t"
+                   "atom.shared.add.u32 oh, [%4+4], h;\n\tadd.cc.u32 t, oh, h;\n\taddc.u32 %0, %0, 0;\n\t}"
+                   : "+r"(ovf) : "r"(old[q]), "r"(xlo), "r"(xhi), "r"(a[q]) : "memory");
 #else
       asm volatile("{\n\t.reg .u32 t, h;\n\t.reg .pred q;\n\tadd.cc.u32 t, %0, %1;\n\taddc.u32 h, %2, 0;\n\t"
                    "setp.ne.u32 q, h, 0;\n\t@q red.shared.add.u32 [%3+4], h;\n\t}"
@@ -156,17 +186,8 @@ struct PoolMap {
  * largest pool); the association differs from the reference's prod 1/prob by a few ulp (L0: jac rtol 1e-13). */
 template <int MAXD, bool EXACT>
 struct PoolJac {
-  double n_lo, n_hi; /* N^h, N^(d-h) */
-  int h;
-  __device__ __forceinline__ void init(double nbins_d, int d) {
-    h = (d + 1) >> 1;
-    n_lo = n_hi = 1.0;
-#pragma unroll
-    for (int p = 0; p < (MAXD + 1) / 2; ++p) {
-      if (p < h) n_lo *= nbins_d;
-      if (p < d - h) n_hi *= nbins_d;
-    }
-  }
+  int h; /* the powers themselves are read from the problem descriptor (constant bank): no registers held across the loop */
+  __device__ __forceinline__ void init(int d) { h = (d + 1) >> 1; }
 };
 
 /* the draws of one sample on the pool: slots 1..d from Philox calls (s, j, block), two slots per call
@@ -174,39 +195,50 @@ struct PoolJac {
 template <int MAXD, bool EXACT, bool CAN_PAD, int REP>
 __device__ __forceinline__ void pool_draw(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M, const PoolJac<MAXD, EXACT> &J,
                                           uint64_t s, uint32_t block, PoolX<MAXD> &X, int *bin, double *prob, double &jac) {
-  const double nbins_d = P.leaf[0].nbins_d, neg_nbins_d = -nbins_d;
+  const double nbins_d = P.leaf[0].nbins_d;
+#if MCI_POOL_FMA_INDEX
+  const double neg_nbins_d = -nbins_d;
+#endif
   const int d = EXACT ? MAXD : P.maxdof[0];
-  jac = J.n_lo;
+  jac = MCI_POOL_HALF_JAC ? P.pool_npow[0] : 1.0;
 #pragma unroll
   for (int j = 0; j < (MAXD + 1) / 2; ++j) {
     if (2 * j < d) {
       uint32_t o0, o1, o2, o3;
       philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)j, block, K, o0, o1, o2, o3);
-      double dx, dy, g;
-      map_index_m(nbins_d, neg_nbins_d, m52(o0, o1), bin[2 * j], dy);
-      M.lookup(bin[2 * j], g, dx);
-      X.v[2 * j] = __dadd_rn(g, __dmul_rn(dy, dx));
-      if (2 * j == J.h) jac *= J.n_hi;
-      jac *= dx;
-      if (CAN_PAD && P.need_pad) prob[2 * j] = 1.0 / __dmul_rn(nbins_d, dx);
-      if (2 * j + 1 < MAXD && 2 * j + 1 < d) {
-        map_index_m(nbins_d, neg_nbins_d, m52(o2, o3), bin[2 * j + 1], dy);
-        M.lookup(bin[2 * j + 1], g, dx);
-        X.v[2 * j + 1] = __dadd_rn(g, __dmul_rn(dy, dx));
-        if (2 * j + 1 == J.h) jac *= J.n_hi;
-        jac *= dx;
-        if (CAN_PAD && P.need_pad) prob[2 * j + 1] = 1.0 / __dmul_rn(nbins_d, dx);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int p = 2 * j + e;
+        if (p < MAXD && p < d) {
+          double dx, dy, g;
+#if MCI_POOL_FMA_INDEX
+          map_index_m(nbins_d, neg_nbins_d, e ? m52(o2, o3) : m52(o0, o1), bin[p], dy);
+#else
+          map_index(P.leaf[0].nbins, nbins_d, e ? u52(o2, o3) : u52(o0, o1), bin[p], dy);
+#endif
+          M.lookup(bin[p], g, dx);
+          X.v[p] = __dadd_rn(g, __dmul_rn(dy, dx));
+#if MCI_POOL_HALF_JAC
+          if (p == J.h) jac *= P.pool_npow[1];
+          jac *= dx;
+          if (CAN_PAD && P.need_pad) prob[p] = 1.0 / __dmul_rn(nbins_d, dx);
+#else
+          const double ndx = __dmul_rn(nbins_d, dx);
+          jac *= ndx;
+          if (CAN_PAD && P.need_pad) prob[p] = 1.0 / ndx;
+#endif
+        }
       }
     }
   }
-  if (J.h >= d) jac *= J.n_hi; /* d == 1: the second half is empty (n_hi = 1) */
+  if (MCI_POOL_HALF_JAC && J.h >= d) jac *= P.pool_npow[1]; /* d == 1: the second half is empty (N^0 = 1) */
 }
 
 template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD, int REP>
 __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M, const PoolJac<MAXD, EXACT> &J,
                                             uint32_t hist_saddr, double *__restrict__ ghist, uint64_t s, uint32_t block,
                                             bool active, double *acc, int &cnt, unsigned long long &bad, double fx_scale,
-                                            double &fx_total) {
+                                            uint32_t &fx_ovf) {
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr bool CAN_PAD = NI > 1 && !EXACT; /* one integrand, or EXACT: dof == maxdof by construction */
@@ -257,12 +289,12 @@ __device__ __forceinline__ void pool_sample(const Problem &P, const PhiloxKey &K
       if constexpr (HMODE == HIST_SMEM_FIXED) {
         /* one conversion per (sample, pass): X = round-to-nearest(w2 2^E); every slot then adds the same integer */
         const double xs = w2 * fx_scale;
-        fx_total += xs; /* range check at CTA exit: no cell can exceed the sum of everything this CTA added */
-        const unsigned long long Xi = xs < 4.6e18 ? __double2ull_rn(xs) : 0ull;
-        if (!(xs < 4.6e18)) fx_total = 1.0e300; /* a single weight beyond 2^62 (or NaN): trip the check */
+        const bool in_range = xs < 9.0e18; /* below 2^63 (false for NaN too): a larger weight is reported, not wrapped */
+        const unsigned long long Xi = in_range ? __double2ull_rn(xs) : 0ull;
+        if (!in_range) fx_ovf = 1u;
         const uint32_t xlo = (uint32_t)Xi, xhi = (uint32_t)(Xi >> 32);
 #pragma unroll
-        for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) fixed_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, xlo, xhi);
+        for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) fixed_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, xlo, xhi, fx_ovf);
       } else if constexpr (HMODE == HIST_SMEM_STRIPED && MCI_HIST_BATCH > 1) {
 #pragma unroll
         for (int p0 = 0; p0 < MAXD; p0 += MCI_HIST_BATCH) hist_batch<MCI_HIST_BATCH, MAXD, EXACT>(hist_saddr, bin, p0, di, w2);
@@ -290,6 +322,9 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
+  /* HIST_SMEM_FIXED handles launch the fixed-point kernel AND the fp64 striped kernel every iteration; the scale the device
+   * chose after the previous iteration says whose turn it is (valid: fixed-point; invalid: fp64), the other returns at once */
+  if (A.fixed_exp != nullptr && (HMODE == HIST_SMEM_FIXED) != (*A.fixed_exp != FIXED_EXP_INVALID)) return;
   static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED ||
                     HMODE == HIST_SMEM_FIXED, "pool kernel histogram modes");
   static_assert(IntegrandWD<FID>::value == 1, "complex integrands run on the generic kernel");
@@ -320,10 +355,10 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   const uint32_t hist_saddr = (uint32_t)__cvta_generic_to_shared(shist) + (STRIPED ? 8u * (lane & (STRIPE - 1)) : 0u);
   /* fixed-point cells: scale 2^E of this iteration, chosen on the device after the previous one (fixed_scale_kernel) */
   int fx_exp = 0;
-  double fx_scale = 1.0, fx_total = 0.0;
+  double fx_scale = 1.0;
+  uint32_t fx_ovf = 0u;
   if (HMODE == HIST_SMEM_FIXED) {
-    fx_exp = *A.fixed_exp;
-    if (fx_exp == FIXED_EXP_INVALID) { fx_exp = 0; fx_total = 1.0e300; } /* no usable scale: report it */
+    fx_exp = *A.fixed_exp + A.fixed_bias;
     fx_scale = scalbn(1.0, fx_exp);
   }
   double *ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
@@ -332,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   philox_expand_key(P.seed, A.iter, K);
   unsigned long long bad = 0;
   PoolJac<MAXD, EXACT> J;
-  J.init(P.leaf[0].nbins_d, EXACT ? MAXD : P.maxdof[0]);
+  J.init(EXACT ? MAXD : P.maxdof[0]);
 
   const int n_tiles = A.n_local_blocks * A.tiles_per_block;
   const uint64_t tile_samples = (uint64_t)THREADS * A.spt;
@@ -349,18 +384,18 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
       if (adapt) {
         for (int k = 0; k < A.spt; ++k)
           pool_sample<FID, MAXD, HMODE, EXACT, false, REP>(P, K, M, J, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid, block,
-                                                       true, acc, cnt, bad, fx_scale, fx_total);
+                                                       true, acc, cnt, bad, fx_scale, fx_ovf);
       } else {
         for (int k = 0; k < A.spt; ++k)
           pool_sample<FID, MAXD, HIST_NONE, EXACT, false, REP>(P, K, M, J, hist_saddr, ghist, s0 + (uint64_t)k * THREADS + tid,
-                                                           block, true, acc, cnt, bad, fx_scale, fx_total);
+                                                           block, true, acc, cnt, bad, fx_scale, fx_ovf);
       }
     } else { /* ragged last tile of a block */
       for (int k = 0; k < A.spt; ++k) {
         const uint64_t s = s0 + (uint64_t)k * THREADS + tid;
         const bool active = s < A.neval_per_block;
-        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_total);
-        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_total);
+        if (adapt) pool_sample<FID, MAXD, HMODE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_ovf);
+        else pool_sample<FID, MAXD, HIST_NONE, EXACT, true, REP>(P, K, M, J, hist_saddr, ghist, s, block, active, acc, cnt, bad, fx_scale, fx_ovf);
       }
     }
     /* tile flush: warp shuffle -> shared -> one thread sums the warps in order */
@@ -387,11 +422,7 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
     }
   }
   if (bad) atomicAdd(A.flags, bad);
-  if (HMODE == HIST_SMEM_FIXED) { /* range check: every cell <= the sum of all weights this CTA added, which must stay below
-                                     2^63: each of the <= 32 warps below 2^58 */
-    const double t = warp_sum(fx_total);
-    if (lane == 0 && !(t < 2.8e17)) atomicAdd(A.flags + 2, 1ull);
-  }
+  if (HMODE == HIST_SMEM_FIXED && fx_ovf) atomicAdd(A.flags + 2, 1ull); /* a weight beyond 2^63 units or a cell that wrapped */
   /* histogram flush: one global partial per CTA (stripes summed in a fixed order) */
   if (NCOPY > 0) {
     __syncthreads();
@@ -492,17 +523,28 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   double *smaps = smem;
   const int map_smem = A.maps_in_smem ? P.map_doubles : 0;
   double *shist = smem + map_smem;
-  const int hmode = A.hist_mode;
-  double *sred = shist + (hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (hmode == HIST_SMEM_ATOMIC ? P.hist_len : 0));
+  /* HIST_SMEM_FIXED: one CTA-shared histogram of 64-bit fixed-point cells (native integer adds, mci_device.cuh) while the
+   * device-side scale is valid; the same shared array as fp64 cells with compare-and-swap adds while it is not */
+  int hmode = A.hist_mode, fx_exp = 0;
+  double fx_scale = 1.0;
+  uint32_t fx_ovf = 0u;
+  const bool fixed_req = hmode == HIST_SMEM_FIXED;
+  if (fixed_req) {
+    fx_exp = *A.fixed_exp;
+    if (fx_exp == FIXED_EXP_INVALID) hmode = HIST_SMEM_ATOMIC;
+    else { fx_exp += A.fixed_bias; fx_scale = scalbn(1.0, fx_exp); }
+  }
+  const bool one_smem_copy = hmode == HIST_SMEM_ATOMIC || hmode == HIST_SMEM_FIXED;
+  double *sred = shist + (hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (one_smem_copy ? P.hist_len : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (A.maps_in_smem) stage_maps(P, smaps, A.gmaps);
-  const int nsh = hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (hmode == HIST_SMEM_ATOMIC ? P.hist_len : 0);
+  const int nsh = hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (one_smem_copy ? P.hist_len : 0);
   for (int i = tid; i < nsh; i += THREADS) shist[i] = 0.0;
   __syncthreads();
   const double *maps = A.maps_in_smem ? smaps : A.gmaps;
   double *myhist = hmode == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
-                   : hmode == HIST_SMEM_ATOMIC ? shist
+                   : one_smem_copy ? shist
                                                : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
@@ -550,7 +592,27 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
         }
         cnt++;
       }
-      if (hmode != HIST_NONE) {
+      if (hmode == HIST_SMEM_FIXED) {
+        const uint32_t cells = (uint32_t)__cvta_generic_to_shared(shist);
+        MCI_UNROLL_LAYOUT
+        for (int i = 0; i < NI; ++i) {
+          const double a = wabs<WD>(w, i) * jac;
+          const double xs = a * a * fx_scale; /* one conversion per (sample, integrand): every slot adds the same integer */
+          const bool in_range = xs < 9.0e18;
+          const unsigned long long Xi = in_range ? __double2ull_rn(xs) : 0ull;
+          if (active && !in_range) fx_ovf = 1u;
+          const uint32_t xlo = (uint32_t)Xi, xhi = (uint32_t)(Xi >> 32);
+          MCI_UNROLL_LAYOUT
+          for (int v = 0; v < P.nv; ++v)
+            MCI_UNROLL_LAYOUT
+            for (int p = 0; p < P.dof[i * P.nv + v]; ++p)
+              MCI_UNROLL_LAYOUT
+              for (int l = 0; l < P.top_nleaf[v]; ++l) {
+                const DevLeaf &L = P.leaf[P.top_first[v] + l];
+                if (L.adapt && active) fixed_add1(cells + 8u * (uint32_t)(L.hist_off + bin[L.base + p * L.stride]), xlo, xhi, fx_ovf);
+              }
+        }
+      } else if (hmode != HIST_NONE) {
         MCI_UNROLL_LAYOUT
         for (int v = 0; v < P.nv; ++v)
           MCI_UNROLL_LAYOUT
@@ -584,7 +646,14 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
     }
   }
   if (bad) atomicAdd(A.flags, bad);
-  if (hmode == HIST_WARP_PRIVATE || hmode == HIST_SMEM_ATOMIC) {
+  if (fx_ovf) atomicAdd(A.flags + 2, 1ull);
+  if (hmode == HIST_SMEM_FIXED) { /* one conversion per bin and an exact power-of-two scaling */
+    __syncthreads();
+    double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
+    const unsigned long long *cells = reinterpret_cast<const unsigned long long *>(shist);
+    const double inv = scalbn(1.0, -fx_exp);
+    for (int i = tid; i < P.hist_len; i += THREADS) out[i] = (double)cells[i] * inv;
+  } else if (hmode == HIST_WARP_PRIVATE || hmode == HIST_SMEM_ATOMIC) {
     __syncthreads();
     double *out = A.cta_hist + (size_t)blockIdx.x * P.hist_len;
     for (int i = tid; i < P.hist_len; i += THREADS) {
@@ -631,7 +700,7 @@ __global__ void vegas_pool_trace_kernel(const __grid_constant__ DevProblem Pp, c
   PoolMap<1> M;
   M.pair = reinterpret_cast<const double2 *>(gmaps);
   PoolJac<MAXD, false> J;
-  J.init(P.leaf[0].nbins_d, P.maxdof[0]);
+  J.init(P.maxdof[0]);
   PoolX<MAXD> X;
   int bin[MAXD];
   double prob[1], jac, w[NI];

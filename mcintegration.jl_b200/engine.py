@@ -128,7 +128,8 @@ class HandleEngine:
         x = np.zeros((count, nd))
         bins = np.zeros((count, nd), dtype=np.int32)
         jac = np.zeros(count)
-        w = np.zeros((count, self.spec.n_integrand))
+        # integrand values: one double per integrand, (re, im) pairs for complex weights (MCI_WEIGHT_COMPLEX)
+        w = np.zeros((count, self.spec.n_integrand * (2 if self.spec.weight_kind == _abi.WEIGHT_COMPLEX else 1)))
         self._check(self._fn("trace_samples")(self.h, int(it), int(block), int(first), int(count), _dp(x),
                                               bins.ctypes.data_as(C.POINTER(C.c_int32)), _dp(jac), _dp(w)))
         return x, bins, jac, w

@@ -98,7 +98,8 @@ def test_L1_vegas_iteration(name):
         gpu.close(); cpu.close()
 
 
-@pytest.mark.parametrize("policy", [_abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED, _abi.HIST_WARP_PRIVATE, _abi.HIST_SMEM_STRIPED])
+@pytest.mark.parametrize("policy", [_abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED, _abi.HIST_WARP_PRIVATE, _abi.HIST_SMEM_STRIPED,
+                                    _abi.HIST_SMEM_FIXED])
 @pytest.mark.parametrize("name", ["gauss10", "sphere2", "bubble", "genz6_comp"])
 def test_L1_hist_policies(name, policy):
     gpu, cpu, _ = _pair(name, "vegas", neval_per_block=3000, hist_policy=policy)
@@ -404,11 +405,18 @@ def test_warm_restart_like_the_reference():
     from mcintegration_jl_b200.integrands import lindhard_finite_temperature
     for i, q in enumerate(c["para"].extQ):
         assert abs(r2.mean[0][i] - lindhard_finite_temperature(c["para"], q)) < 7 * r2.stdev[0][i]
-    o1 = oracle_integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8,
+    # The trained map against the oracle's.  The adaptive iteration is chaotic for this problem (alpha = 3, ~100 samples per
+    # increment): on the ORACLE ALONE a 1e-13 relative perturbation of the starting grid grows to 1.2e-3 after ten
+    # refinements (a factor ~10 per iteration; measured, round 2), so a ten-iteration grid comparison only measures luck.
+    # Three iterations keep the ulp-level differences between the device and the oracle (summation order, libm) far below
+    # a meaningful tolerance:
+    g3 = mci.integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8, niter=3,
+                       config=mci.Configuration(seed=3, **c["cfg"]()))
+    o3 = oracle_integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8, niter=3,
                           config=mci.Configuration(seed=3, **c["cfg"]()))
-    # g1: before the restart trained it further.  Ten refinements compound the 1e-12 histogram differences (each
-    # iteration's samples are drawn through the previous grid): grids agree to ~5e-6
-    np.testing.assert_allclose(g1, o1.config.var[0].grid, rtol=1e-4, atol=1e-9)
+    for k in range(4):
+        np.testing.assert_allclose(g3.config.var[k].grid, o3.config.var[k].grid, rtol=1e-8, atol=1e-11)
+    assert abs(g3.mean[0][0] - o3.mean[0][0]) <= 1e-9 * abs(o3.mean[0][0]) + 1e-3 * o3.stdev[0][0]
 
 
 @pytest.mark.parametrize("name,solver", [("bubble", "vegasmc"), ("product4", "mcmc"), ("sphere2", "mcmc")])
