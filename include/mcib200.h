@@ -198,9 +198,11 @@ enum { MCI_JIT_AUTO = 0, MCI_JIT_ON = 1, MCI_JIT_OFF = 2 };
  *   SMEM_FIXED   (single-pool VEGAS kernel, opt-in) the striped copies as 64-bit FIXED-POINT cells of two u32 limbs updated
  *                with the native shared-memory integer add (sm_100a has no native shared fp64 add: every fp64 update is a
  *                load + add + compare-and-swap).  A sample's weight is scaled by a power of two chosen on the device from
- *                the previous iteration's histogram, rounded to nearest once and added exactly: the sums are
- *                order-independent, i.e. bit-reproducible.  The first iteration of a handle (no scale yet) runs SMEM_STRIPED;
- *                a weight beyond the fixed-point range makes mci_fetch_iteration fail with MCI_ERR_NUMERIC. */
+ *                the largest bin of the previous iteration's histogram (2^58 units), rounded to nearest once and added
+ *                exactly: the sums are order-independent, i.e. bit-reproducible.  Iterations whose histogram has not settled
+ *                within 2^8 of the one before (the first two of an untrained map) run the fp64 kernel; a bin that outgrows
+ *                the 2^6 of headroom is detected at the add that wraps and the iteration is recomputed in fp64 at once
+ *                (mci_hist_rescues counts them).  Also available on any layout of the generic VEGAS kernel (one shared copy). */
 enum { MCI_HIST_AUTO = 0, MCI_HIST_SMEM_ATOMIC = 1, MCI_HIST_GLOBAL_RED = 2, MCI_HIST_WARP_PRIVATE = 3, MCI_HIST_SMEM_STRIPED = 4,
        MCI_HIST_SMEM_FIXED = 5 };
 
@@ -352,6 +354,13 @@ int mci_nonfinite_count(const mci_handle_t *h, uint64_t *n);
  */
 int mci_run_iterations(mci_handle_t *h, uint64_t first_iter, int32_t niter, double gamma, const double *goal,
                        int32_t do_reweight, int32_t do_refine, mci_iteration_out_t *out);
+
+/*
+ * MCI_HIST_SMEM_FIXED: number of fetched iterations whose fixed-point histogram left its 64-bit range (a bin outgrew the
+ * largest bin of the iteration before by more than 2^6) and were recomputed on the spot by the fp64 launch that follows
+ * every fixed-point launch.  Informational: the statistics handed out are the fp64 ones.
+ */
+int mci_hist_rescues(const mci_handle_t *h, uint64_t *n);
 
 /* measurement helpers ---------------------------------------------------- */
 /* number of kernel launches issued by this handle so far */

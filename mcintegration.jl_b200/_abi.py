@@ -146,6 +146,7 @@ EXPORTS = [
     "mci_chain_info",
     "mci_nonfinite_count",
     "mci_run_iterations",
+    "mci_hist_rescues",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -205,6 +206,7 @@ def declare(lib, prefix="mci_"):
         f("chain_info", C.c_int, [H, ip, C.POINTER(C.c_uint64), ip])
         f("launch_info", C.c_int, [H, ip, ip, C.POINTER(C.c_int64), ip, ip, ip])
         f("nonfinite_count", C.c_int, [H, C.POINTER(C.c_uint64)])
+        f("hist_rescues", C.c_int, [H, C.POINTER(C.c_uint64)])
         f("run_iterations", C.c_int, [H, C.c_uint64, C.c_int32, C.c_double, dp, C.c_int32, C.c_int32, C.POINTER(IterationOut)])
     return lib
 

@@ -71,11 +71,21 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 thread_local char g_err[256];
 /* auto policy of the pool kernel = 16 bank-striped shared copies: measured 39.8 vs 28.0 G samples/s (one shared copy) on C2, profiles/r1_hist_policy_sweeps.jsonl */
 constexpr bool MCI_AUTO_STRIPED = true;
-/* auto policy of the generic kernel where the fp64 histogram would have to live in L2: fixed-point cells in shared memory */
+/* auto policy of the generic kernel wherever the cells of all leaves fit in shared memory: fixed-point cells.  Measured
+ * (B200, 16 blocks x 2^22 samples, G samples/s, fp64 automatic choice -> fixed point): 16-leaf composite Genz (BASELINE C3-B,
+ * fp64 = L2 reductions) 9.07 -> 16.41; 6-leaf composite 23.50 -> 32.06; example/bubble.jl under :vegas 19.90 -> 22.12
+ * (profiles/r2_hist_fixed_point.jsonl) */
 #ifndef MCI_AUTO_FIXED_GENERIC_DEFAULT
-#define MCI_AUTO_FIXED_GENERIC_DEFAULT 0
+#define MCI_AUTO_FIXED_GENERIC_DEFAULT 1
 #endif
 constexpr bool MCI_AUTO_FIXED_GENERIC = MCI_AUTO_FIXED_GENERIC_DEFAULT != 0;
+/* auto policy of the pool kernel: the striped copies as fixed-point cells.  Measured (same job, G samples/s, fp64 striped
+ * copies -> fixed point): C2 42.3 -> 53.0, C3-A 22.7 -> 34.5, C5 integrand under :vegas 16.3 -> 21.7
+ * (profiles/r2_hist_fixed_point.jsonl) */
+#ifndef MCI_AUTO_FIXED_POOL_DEFAULT
+#define MCI_AUTO_FIXED_POOL_DEFAULT 1
+#endif
+constexpr bool MCI_AUTO_FIXED_POOL = MCI_AUTO_FIXED_POOL_DEFAULT != 0;
 }  // namespace
 
 struct mci_handle_t {
@@ -101,6 +111,7 @@ struct mci_handle_t {
   unsigned long long *d_flags = nullptr; /* [4]: non-finite weights, mcmc walkers without a start, fixed-point range, spare */
   int *d_err = nullptr, *d_fixed_exp = nullptr;
   double *d_fixed_state = nullptr; /* largest histogram bin of the previous iteration (fixed_scale_kernel) */
+  double *d_stage = nullptr;       /* staging area of mci_set_maps on fixed-point handles: grids | dist */
   /* the buffers above are carved out of three allocations (cudaMalloc / cudaFree / cudaMallocHost cost 0.1-1 ms each
    * and synchronise the device: a job of the reference's default size, neval = 1e4, is over in 4 ms):
    * the fixed state, the per-launch partials (re-planned by mci_set_partition) and the pinned host mirrors */
@@ -128,11 +139,13 @@ struct mci_handle_t {
   /* JIT specialisation (mci_jit.cu) */
   bool use_jit = false;
   std::string user_source, kernel_name_jit;
+  bool kernel_name_is_jit() const { return kernel_name == kernel_name_jit.c_str() && !kernel_name_jit.empty(); }
   const void *jit_lib = nullptr, *trace_kernel = nullptr;
   bool jit_failed = false;
   int jit_mode = 0, chain_maxt = 1024;
   uint64_t launches = 0;
   uint64_t nonfinite = 0; /* non-finite integrand values of the last fetched iteration (flags[0]) */
+  uint64_t hist_rescues = 0; /* fetched iterations whose fixed-point histogram was recomputed in fp64 (flags[3]) */
   float fill_ms = 0.f, iter_ms = 0.f;
   char err[256];
 };
@@ -280,6 +293,12 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   }
   std::vector<std::string> exprs{name};
   if (kind == 0) { char t[80]; snprintf(t, sizeof t, "mci::vegas_pool_trace_kernel<%d, %d>", P.fid, P.maxdof[0]); exprs.push_back(t); }
+  const bool with_twin = kind == 0 && mode == HIST_SMEM_FIXED; /* the fp64 striped twin of a fixed-point pool kernel: same program */
+  if (with_twin) {
+    char t[160];
+    snprintf(t, sizeof t, "mci::vegas_pool_kernel<%d, %d, %d, %d, %s>", P.fid, P.maxdof[0], HIST_SMEM_STRIPED, threads, exact ? "true" : "false");
+    exprs.push_back(t);
+  }
   if (kind == 1) { char t[64]; snprintf(t, sizeof t, "mci::vegas_trace_kernel<%d>", P.fid); exprs.push_back(t); }
   std::vector<const void *> ks;
   std::string err;
@@ -302,6 +321,7 @@ const void *resolve_kernel(mci_handle_t *h, int kind, int mode, int threads, boo
   if (h->jit_lib) jit_unload(h->jit_lib);
   h->jit_lib = ks.back();
   h->trace_kernel = kind <= 1 ? ks[1] : nullptr;
+  if (with_twin) h->kernel_first = ks[2];
   h->kernel_name_jit = std::string(name) + " [jit]";
   h->kernel_name = h->kernel_name_jit.c_str();
   return ks[0];
@@ -352,21 +372,22 @@ int plan(mci_handle_t *h) {
       /* 16 bank-striped copies of the histogram, one 1024-thread CTA per SM, when they fit */
       const size_t red_s = (size_t)(POOL_THREADS_STRIPED / 32) * (P.ni + 1) * 8;
       const bool striped_fits = (size_t)POOL_MAP_REP * map_bytes + (size_t)STRIPE * hist_bytes + red_s <= SMEM_MAX;
-      /* fixed-point cells: built-in integrands with an ahead-of-time instantiation only (two kernels per handle) */
-      const bool want_fixed = p.hist_policy == MCI_HIST_SMEM_FIXED && P.fid != MCI_F_USER && P.maxdof[0] <= 20 &&
-                              lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_FIXED, nullptr) != nullptr;
+      /* fixed-point cells (two kernels per handle: the fixed-point one and its fp64 twin): asked for, or the automatic choice */
+      const bool want_fixed = (p.hist_policy == MCI_HIST_SMEM_FIXED || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_FIXED_POOL)) &&
+                              P.maxdof[0] <= 20;
       if (P.any_adapt && striped_fits && (p.hist_policy == MCI_HIST_SMEM_STRIPED || want_fixed || (p.hist_policy == MCI_HIST_AUTO && MCI_AUTO_STRIPED))) {
         mode = want_fixed ? HIST_SMEM_FIXED : HIST_SMEM_STRIPED; threads = POOL_THREADS_STRIPED; nwarp = threads / 32; red = red_s;
         hs = (size_t)STRIPE * hist_bytes + (size_t)(POOL_MAP_REP - 1) * map_bytes; h->maps_in_smem = 1;
       }
       if (h->maps_in_smem) {
-        const void *k = nullptr;
-        if (mode == HIST_SMEM_FIXED) { /* iterations without a scale yet run the fp64 striped kernel of the same shape */
-          k = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_FIXED, &h->kernel_name);
+        const void *k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
+        if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
+        if (k && mode == HIST_SMEM_FIXED && !h->kernel_name_is_jit()) {
+          /* ahead-of-time build: the fp64 striped instantiation of the same shape is the twin */
           h->kernel_first = lookup_vegas_pool(P.fid, P.maxdof[0], !P.need_pad, HIST_SMEM_STRIPED, nullptr);
-          if (!h->kernel_first) k = nullptr;
-          if (k) h->use_jit = false;
-        } else {
+        }
+        if (mode == HIST_SMEM_FIXED && (!k || !h->kernel_first)) { /* no fixed-point pair for this problem: plain striped copies */
+          mode = HIST_SMEM_STRIPED; h->kernel_first = nullptr;
           k = resolve_kernel(h, 0, mode, threads, !P.need_pad);
           if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
         }
@@ -392,12 +413,14 @@ int plan(mci_handle_t *h) {
        * second CTA).  Large histograms take one 1024-thread CTA per SM; the maps then stay in global memory (L1 / L2 hits)
        * unless they fit beside the cells */
       const bool fixed_ok = P.any_adapt && hist_bytes + (size_t)(GENERIC_THREADS_BIG / 32) * (P.obs_total + 1) * 8 + 1024 <= SMEM_MAX;
-      if (fixed_ok && (p.hist_policy == MCI_HIST_SMEM_FIXED || (p.hist_policy == MCI_HIST_AUTO && mode == HIST_GLOBAL_RED && MCI_AUTO_FIXED_GENERIC))) {
+      if (fixed_ok && (p.hist_policy == MCI_HIST_SMEM_FIXED || (p.hist_policy == MCI_HIST_AUTO && mode != HIST_NONE && MCI_AUTO_FIXED_GENERIC))) {
         mode = HIST_SMEM_FIXED;
-        if (hist_bytes > SMEM_MAX / 4) gthreads = GENERIC_THREADS_BIG;
+        const size_t red_big = (size_t)(GENERIC_THREADS_BIG / 32) * (P.obs_total + 1) * 8;
+        h->maps_in_smem = map_bytes + hist_bytes + red_big <= SMEM_MAX ? 1 : 0;
+        /* more than half of an SM's shared memory per CTA means one CTA per SM: let it be a 1024-thread one */
+        if ((h->maps_in_smem ? map_bytes : 0) + hist_bytes + red > SMEM_MAX / 2) gthreads = GENERIC_THREADS_BIG;
         nwarp = gthreads / 32;
         red = (size_t)nwarp * (P.obs_total + 1) * 8;
-        h->maps_in_smem = map_bytes + hist_bytes + red <= SMEM_MAX ? 1 : 0;
       }
       h->kernel = resolve_kernel(h, 1, mode, gthreads, false);
       if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
@@ -824,14 +847,14 @@ int mci_create(const mci_problem_t *p, mci_handle_t **out) {
     const size_t o_gmaps = D.reserve<double>(mo + 2);
     const size_t o_lg = D.reserve<int>(nleaf), o_ld = D.reserve<int>(nleaf), o_la = D.reserve<int>(nleaf);
     const size_t o_packed = D.reserve<double>(Y.len), o_flags = D.reserve<unsigned long long>(4), o_err = D.reserve<int>(1);
-    const size_t o_fx = D.reserve<int>(1), o_fxs = D.reserve<double>(1);
+    const size_t o_fx = D.reserve<int>(1), o_fxs = D.reserve<double>(1), o_stage = D.reserve<double>(go + dd + 2);
     TRY(arena_device(h, D, &h->d_state_arena, &h->state_cap, false));
     h->d_grids = D.at<double>(o_grids); h->d_dist = D.at<double>(o_dist); h->d_accum = D.at<double>(o_accum);
     h->d_reweight = D.at<double>(o_rw); h->d_goal = D.at<double>(o_goal); h->d_alpha = D.at<double>(o_alpha);
     h->d_gmaps = D.at<double>(o_gmaps);
     h->d_leaf_grid_off = D.at<int>(o_lg); h->d_leaf_dist_off = D.at<int>(o_ld); h->d_leaf_acc_off = D.at<int>(o_la);
     h->d_packed = D.at<double>(o_packed); h->d_flags = D.at<unsigned long long>(o_flags); h->d_err = D.at<int>(o_err);
-    h->d_fixed_exp = D.at<int>(o_fx); h->d_fixed_state = D.at<double>(o_fxs);
+    h->d_fixed_exp = D.at<int>(o_fx); h->d_fixed_state = D.at<double>(o_fxs); h->d_stage = D.at<double>(o_stage);
     Arena H;
     const size_t ho_packed = H.reserve<double>(Y.len), ho_flags = H.reserve<unsigned long long>(4), ho_err = H.reserve<int>(1);
     const size_t ho_init = H.reserve<char>(D.total); /* staging image of the device state */
@@ -891,17 +914,24 @@ int mci_sizes(const mci_handle_t *h, int32_t *grid_len, int32_t *disc_len, int32
 int mci_set_maps(mci_handle_t *h, const double *grids, const double *dist, const double *accum, const double *rw) {
   if (!h) return MCI_ERR_INVALID;
   CU(h, cudaSetDevice(h->device));
-  if (grids && h->grid_len) CU(h, cudaMemcpyAsync(h->d_grids, grids, h->grid_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (dist && h->disc_len) CU(h, cudaMemcpyAsync(h->d_dist, dist, h->disc_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const bool fixed = h->hist_mode == HIST_SMEM_FIXED;
+  if (grids && h->grid_len) {
+    if (fixed) { /* through the staging area: the scale survives only if the maps are the ones already in place (mci_aux.cuh) */
+      CU(h, cudaMemcpyAsync(h->d_stage, grids, h->grid_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      adopt_maps_kernel<<<1, 256, 0, h->stream>>>(h->d_stage, h->d_grids, h->grid_len, h->d_fixed_exp, h->d_fixed_state);
+      h->launches++;
+    } else CU(h, cudaMemcpyAsync(h->d_grids, grids, h->grid_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (dist && h->disc_len) {
+    if (fixed) {
+      CU(h, cudaMemcpyAsync(h->d_stage + h->grid_len, dist, h->disc_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      adopt_maps_kernel<<<1, 256, 0, h->stream>>>(h->d_stage + h->grid_len, h->d_dist, h->disc_len, h->d_fixed_exp, h->d_fixed_state);
+      h->launches++;
+    } else CU(h, cudaMemcpyAsync(h->d_dist, dist, h->disc_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   if (accum && h->accum_len) CU(h, cudaMemcpyAsync(h->d_accum, accum, h->accum_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (rw) CU(h, cudaMemcpyAsync(h->d_reweight, rw, h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (grids && h->hist_mode == HIST_SMEM_FIXED) {
-    /* maps replaced from outside: the fixed-point scale learnt from the old map's histogram says nothing about the
-     * new one — forget it, the fp64 kernel runs until the histogram has settled again */
-    static const int invalid = FIXED_EXP_INVALID;
-    CU(h, cudaMemcpyAsync(h->d_fixed_exp, &invalid, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemsetAsync(h->d_fixed_state, 0, sizeof(double), h->stream));
-  }
+  CU(h, cudaGetLastError());
   CU(h, cudaStreamSynchronize(h->stream)); /* the caller may reuse its buffers */
   h->maps_dirty = true;
   return MCI_OK;
@@ -944,7 +974,7 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   if (p.solver == MCI_SOLVER_VEGAS) {
     FA.gmaps = h->d_gmaps; FA.tile_obs = h->d_tile_obs; FA.tile_cnt = h->d_tile_cnt; FA.cta_hist = h->d_cta_hist;
     FA.flags = h->d_flags; FA.fixed_exp = h->hist_mode == HIST_SMEM_FIXED ? h->d_fixed_exp : nullptr; FA.iter = iter;
-    FA.fixed_bias = 0;
+    FA.fixed_bias = 0; FA.rescue = 0;
     if (const char *e = getenv("MCIB200_FIXED_EXP_BIAS")) FA.fixed_bias = atoi(e); /* test hook: shrink the headroom */ FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
     FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
     FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
@@ -961,9 +991,12 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
   if (!h->ev_fill0[slot]) { CU(h, cudaEventCreate(&h->ev_fill0[slot])); CU(h, cudaEventCreate(&h->ev_fill1[slot])); }
   CU(h, cudaEventRecord(h->ev_fill0[slot], h->stream));
   CU(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
-  if (h->hist_mode == HIST_SMEM_FIXED && h->is_pool) { /* ... and its fp64 twin: the device-side scale decides which of the two works
-                                                           (mci_vegas.cuh); the generic kernel switches inside one launch */
-    CU(h, cudaLaunchKernel(h->kernel_first, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
+  if (h->hist_mode == HIST_SMEM_FIXED) {
+    /* ... and behind it the fp64 launch of the same iteration: it works when the device-side scale is not settled, or when
+     * the fixed-point launch reported that it left its range (rescue), and returns at once otherwise (mci_vegas.cuh).  The
+     * pool layout has a twin kernel for it; the generic kernel is launched a second time in rescue mode */
+    FA.rescue = 1;
+    CU(h, cudaLaunchKernel(h->is_pool ? h->kernel_first : h->kernel, dim3(h->grid), dim3(h->threads), args, h->smem, h->stream));
     h->launches++;
   }
   CU(h, cudaEventRecord(h->ev_fill1[slot], h->stream));
@@ -1018,9 +1051,9 @@ static int unpack_iteration(mci_handle_t *h, const double *pk, const unsigned lo
   if (out->accept) for (int i = 0; i < Y.pa_len; ++i) out->accept[i] = B1 * 1.0e-10 + pk[Y.off_accept + i];
   if (out->neval) *out->neval = (uint64_t)pk[Y.off_neval];
   h->nonfinite = flags[0];
-  if (flags[2])
-    return fail(h, MCI_ERR_NUMERIC, "fixed-point histogram (MCI_HIST_SMEM_FIXED): a bin outgrew the largest bin of the previous "
-                                    "iteration by more than 2^6 and left the 64-bit range; use another hist_policy");
+  if (flags[3]) h->hist_rescues++; /* the fixed-point histogram left its range; the fp64 launch recomputed the iteration */
+  if (flags[2] && !flags[3])
+    return fail(h, MCI_ERR_NUMERIC, "fixed-point histogram (MCI_HIST_SMEM_FIXED): a bin left the 64-bit range and no fp64 rescue ran");
   if (flags[1]) /* mcmc/montecarlo.jl:109-113 */
     return fail(h, MCI_ERR_MCMC_START, "Cannot find the variables that makes the #%d integrand nonzero!", h->dp.start_idx + 1);
   for (int b = 0; b < nb; ++b)
@@ -1300,6 +1333,12 @@ int mci_jit_check(const mci_problem_t *p, char *log, int32_t log_cap) {
 int mci_nonfinite_count(const mci_handle_t *h, uint64_t *n) {
   if (!h || !n) return MCI_ERR_INVALID;
   *n = h->nonfinite;
+  return MCI_OK;
+}
+
+int mci_hist_rescues(const mci_handle_t *h, uint64_t *n) {
+  if (!h || !n) return MCI_ERR_INVALID;
+  *n = h->hist_rescues;
   return MCI_OK;
 }
 

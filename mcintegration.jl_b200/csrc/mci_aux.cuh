@@ -331,6 +331,21 @@ __global__ void fixed_scale_kernel(PackedLayout Y, const double *__restrict__ pa
   }
 }
 
+/* mci_set_maps on a fixed-point handle: move the uploaded maps from the staging area into place and, if they DIFFER from
+ * the maps they replace, forget the fixed-point scale — it was learnt from the old map's histogram and says nothing about
+ * the new one (the fp64 kernel then runs until the histogram has settled again).  A host that hands back the very maps
+ * it read (the end-to-end loop of bench.py; a warm restart of the same handle) keeps the scale. */
+__global__ void adopt_maps_kernel(const double *__restrict__ stage, double *__restrict__ maps, int n, int *__restrict__ fixed_exp,
+                                  double *__restrict__ state) {
+  int changed = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = stage[i];
+    if (__double_as_longlong(v) != __double_as_longlong(maps[i])) changed = 1;
+    maps[i] = v;
+  }
+  if (__syncthreads_or(changed) && threadIdx.x == 0) { *fixed_exp = FIXED_EXP_INVALID; state[0] = 0.0; }
+}
+
 /* mci_run_iterations: keep this iteration's packed statistics and flags in the per-call history (one launch) */
 __global__ void snapshot_kernel(const double *__restrict__ packed, int len, const unsigned long long *__restrict__ flags,
                                 double *__restrict__ rec) {

@@ -48,9 +48,11 @@ struct FillArgs {
   double *tile_obs;      /* [n_tiles_total][obs_total]                                             */
   double *tile_cnt;      /* [n_tiles_total] measured samples of the tile                            */
   double *cta_hist;      /* [n_hist_copies][hist_len] partial histograms (zeroed before launch)     */
-  unsigned long long *flags; /* [0] = number of non-finite weights seen, [2] = fixed-point histogram range exceeded */
+  unsigned long long *flags; /* [0] = number of non-finite weights seen, [2] = fixed-point histogram range exceeded,
+                                [3] = ... and the iteration was recomputed by the fp64 rescue launch                */
   const int *fixed_exp;  /* HIST_SMEM_FIXED: the exponent E of this iteration's scale 2^E (device memory)      */
-  int fixed_bias;        /* added to E (0; the tests raise it through MCIB200_FIXED_EXP_BIAS to provoke the overflow report) */
+  int fixed_bias;        /* added to E (0; the tests raise it through MCIB200_FIXED_EXP_BIAS to provoke an overflow) */
+  int rescue;            /* generic kernel, second launch of an iteration: work only if the first one left the fixed-point range */
   uint64_t iter;
   uint64_t neval_per_block;
   int n_local_blocks, rank, world; /* this rank runs blocks b = rank + k*world                      */
@@ -195,12 +197,17 @@ struct PoolJac {
 template <int MAXD, bool EXACT, bool CAN_PAD, int REP>
 __device__ __forceinline__ void pool_draw(const Problem &P, const PhiloxKey &K, const PoolMap<REP> &M, const PoolJac<MAXD, EXACT> &J,
                                           uint64_t s, uint32_t block, PoolX<MAXD> &X, int *bin, double *prob, double &jac) {
+  /* Which of the two trims pays depends on the register budget (64 at 1024 threads per CTA): the fma index keeps N in a
+   * register pair for the whole sample, the halved Jacobian product changes ptxas' schedule.  Measured per pool size
+   * (A/B of the four combinations in one job, B200, G samples/s, fp64 striped / fixed-point histogram; profiles/
+   * r2_pool_trim_variants.jsonl): d = 10 both (43.9 / 53.0 against 41.1 / 51.1 with neither); d = 16 the fma index alone
+   * (27.0 / 34.8; both: 22.8 / 34.6 — the fp64 variant spills); d = 20 the halved product alone (20.0 / 21.9; both: 16.3 / 21.7) */
+  constexpr bool FMA_INDEX = MCI_POOL_FMA_INDEX && MAXD <= 16;
+  constexpr bool HALF_JAC = MCI_POOL_HALF_JAC && (MAXD <= 12 || MAXD > 16);
   const double nbins_d = P.leaf[0].nbins_d;
-#if MCI_POOL_FMA_INDEX
   const double neg_nbins_d = -nbins_d;
-#endif
   const int d = EXACT ? MAXD : P.maxdof[0];
-  jac = MCI_POOL_HALF_JAC ? P.pool_npow[0] : 1.0;
+  jac = HALF_JAC ? P.pool_npow[0] : 1.0;
 #pragma unroll
   for (int j = 0; j < (MAXD + 1) / 2; ++j) {
     if (2 * j < d) {
@@ -211,27 +218,24 @@ __device__ __forceinline__ void pool_draw(const Problem &P, const PhiloxKey &K, 
         const int p = 2 * j + e;
         if (p < MAXD && p < d) {
           double dx, dy, g;
-#if MCI_POOL_FMA_INDEX
-          map_index_m(nbins_d, neg_nbins_d, e ? m52(o2, o3) : m52(o0, o1), bin[p], dy);
-#else
-          map_index(P.leaf[0].nbins, nbins_d, e ? u52(o2, o3) : u52(o0, o1), bin[p], dy);
-#endif
+          if constexpr (FMA_INDEX) map_index_m(nbins_d, neg_nbins_d, e ? m52(o2, o3) : m52(o0, o1), bin[p], dy);
+          else map_index(P.leaf[0].nbins, nbins_d, e ? u52(o2, o3) : u52(o0, o1), bin[p], dy);
           M.lookup(bin[p], g, dx);
           X.v[p] = __dadd_rn(g, __dmul_rn(dy, dx));
-#if MCI_POOL_HALF_JAC
-          if (p == J.h) jac *= P.pool_npow[1];
-          jac *= dx;
-          if (CAN_PAD && P.need_pad) prob[p] = 1.0 / __dmul_rn(nbins_d, dx);
-#else
-          const double ndx = __dmul_rn(nbins_d, dx);
-          jac *= ndx;
-          if (CAN_PAD && P.need_pad) prob[p] = 1.0 / ndx;
-#endif
+          if constexpr (HALF_JAC) {
+            if (p == J.h) jac *= P.pool_npow[1];
+            jac *= dx;
+            if (CAN_PAD && P.need_pad) prob[p] = 1.0 / __dmul_rn(nbins_d, dx);
+          } else {
+            const double ndx = __dmul_rn(nbins_d, dx);
+            jac *= ndx;
+            if (CAN_PAD && P.need_pad) prob[p] = 1.0 / ndx;
+          }
         }
       }
     }
   }
-  if (MCI_POOL_HALF_JAC && J.h >= d) jac *= P.pool_npow[1]; /* d == 1: the second half is empty (N^0 = 1) */
+  if (HALF_JAC && J.h >= d) jac *= P.pool_npow[1]; /* d == 1: the second half is empty (N^0 = 1) */
 }
 
 template <int FID, int MAXD, int HMODE, bool EXACT, bool GUARD, int REP>
@@ -322,9 +326,21 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   using F = Integrand<FID>;
   constexpr int NI = F::NI;
   constexpr int NWARP = THREADS / 32;
-  /* HIST_SMEM_FIXED handles launch the fixed-point kernel AND the fp64 striped kernel every iteration; the scale the device
-   * chose after the previous iteration says whose turn it is (valid: fixed-point; invalid: fp64), the other returns at once */
-  if (A.fixed_exp != nullptr && (HMODE == HIST_SMEM_FIXED) != (*A.fixed_exp != FIXED_EXP_INVALID)) return;
+  /* HIST_SMEM_FIXED handles launch the fixed-point kernel AND, behind it, the fp64 striped kernel every iteration.  The scale
+   * the device chose after the previous iteration says whose turn it is: valid -> fixed-point, invalid -> fp64, the other
+   * returns at once.  The fp64 kernel is also the RESCUE: if the fixed-point kernel before it reported that a cell or a weight
+   * left the 64-bit range (flags[2]), it recomputes the whole iteration — same samples, same block sums, fp64 histogram —
+   * and says so in flags[3].  No host round trip, so the asynchronous and the fused drivers are covered as well. */
+  bool rescue = false;
+  if (A.fixed_exp != nullptr) {
+    const bool valid = *A.fixed_exp != FIXED_EXP_INVALID;
+    if (HMODE == HIST_SMEM_FIXED) { if (!valid) return; }
+    else {
+      rescue = valid && *reinterpret_cast<volatile unsigned long long *>(A.flags + 2) != 0ull;
+      if (valid && !rescue) return;
+      if (rescue && blockIdx.x == 0 && threadIdx.x == 0) A.flags[3] = 1ull;
+    }
+  }
   static_assert(HMODE == HIST_NONE || HMODE == HIST_SMEM_ATOMIC || HMODE == HIST_SMEM_STRIPED || HMODE == HIST_GLOBAL_RED ||
                     HMODE == HIST_SMEM_FIXED, "pool kernel histogram modes");
   static_assert(IntegrandWD<FID>::value == 1, "complex integrands run on the generic kernel");
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
       }
     }
   }
-  if (bad) atomicAdd(A.flags, bad);
+  if (bad && !rescue) atomicAdd(A.flags, bad); /* (the fixed-point launch of this iteration has counted them already) */
   if (HMODE == HIST_SMEM_FIXED && fx_ovf) atomicAdd(A.flags + 2, 1ull); /* a weight beyond 2^63 units or a cell that wrapped */
   /* histogram flush: one global partial per CTA (stripes summed in a fixed order) */
   if (NCOPY > 0) {
@@ -531,7 +547,11 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   const bool fixed_req = hmode == HIST_SMEM_FIXED;
   if (fixed_req) {
     fx_exp = *A.fixed_exp;
-    if (fx_exp == FIXED_EXP_INVALID) hmode = HIST_SMEM_ATOMIC;
+    if (A.rescue) { /* second launch of the iteration: recompute in fp64 if the first one left the fixed-point range */
+      if (fx_exp == FIXED_EXP_INVALID || *reinterpret_cast<volatile unsigned long long *>(A.flags + 2) == 0ull) return;
+      if (blockIdx.x == 0 && threadIdx.x == 0) A.flags[3] = 1ull;
+      hmode = HIST_SMEM_ATOMIC;
+    } else if (fx_exp == FIXED_EXP_INVALID) hmode = HIST_SMEM_ATOMIC;
     else { fx_exp += A.fixed_bias; fx_scale = scalbn(1.0, fx_exp); }
   }
   const bool one_smem_copy = hmode == HIST_SMEM_ATOMIC || hmode == HIST_SMEM_FIXED;
@@ -645,7 +665,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
       else A.tile_cnt[gt] = t;
     }
   }
-  if (bad) atomicAdd(A.flags, bad);
+  if (bad && !(fixed_req && A.rescue)) atomicAdd(A.flags, bad);
   if (fx_ovf) atomicAdd(A.flags + 2, 1ull);
   if (hmode == HIST_SMEM_FIXED) { /* one conversion per bin and an exact power-of-two scaling */
     __syncthreads();

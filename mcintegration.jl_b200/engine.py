@@ -176,6 +176,12 @@ class CudaEngine(HandleEngine):
         self._check(self.lib.mci_nonfinite_count(self.h, C.byref(n)))
         return n.value
 
+    def hist_rescues(self) -> int:
+        """fetched iterations whose fixed-point histogram left its range and were recomputed in fp64 (mci_hist_rescues)"""
+        n = C.c_uint64()
+        self._check(self.lib.mci_hist_rescues(self.h, C.byref(n)))
+        return n.value
+
     def run_iterations(self, first_iter: int, niter: int, *, gamma=1.0, goal=None, do_reweight=False, do_refine=True):
         """niter whole iterations (fill -> statistics -> doReweight! -> train!) in ONE library call, no host round
         trip in between (mci_run_iterations); returns the IterationStats of every iteration."""

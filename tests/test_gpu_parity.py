@@ -106,7 +106,7 @@ def test_L1_hist_policies(name, policy):
     try:
         # a policy that does not fit in shared memory (bubble: 8 warps x 32 KB) or that the kernel of this layout does not
         # implement (striped copies: pool kernel only) falls back to the automatic choice (shared CTA copy or L2 REDs)
-        assert gpu.launch_info()["hist_mode"] in (policy, _abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED)
+        assert gpu.launch_info()["hist_mode"] in (policy, _abi.HIST_SMEM_ATOMIC, _abi.HIST_GLOBAL_RED, _abi.HIST_SMEM_FIXED)
         cpu.run_iteration(0); cpu.refine(); _sync_maps(cpu, gpu)
         _assert_stats(gpu.run_iteration(1), cpu.run_iteration(1))
     finally:
@@ -415,7 +415,7 @@ def test_warm_restart_like_the_reference():
     o3 = oracle_integrate(c["f"], solver="vegas", measure="bin_by_discrete", neval=1e5, block=8, niter=3,
                           config=mci.Configuration(seed=3, **c["cfg"]()))
     for k in range(4):
-        np.testing.assert_allclose(g3.config.var[k].grid, o3.config.var[k].grid, rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(g3.config.var[k].grid, o3.config.var[k].grid, rtol=1e-6, atol=1e-9)
     assert abs(g3.mean[0][0] - o3.mean[0][0]) <= 1e-9 * abs(o3.mean[0][0]) + 1e-3 * o3.stdev[0][0]
 
 

@@ -115,7 +115,9 @@ def test_user_gaussian_matches_builtin():
             a, c = u.run_iteration(it), b.run_iteration(it)
             np.testing.assert_allclose(a.block_obs, c.block_obs, rtol=1e-12)  # libdevice exp vs exp_nonpos: <= 2 ulp per weight
             assert np.array_equal(a.block_norm, c.block_norm)
-            np.testing.assert_allclose(a.hist, c.hist, rtol=1e-10)
+            # the built-in handle switches to fixed-point histogram cells once its histogram has settled (one unit = 2^-58
+            # of the previous iteration's largest bin, at most half a unit lost per add: tests/test_gpu_round2.py)
+            np.testing.assert_allclose(a.hist, c.hist, rtol=1e-10, atol=c.hist.max() * 2.0 ** -38)
             b.refine()
             u.set_maps(*b.get_maps())
         xu, bu, ju, wu = u.trace_samples(2, 5, 1000, 256)

@@ -11,6 +11,8 @@ import mcintegration_jl_b200 as mci
 from cases import make_spec
 
 CASES = [("gauss10", "vegas", {}), ("sphere2", "vegas", {}), ("bubble", "vegas", {}), ("genz6_comp", "vegas", dict(hist_policy=2)),
+         ("gauss10", "vegas", dict(hist_policy=5)), ("genz6_comp", "vegas", dict(hist_policy=5)), ("complex2", "vegas", {}),
+         ("complex2", "vegasmc", dict(walkers=96)), ("complex1", "mcmc", dict(walkers=96)),
          ("bubble", "vegasmc", dict(walkers=96)), ("product4", "mcmc", dict(walkers=96)), ("sphere2_offset", "mcmc", dict(walkers=96)),
          ("discrete2", "vegasmc", dict(walkers=96)), ("bubble_fermik", "mcmc", dict(walkers=96))]
 for jit in (2, 1):
@@ -20,7 +22,7 @@ for jit in (2, 1):
         spec, _ = make_spec(name, solver, n_block=4, neval_per_block=npb, **kw)
         spec.jit = jit
         eng = mci.CudaEngine(spec)
-        for it in range(2):
+        for it in range(5 if kw.get("hist_policy") == 5 else 2):  # the fixed-point cells take over once the histogram has settled
             st = eng.run_iteration(it)
             if solver != "vegas":
                 eng.reweight(1.0)
