@@ -130,7 +130,6 @@ struct mci_handle_t {
   const char *kernel_name = "";
   bool is_pool = false;
   int threads = 0, grid = 0, hist_mode = 0, n_hist_copies = 1, maps_in_smem = 1;
-  int maps_staged = 0; /* generic VEGAS kernel: doubles of the map image staged in shared memory (all, or a prefix of the leaves) */
   size_t smem = 0;
   int tiles_per_block = 0, spt = 0, ctas_per_block = 0, max_grid = 0, chain_rows = 0, coop_ci = 0, walkers = 1;
   bool has_fermik = false; /* some variable is a FermiK (mcmc only; no cooperative create!) */
@@ -406,7 +405,6 @@ int plan(mci_handle_t *h) {
     }
     if (!h->is_pool) {
       int gthreads = GENERIC_THREADS;
-      size_t staged_bytes = 0;
       int nwarp = gthreads / 32;
       size_t red = (size_t)nwarp * (P.obs_total + 1) * 8;
       int mode = pick_hist(nwarp, red, true);
@@ -419,18 +417,8 @@ int plan(mci_handle_t *h) {
         mode = HIST_SMEM_FIXED;
         const size_t red_big = (size_t)(GENERIC_THREADS_BIG / 32) * (P.obs_total + 1) * 8;
         h->maps_in_smem = map_bytes + hist_bytes + red_big <= SMEM_MAX ? 1 : 0;
-        staged_bytes = h->maps_in_smem ? map_bytes : 0;
-        if (!h->maps_in_smem) {
-          /* the maps do not all fit beside the cells: stage the leading leaves that do (BASELINE C3-B: 6 of its 16 grids),
-           * the others are read from global memory through L1 / L2 */
-          const size_t room = SMEM_MAX - hist_bytes - red_big;
-          for (int l = 0; l < P.nleaf; ++l) { /* end of leaf l's tables in the image, rounded up to the 16-byte staging unit */
-            const size_t end = (((size_t)(P.leaf[l].smem_off + 2 * P.leaf[l].nbins + (P.leaf[l].kind == MCI_LEAF_CONTINUOUS ? 0 : 1)) * 8) + 15) & ~(size_t)15;
-            if (end <= room) staged_bytes = std::max(staged_bytes, end);
-          }
-        }
         /* more than half of an SM's shared memory per CTA means one CTA per SM: let it be a 1024-thread one */
-        if (staged_bytes + hist_bytes + red > SMEM_MAX / 2) gthreads = GENERIC_THREADS_BIG;
+        if ((h->maps_in_smem ? map_bytes : 0) + hist_bytes + red > SMEM_MAX / 2) gthreads = GENERIC_THREADS_BIG;
         nwarp = gthreads / 32;
         red = (size_t)nwarp * (P.obs_total + 1) * 8;
       }
@@ -438,9 +426,7 @@ int plan(mci_handle_t *h) {
       if (h->jit_failed) return MCI_ERR_UNSUPPORTED;
       if (!h->kernel) return fail(h, MCI_ERR_UNSUPPORTED, "integrand id %d has no vegas kernel", P.fid);
       h->threads = gthreads; h->hist_mode = mode;
-      if (mode != HIST_SMEM_FIXED) staged_bytes = h->maps_in_smem ? map_bytes : 0;
-      h->maps_staged = (int)(staged_bytes / 8);
-      h->smem = staged_bytes + (mode == HIST_SMEM_FIXED ? hist_bytes : hist_smem(mode, nwarp)) + red;
+      h->smem = (h->maps_in_smem ? map_bytes : 0) + (mode == HIST_SMEM_FIXED ? hist_bytes : hist_smem(mode, nwarp)) + red;
     }
   } else {
     /* chain solvers: walker state in shared memory rows [row][thread]; pick the CTA size that keeps most walkers
@@ -992,7 +978,6 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
     if (const char *e = getenv("MCIB200_FIXED_EXP_BIAS")) FA.fixed_bias = atoi(e); /* test hook: shrink the headroom */ FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
     FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
     FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
-    FA.maps_staged = h->maps_staged;
     args[0] = &h->dp; args[1] = &FA;
   } else {
     CA.gmaps = h->d_gmaps; CA.reweight = h->d_reweight; CA.cta_stats = h->d_cta_stats; CA.cta_hist = h->d_cta_hist;

@@ -59,8 +59,6 @@ struct FillArgs {
   int tiles_per_block, spt;
   int hist_mode, n_hist_copies;
   int maps_in_smem;
-  int maps_staged;       /* generic kernel: doubles of the staged map image kept in shared memory — all of it, or the
-                            leading leaves that fit beside the histogram cells (the rest is read from global memory) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -472,9 +470,9 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
 /* sampler.jl:431-440).  tprob[] = probability of each (variable, slot), only when need_pad.     */
 /* ------------------------------------------------------------------------------------------ */
 template <int FID>
-__device__ __forceinline__ void vegas_sample_generic(const Problem &P, const double *smaps, int staged, const double *gmaps,
-                                                     const PhiloxKey &K, uint64_t s, uint32_t block, double *x, int *bin,
-                                                     double *tprob, double &jac, double *w, double *pad) {
+__device__ __forceinline__ void vegas_sample_generic(const Problem &P, const double *maps, const PhiloxKey &K,
+                                                     uint64_t s, uint32_t block, double *x, int *bin, double *tprob,
+                                                     double &jac, double *w, double *pad) {
   using F = Integrand<FID>;
   jac = 1.0;
   int k = 0;
@@ -487,8 +485,6 @@ __device__ __forceinline__ void vegas_sample_generic(const Problem &P, const dou
       MCI_UNROLL_LAYOUT
       for (int l = 0; l < P.top_nleaf[v]; ++l, ++k) {
         const DevLeaf &L = P.leaf[P.top_first[v] + l];
-        /* this leaf's tables: in shared memory if the staged prefix of the image covers them */
-        const double *maps = (L.smem_off + 2 * L.nbins + (L.kind == MCI_LEAF_CONTINUOUS ? 0 : 1) <= staged) ? smaps : gmaps;
         double u;
         if ((k & 1) == 0) {
           philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(k >> 1), block, K, o0, o1, o2, o3);
@@ -541,7 +537,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   constexpr int NWARP = THREADS / 32;
   extern __shared__ __align__(16) double smem[];
   double *smaps = smem;
-  const int map_smem = A.maps_staged;
+  const int map_smem = A.maps_in_smem ? P.map_doubles : 0;
   double *shist = smem + map_smem;
   /* HIST_SMEM_FIXED: one CTA-shared histogram of 64-bit fixed-point cells (native integer adds, mci_device.cuh) while the
    * device-side scale is valid; the same shared array as fp64 cells with compare-and-swap adds while it is not */
@@ -562,14 +558,11 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   double *sred = shist + (hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (one_smem_copy ? P.hist_len : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  { /* stage the leading map_smem doubles of the map image (16-byte loads) */
-    const double2 *src = reinterpret_cast<const double2 *>(A.gmaps);
-    double2 *dst = reinterpret_cast<double2 *>(smaps);
-    for (int i = tid; i < (map_smem >> 1); i += THREADS) dst[i] = __ldg(src + i);
-  }
+  if (A.maps_in_smem) stage_maps(P, smaps, A.gmaps);
   const int nsh = hmode == HIST_WARP_PRIVATE ? NWARP * P.hist_len : (one_smem_copy ? P.hist_len : 0);
   for (int i = tid; i < nsh; i += THREADS) shist[i] = 0.0;
   __syncthreads();
+  const double *maps = A.maps_in_smem ? smaps : A.gmaps;
   double *myhist = hmode == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
                    : one_smem_copy ? shist
                                                : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
@@ -594,7 +587,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
       if (!__any_sync(0xffffffffu, active)) break;
       double x[MAX_DRAW], tprob[MAX_DRAW], w[NI * WD], pad[NI], jac;
       int bin[MAX_DRAW];
-      vegas_sample_generic<FID>(P, smaps, map_smem, A.gmaps, K, s, block, x, bin, tprob, jac, w, pad);
+      vegas_sample_generic<FID>(P, maps, K, s, block, x, bin, tprob, jac, w, pad);
       bool finite = true;
 #pragma unroll
       for (int i = 0; i < NI * WD; ++i) finite = finite && isfinite(w[i]);
@@ -707,7 +700,7 @@ __global__ void vegas_trace_kernel(const __grid_constant__ DevProblem Pp, const 
   constexpr int WD = IntegrandWD<FID>::value;
   double x[MAX_DRAW], tprob[MAX_DRAW], w[Integrand<FID>::NI * WD], pad[Integrand<FID>::NI], jac;
   int bin[MAX_DRAW];
-  vegas_sample_generic<FID>(P, gmaps, 0, gmaps, K, first + t, block, x, bin, tprob, jac, w, pad);
+  vegas_sample_generic<FID>(P, gmaps, K, first + t, block, x, bin, tprob, jac, w, pad);
   for (int k = 0; k < P.n_draw; ++k) { xo[(size_t)t * P.n_draw + k] = x[k]; bo[(size_t)t * P.n_draw + k] = bin[k]; }
   jo[t] = jac;
   for (int i = 0; i < P.ni * WD; ++i) wo[(size_t)t * P.ni * WD + i] = w[i]; /* complex: (re, im) interleaved */
