@@ -417,8 +417,13 @@ int plan(mci_handle_t *h) {
         mode = HIST_SMEM_FIXED;
         const size_t red_big = (size_t)(GENERIC_THREADS_BIG / 32) * (P.obs_total + 1) * 8;
         h->maps_in_smem = map_bytes + hist_bytes + red_big <= SMEM_MAX ? 1 : 0;
-        /* more than half of an SM's shared memory per CTA means one CTA per SM: let it be a 1024-thread one */
-        if ((h->maps_in_smem ? map_bytes : 0) + hist_bytes + red > SMEM_MAX / 2) gthreads = GENERIC_THREADS_BIG;
+        /* cells (and maps) limit the CTAs per SM: size the CTA so that an SM still holds ~1024 threads — one CTA per SM ->
+         * 1024 threads, two -> 512, else 256 */
+        {
+          const size_t per_cta = (h->maps_in_smem ? map_bytes : 0) + hist_bytes + red;
+          if (per_cta > SMEM_MAX / 2) gthreads = GENERIC_THREADS_BIG;
+          else if (per_cta > SMEM_MAX / 3) gthreads = GENERIC_THREADS_MID;
+        }
         nwarp = gthreads / 32;
         red = (size_t)nwarp * (P.obs_total + 1) * 8;
       }

@@ -447,6 +447,19 @@ __device__ __forceinline__ void chain_flush_hist(const Problem &P, const ChainAr
 #endif
 /* uniforms the MCMC kernel generates ahead per step (RngAhead): update type, variable, slot(s), shift, accept */
 constexpr int MCMC_DRAWS_AHEAD = 6;
+/* ... per kernel: a step draws the update kind, the variable, one or two slots / one uniform per leaf of the shifted
+ * variable, and the acceptance — 5 uniforms when every variable is a single leaf, which RngAhead<5> serves with THREE
+ * Philox calls per step for either parity of the stream position (6 take four: ncu, round 2: the look-ahead is 19 % of the
+ * instructions of the C5 kernel).  Variables of several leaves (CompositeVar, FermiK) keep 6 */
+template <int FID>
+__device__ __host__ constexpr int mcmc_draws_ahead() {
+#ifdef MCI_JIT
+  return JitProblem::max_nleaf == 1 ? 5 : MCMC_DRAWS_AHEAD;
+#else
+  return (FID == MCI_F_GENZ_CORNER_COMP || FID == MCI_F_LATTICE_COMP || FID == MCI_F_DISCRETE2_CONST || FID == MCI_F_BUBBLE_FERMIK)
+             ? MCMC_DRAWS_AHEAD : 5;
+#endif
+}
 /* bin-by-Discrete observables of the chain kernels are kept in this many per-thread accumulators (mci_create checks) */
 constexpr int CHAIN_MAX_BINNED_OBS = 8;
 /* per-thread observable accumulators: one per integrand (default measure), CHAIN_MAX_BINNED_OBS for the single binned
@@ -768,7 +781,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
   constexpr bool FK = chain_has_fermik<FID>();
-  ChainCtxT<RngAhead<MCMC_DRAWS_AHEAD>, FK> C(P, S.maps, K);
+  ChainCtxT<RngAhead<mcmc_draws_ahead<FID>()>, FK> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
   if constexpr (FK) fermik_reset(P, W);
   ChainX X{W.data, &P, W.T};
@@ -915,19 +928,36 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
       if (curr == N) {
         normalization += __ddiv_rn(1.0, rw[N]);
       } else {
-        if (hmode != HIST_NONE)
+        /* accumulate!(var, pos, 1.0) for every slot of the current integrand (:148-155).  The policy test stays outside
+         * the slot loops and the shared counters are addressed through their 32-bit shared address: 4 instructions per
+         * slot (index, LDS.U16, address, ATOMS) — the generic-pointer form with the test inside cost 12, 14 % of the C5
+         * kernel (ncu source view, round 2) */
+        if (hmode == HIST_SMEM_ATOMIC) {
+          MCI_UNROLL_LAYOUT
+          for (int v = 0; v < P.nv; ++v) {
+            const int cd = P.dof[curr * P.nv + v];
+            MCI_UNROLL_LAYOUT
+            for (int k = 0; k < P.top_nleaf[v]; ++k) {
+              const DevLeaf &L = P.leaf[P.top_first[v] + k];
+              if (!L.adapt) continue;
+              const uint32_t cells = S.hist_saddr + 4u * (uint32_t)L.hist_off;
+              const gidx_t *g = W.gidx + frow(L, 1) * W.T;
+              const int step = L.stride * W.T;
+#pragma unroll 4
+              for (int pos = 0; pos < cd; ++pos)
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cells + 4u * (uint32_t)g[pos * step]), "r"(1u) : "memory");
+            }
+          }
+        } else if (hmode != HIST_NONE) {
           for (int v = 0; v < P.nv; ++v) {
             const int cd = P.dof[curr * P.nv + v];
             for (int pos = 1; pos <= cd; ++pos)
               for (int k = 0; k < P.top_nleaf[v]; ++k) {
                 const DevLeaf &L = P.leaf[P.top_first[v] + k];
-                if (L.adapt) {
-                  const int bin = W.gidx[frow(L, pos) * W.T];
-                  if (hmode == HIST_SMEM_ATOMIC) atomicAdd(reinterpret_cast<unsigned int *>(S.shist) + L.hist_off + bin, 1u); /* ATOMS.ADD */
-                  else atomicAdd(S.ghist + L.hist_off + bin, 1.0);
-                }
+                if (L.adapt) atomicAdd(S.ghist + L.hist_off + W.gidx[frow(L, pos) * W.T], 1.0);
               }
           }
+        }
         double relw[WD]; /* relativeWeight = state.weight / state.probability (:163), component by component */
 #pragma unroll
         for (int c = 0; c < WD; ++c) relw[c] = __ddiv_rn(weight[c], prob_cur);

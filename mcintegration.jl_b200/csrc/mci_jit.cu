@@ -103,6 +103,8 @@ std::string jit_problem_header(const DevProblem &P) {
   const int nvv = P.nv > 0 ? P.nv : 1;
   bool has_fermik = false;
   for (int l = 0; l < P.nleaf; ++l) has_fermik = has_fermik || P.leaf[l].kind == MCI_LEAF_FERMIK;
+  int max_nleaf = 1;
+  for (int v = 0; v < P.nv; ++v) max_nleaf = P.top_nleaf[v] > max_nleaf ? P.top_nleaf[v] : max_nleaf;
   itab(tabs, members, "top_nleaf", P.top_nleaf, nvv); itab(tabs, members, "top_first", P.top_first, nvv);
   itab(tabs, members, "top_base", P.top_base, nvv); itab(tabs, members, "maxdof", P.maxdof, nvv);
   itab(tabs, members, "top_tslot", P.top_tslot, nvv); itab(tabs, members, "top_skip", P.top_skip, nvv);
@@ -127,9 +129,9 @@ std::string jit_problem_header(const DevProblem &P) {
   snprintf(buf, sizeof buf,
            "  static constexpr int solver = %d, fid = %d, measure_kind = %d, ni = %d, nd = %d, nv = %d, nleaf = %d, n_draw = %d;\n"
            "  static constexpr int obs_total = %d, hist_len = %d, pa_dim = %d, measurefreq = %d, need_pad = %d, any_adapt = %d;\n"
-           "  static constexpr int map_doubles = %d, n_tslot = %d, wdim = %d, start_idx = %d;\n  static constexpr bool has_fermik = %s;\n",
+           "  static constexpr int map_doubles = %d, n_tslot = %d, wdim = %d, start_idx = %d, max_nleaf = %d;\n  static constexpr bool has_fermik = %s;\n",
            P.solver, P.fid, P.measure_kind, P.ni, P.nd, P.nv, P.nleaf, P.n_draw, P.obs_total, P.hist_len, P.pa_dim, P.measurefreq,
-           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot, P.wdim, P.start_idx, has_fermik ? "true" : "false");
+           P.need_pad, P.any_adapt, P.map_doubles, P.n_tslot, P.wdim, P.start_idx, max_nleaf, has_fermik ? "true" : "false");
   o += buf;
   o += members;
   o += "  struct T_leaf { __device__ __forceinline__ const DevLeaf &operator[](int i) const { return jit_tab::leaf[i]; } } leaf;\n";

@@ -14,7 +14,7 @@ const void *lookup_vegas_pool(int fid, int d, bool exact, int hist_mode, const c
 }
 
 const void *lookup_vegas_generic(int fid, const char **name, int threads) {
-  if (threads == GENERIC_THREADS_BIG) return lookup_vegas_generic_big(fid, name);
+  if (threads != GENERIC_THREADS) return lookup_vegas_generic_big(fid, name, threads);
   switch (fid) {
 #define M(FID) case FID: if (name) *name = "vegas_generic_kernel<" #FID ">"; return (const void *)vegas_generic_kernel<FID, GENERIC_THREADS>;
     MCI_FOR_EACH_FID(M)
