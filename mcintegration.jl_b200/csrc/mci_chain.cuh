@@ -274,6 +274,7 @@ __device__ __forceinline__ double top_prob(const Problem &P, const Walker<true> 
   const int nl = P.top_nleaf[v];
   if (nl == 1) return W.prob[frow(P.leaf[P.top_first[v]], pos) * W.T];
   double tp = 1.0;
+  MCI_UNROLL_LAYOUT
   for (int k = 0; k < nl; ++k) tp = __dmul_rn(tp, W.prob[frow(P.leaf[P.top_first[v] + k], pos) * W.T]);
   return tp;
 }
@@ -357,14 +358,20 @@ __device__ __forceinline__ void var_initialize(CTX &C, Walker<HP> &W, int v) {
 /* variable.jl:606-619 / :628-641 */
 __device__ __forceinline__ double probability(const Problem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
-  for (int v = 0; v < P.nv; ++v)
+  MCI_UNROLL_LAYOUT
+  for (int v = 0; v < P.nv; ++v) {
+    MCI_UNROLL_LAYOUT
     for (int pos = 1; pos <= P.dof[i * P.nv + v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
+  }
   return pr;
 }
 __device__ __forceinline__ double padding_probability(const Problem &P, const Walker<true> &W, int i) {
   double pr = 1.0;
-  for (int v = 0; v < P.nv; ++v)
+  MCI_UNROLL_LAYOUT
+  for (int v = 0; v < P.nv; ++v) {
+    MCI_UNROLL_LAYOUT
     for (int pos = P.dof[i * P.nv + v] + 1; pos <= P.maxdof[v]; ++pos) pr = __dmul_rn(pr, top_prob(P, W, v, pos));
+  }
   return pr;
 }
 
@@ -590,19 +597,24 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
         const double f2 = __ddiv_rn(__dmul_rn(aw, aw), probability(P, W, i));
         wf2[i] = __ddiv_rn(__dmul_rn(f2, pad[i]), prob_cur);
       }
-      for (int v = 0; v < P.nv; ++v)
+      MCI_UNROLL_LAYOUT
+      for (int v = 0; v < P.nv; ++v) {
+        MCI_UNROLL_LAYOUT
         for (int pos = 1; pos <= P.maxdof[v]; ++pos) {
           double t = 0.0;
           bool any = false;
 #pragma unroll
           for (int i = 0; i < N; ++i)
             if (pos <= P.dof[i * P.nv + v]) { t += wf2[i]; any = true; }
-          if (any)
+          if (any) {
+            MCI_UNROLL_LAYOUT
             for (int k = 0; k < P.top_nleaf[v]; ++k) {
               const DevLeaf &L = P.leaf[P.top_first[v] + k];
               if (L.adapt) chain_hist_add(hmode, S.hist_saddr + 8u * (uint32_t)L.hist_off, S.ghist + L.hist_off, W.gidx[frow(L, pos) * W.T], t);
             }
+          }
         }
+      }
     }
     __syncwarp();
     /* measurement: montecarlo.jl:213-232 */

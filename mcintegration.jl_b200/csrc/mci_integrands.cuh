@@ -76,11 +76,18 @@ __device__ __forceinline__ double ipow(double s, int n) {
 }
 
 /* example/bubble.jl:40-50 */
+/* The four cases (sign of tau, sign of w) of the reference differ only in the exponent of the numerator and in the
+ * overall sign; the denominator is 1 + exp(-|w| beta) in all of them.  Selecting the exponent first leaves two exp and
+ * one division per call whatever the mix of cases inside a warp — the same values, bit for bit, as the four-way branch:
+ *   tau >= 0, w > 0 :  exp(-w tau)          tau >= 0, w <= 0 :  exp(w (beta - tau))
+ *   tau <  0, w > 0 : -exp(-w (tau + beta)) tau <  0, w <= 0 : -exp(-w tau) */
 __device__ __forceinline__ double green(double tau, double w, double beta) {
-  if (tau >= 0.0)
-    return w > 0.0 ? exp(-w * tau) / (1 + exp(-w * beta)) : exp(w * (beta - tau)) / (1 + exp(w * beta));
-  else
-    return w > 0.0 ? -exp(-w * (tau + beta)) / (1 + exp(-w * beta)) : -exp(-w * tau) / (1 + exp(w * beta));
+  const bool tp = tau >= 0.0, wp = w > 0.0;
+  const double den = 1 + exp(-fabs(w) * beta);
+  const double t2 = tp ? beta - tau : tau + beta;
+  const double arg = tp == wp ? -w * tau : (tp ? w : -w) * t2;
+  const double g = exp(arg) / den;
+  return tp ? g : -g;
 }
 
 template <int FID>
