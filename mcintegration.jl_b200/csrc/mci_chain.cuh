@@ -850,8 +850,10 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
           prop = __ddiv_rn((double)nnb, (double)(P.nb_ptr[nw + 1] - P.nb_ptr[nw]));
           ci = true; tgt = nw;
           if (A.coop_ci) { /* many slots to create!/remove!: the whole warp does it below */
+            MCI_UNROLL_LAYOUT
             for (int v = 0; v < P.nv; ++v) ci_dof = ci_dof || (P.dof[curr * P.nv + v] != P.dof[nw * P.nv + v]);
           } else {
+            MCI_UNROLL_LAYOUT
             for (int v = 0; v < P.nv; ++v) {
               const int cd = P.dof[curr * P.nv + v], nd_ = P.dof[nw * P.nv + v];
               if (cd < nd_) { for (int pos = cd + 1; pos <= nd_; ++pos) prop = __dmul_rn(prop, var_create(C, W, v, pos)); }

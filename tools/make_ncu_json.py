@@ -56,7 +56,7 @@ rd, wr = in_unit(r, "dram__bytes_read.sum", "byte") or 0.0, in_unit(r, "dram__by
 wave = num(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
 cyc = num(r, "sm__cycles_elapsed.max")
 grid = num(r, "launch__grid_size")
-commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+commit = os.environ.get("MCI_GIT_COMMIT") or subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
                         cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip()
 doc = {
     "kernel": r[col["Kernel Name"]], "units_per_launch": units,
