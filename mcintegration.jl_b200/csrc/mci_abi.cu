@@ -980,12 +980,15 @@ static int enqueue_iteration(mci_handle_t *h, uint64_t iter, bool with_d2h) {
     FA.gmaps = h->d_gmaps; FA.tile_obs = h->d_tile_obs; FA.tile_cnt = h->d_tile_cnt; FA.cta_hist = h->d_cta_hist;
     FA.flags = h->d_flags; FA.fixed_exp = h->hist_mode == HIST_SMEM_FIXED ? h->d_fixed_exp : nullptr; FA.iter = iter;
     FA.fixed_bias = 0; FA.rescue = 0;
-    if (const char *e = getenv("MCIB200_FIXED_EXP_BIAS")) FA.fixed_bias = atoi(e); /* test hook: shrink the headroom */ FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
+    if (const char *e = getenv("MCIB200_FIXED_EXP_BIAS")) FA.fixed_bias = atoi(e); /* test hook: shrink the headroom */
+    FA.neval_per_block = p.neval_per_block; FA.n_local_blocks = n_local;
+    philox_expand_key(h->dp.seed, iter, FA.key);
     FA.rank = h->rank; FA.world = h->world; FA.tiles_per_block = h->tiles_per_block; FA.spt = h->spt;
     FA.hist_mode = h->hist_mode; FA.n_hist_copies = h->n_hist_copies; FA.maps_in_smem = h->maps_in_smem;
     args[0] = &h->dp; args[1] = &FA;
   } else {
     CA.gmaps = h->d_gmaps; CA.reweight = h->d_reweight; CA.cta_stats = h->d_cta_stats; CA.cta_hist = h->d_cta_hist;
+    philox_expand_key(h->dp.seed, iter, CA.key);
     CA.flags = h->d_flags; CA.iter = iter; CA.steps = h->steps; CA.walkers_per_block = std::max(1, h->walkers);
     CA.ctas_per_block = h->ctas_per_block; CA.n_local_blocks = n_local; CA.rank = h->rank; CA.world = h->world;
     CA.hist_mode = h->hist_mode; CA.n_hist_copies = h->n_hist_copies; CA.maps_in_smem = h->maps_in_smem;

@@ -47,6 +47,7 @@ struct ChainArgs {
                              variable has several: the rollback rows of shift!)                    */
   long long burnin;       /* extra unmeasured steps before the reference's loop (mci_problem_t.chain_burnin) */
   int coop_ci;            /* mcmc: changeIntegrand creates/removes enough slots for the warp-cooperative path */
+  PhiloxKey key;          /* the ten round keys of (seed, iter), expanded on the host: operands from the constant bank */
 };
 
 /* a walker's columns of the shared state; T = row stride (threads per CTA) */
@@ -515,8 +516,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) vegasmc_kernel(const __grid
   constexpr int N = NI;
   const int hmode = A.hist_mode;
 
-  PhiloxKey K;
-  philox_expand_key(P.seed, A.iter, K);
+  MCI_ROUND_KEYS(K, P, A);
   ChainCtxT<Rng> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);
   ChainX X{W.data, &P, W.T};
@@ -790,8 +790,7 @@ __global__ void __launch_bounds__(MCI_CHAIN_MAXT, 1) mcmc_kernel(const __grid_co
   const double TINY = 4.9406564584124654e-324 * 1e50;
   const double EPS0 = 4.9406564584124654e-324;
 
-  PhiloxKey K;
-  philox_expand_key(P.seed, A.iter, K);
+  MCI_ROUND_KEYS(K, P, A);
   constexpr bool FK = chain_has_fermik<FID>();
   ChainCtxT<RngAhead<mcmc_draws_ahead<FID>()>, FK> C(P, S.maps, K);
   C.rng.init((uint64_t)walker, block);

@@ -160,6 +160,19 @@ __host__ __device__ inline void philox_expand_key(uint64_t seed, uint64_t iter, 
   }
 }
 
+/* The round keys depend on (seed, iter) only.  Expanded in the kernel they are either kept in 20 registers or — what
+ * ptxas does at the 64-register cap of the 1024-thread kernels — recomputed with 18 additions in front of every Philox
+ * call (4-6 % of the instructions of the chain and generic kernels, ncu source view).  The host expands them into the
+ * launch arguments instead: every round then reads its two keys straight from the constant bank. */
+#ifndef MCI_KEY_IN_ARGS
+#define MCI_KEY_IN_ARGS 1
+#endif
+#if MCI_KEY_IN_ARGS
+#define MCI_ROUND_KEYS(K, P, A) const PhiloxKey &K = (A).key
+#else
+#define MCI_ROUND_KEYS(K, P, A) PhiloxKey K; philox_expand_key((P).seed, (A).iter, K)
+#endif
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &K,
                                                uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
 #pragma unroll

@@ -59,6 +59,7 @@ struct FillArgs {
   int tiles_per_block, spt;
   int hist_mode, n_hist_copies;
   int maps_in_smem;
+  PhiloxKey key;         /* the ten round keys of (seed, iter), expanded on the host: operands from the constant bank */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -566,8 +567,7 @@ __global__ void __launch_bounds__(THREADS) vegas_generic_kernel(const __grid_con
   double *myhist = hmode == HIST_WARP_PRIVATE ? shist + warp * P.hist_len
                    : one_smem_copy ? shist
                                                : A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
-  PhiloxKey K;
-  philox_expand_key(P.seed, A.iter, K);
+  MCI_ROUND_KEYS(K, P, A);
   unsigned long long bad = 0;
   const int OT = P.obs_total;
 
