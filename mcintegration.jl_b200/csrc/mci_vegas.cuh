@@ -22,6 +22,9 @@
 #include "mci_integrands.cuh"
 
 /* updates of one sample issued together (loads / adds back to back, then the dependent halves) */
+#ifndef MCI_POOL_KEY_IN_ARGS
+#define MCI_POOL_KEY_IN_ARGS 1
+#endif
 #ifndef MCI_HIST_BATCH
 #define MCI_HIST_BATCH 5
 #endif
@@ -380,8 +383,12 @@ __global__ void __launch_bounds__(THREADS, PoolMinBlocks<MAXD, THREADS>::value) 
   }
   double *ghist = A.cta_hist + (size_t)(blockIdx.x % A.n_hist_copies) * P.hist_len;
 
+#if MCI_POOL_KEY_IN_ARGS
+  MCI_ROUND_KEYS(K, P, A);
+#else
   PhiloxKey K;
   philox_expand_key(P.seed, A.iter, K);
+#endif
   unsigned long long bad = 0;
   PoolJac<MAXD, EXACT> J;
   J.init(EXACT ? MAXD : P.maxdof[0]);

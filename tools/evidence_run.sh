@@ -7,6 +7,9 @@
 set -u
 mkdir -p gpurun_out/profiles
 O=gpurun_out
+# (0) the GPU test suite on the same build
+python -X faulthandler -m pytest tests -m gpu -q --tb=short -rf > $O/r2_pytest_gpu.log 2>&1
+tail -3 $O/r2_pytest_gpu.log | cut -c1-200
 # (1) ncu --set full of the four fill kernels.  sweep_fill launches (fixed, twin) pairs per iteration; iterations >= 3
 #     run the fixed-point kernel on C2, so skip the first launches
 ncu --set full --clock-control none --import-source on -k regex:vegas_pool_kernel -s 6 -c 4 -f -o $O/r2_prof_fill python tools/sweep_fill.py gauss10 vegas 26 8192 0 6 > $O/r2_prof_fill.log 2>&1
