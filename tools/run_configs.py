@@ -39,6 +39,8 @@ def run(tag, f, exact, *, solver, neval, niter, measure=None, walkers=None, **cf
 
 para = I.BubblePara()
 b = case("bubble")
+# CUDA context, library load and the first launch are paid once per process, not per integral: keep them out of C2's time
+mci.integrate(I.gauss_nd, solver="vegas", neval=1e4, niter=2, seed=1, var=mci.Continuous(-5.0, 5.0), dof=[[10]])
 run("C2 10-D Gaussian, Continuous(-5,5), dof=[[10]]", I.gauss_nd, [[math.erf(5 / math.sqrt(2)) ** 10]], solver="vegas",
     neval=2 ** 30, niter=10, var=mci.Continuous(-5.0, 5.0), dof=[[10]])
 run("C3-A 16-D Genz corner peak, pool", I.genz_corner_peak(16, "pool"), [[4.17984992413838e-05]], solver="vegas",

@@ -24,11 +24,17 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-if rank == 0:
-    idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
-dist.broadcast(idt, 0)
-comm = (rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+
+def fresh_comm():
+    """(rank, world, NCCL unique id) for one integrate() call: an id serves one communicator"""
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    return (rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+
 block = 16 * world
 if which == "c5":
     kw = dict(solver="mcmc", neval=1e9, niter=10, block=block, var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4)
@@ -38,6 +44,10 @@ else:
     para = b["para"]
     kw = dict(solver="vegasmc", neval=1e8, niter=10, block=block, measure="bin_by_discrete", **b["cfg"]())
     f, exact, tag = b["f"], [[I.lindhard_finite_temperature(para, q) for q in para.extQ]], "C4 example/bubble.jl, vegasmc, neval=1e8/iter"
+# the first call of a process pays for the CUDA context, the NVRTC build of the problem's kernel and NCCL's topology
+# discovery: run the same problem once at a small size, then time the real one (which still creates its communicator)
+mci.integrate(f, seed=1, device=local, comm=fresh_comm(), **dict(kw, neval=block * 65536, niter=2))
+comm = fresh_comm()
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
 res = mci.integrate(f, seed=1234, device=local, comm=comm, **kw)
