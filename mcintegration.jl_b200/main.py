@@ -3,6 +3,8 @@ block loop + statistics reduction of one iteration replaced by ONE call into the
 (mci_run_iteration) and train!/doReweight! replaced by mci_refine / mci_reweight on the device."""
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import _abi
@@ -167,14 +169,21 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
                                neval_per_block=nevalperblock, measurefreq=measurefreq, walkers_per_block=W,
                                thermal_ratio=thermal_ratio, device=device, hist_policy=hist_policy, jit=jit, chain_burnin=default_chain_burnin(W if W else DEFAULT_WALKERS, chain_burnin),
                                measure_source=measure_source, seed=config.next_seed(), mcmc_start_idx=int(idx))
+    t0 = time.perf_counter()
     engine = CudaEngine(spec)
     try:
         engine.set_maps(*maps_from_config(config))  # warm restart: config=result.config (main.jl:95-97)
+        t1 = time.perf_counter()
         if comm:
             engine.comm_init(comm[2], comm[0], comm[1])
+        t2 = time.perf_counter()
         if fused is None:
             fused = comm is None
-        return drive(engine, config, solver=solver, niter=niter, block=block, gamma=gamma, adapt=adapt,
-                     reweight_goal=reweight_goal, ignore=ignore, print_level=print_level, debug=bool(debug), fused=fused)
+        res = drive(engine, config, solver=solver, niter=niter, block=block, gamma=gamma, adapt=adapt,
+                    reweight_goal=reweight_goal, ignore=ignore, print_level=print_level, debug=bool(debug), fused=fused)
+        # where the wall time of this call went: building the handle (incl. an NVRTC build on the first use of a problem),
+        # creating the NCCL communicator, and the niter iterations themselves (fill + all-reduce + train!)
+        res.timing = dict(create_s=t1 - t0, comm_init_s=t2 - t1, iterations_s=time.perf_counter() - t2)
+        return res
     finally:
         engine.close()

@@ -51,6 +51,7 @@ class Result:
     ignore: int
     config: object
     iterations: list = field(default_factory=list)  # [(mean[], std[], snapshot), ...]
+    timing: dict = field(default_factory=dict)  # integrate(): seconds spent in create / comm_init / iterations (not in the reference)
 
     @classmethod
     def from_history(cls, history, ignore, config, neval):

@@ -33,7 +33,7 @@ def run(tag, f, exact, *, solver, neval, niter, measure=None, walkers=None, **cf
         dev = [[(m - e) / s if s > 0 else 0.0 for m, s, e in zip(mm, ss, np.ravel(ee))] for mm, ss, ee in zip(mean, std, exact)]
     out = dict(config=tag, solver=solver, neval_per_iter=neval * scale, niter=niter, mean=mean, sigma=std,
                chi2=[np.ravel(c).tolist() for c in res.chi2], exact=[np.ravel(e).tolist() for e in exact] if exact else None,
-               dev_sigma=dev, wall_s=dt, samples_per_s=neval * scale * niter / dt)
+               dev_sigma=dev, wall_s=dt, timing=res.timing, samples_per_s=neval * scale * niter / dt)
     print(json.dumps(out), flush=True)
 
 
