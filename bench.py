@@ -219,6 +219,27 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / scale) if a.size else 0.0
 
 
+_JOB_NCCL_ID = None
+
+
+def job_nccl_id():
+    """The 128-byte NCCL unique id of this job: rank 0 creates it, torch.distributed carries the bytes.  The library owns
+    the communicator and keeps it for the life of the process, so every engine of the job joins the same one."""
+    global _JOB_NCCL_ID
+    if _JOB_NCCL_ID is None:
+        import torch
+        import torch.distributed as dist
+
+        import mcintegration_jl_b200 as mci
+
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if dist.get_rank() == 0:
+            idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        _JOB_NCCL_ID = bytes(idt.cpu().numpy().tobytes())
+    return _JOB_NCCL_ID
+
+
 def parity_check(wl: Workload, rank, world, local, dist):
     """A small fixed problem of this workload, (a) partitioned over the ranks (in-library NCCL all-reduce; at N = 1 two
     handles with blocks b mod 2, summed on the host) and (b) unpartitioned: statistics of two iterations with a refine in
@@ -261,11 +282,7 @@ def parity_check(wl: Workload, rank, world, local, dist):
 
     if world > 1:
         eng = mci.CudaEngine(spec)
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        eng.comm_init(job_nccl_id(), rank, world)
         got, maps = run([eng], False)
         eng.close()
         # maps identical across ranks: compare every rank's grid bytes with rank 0's
@@ -333,12 +350,7 @@ def bench_workload(wl: Workload, args, rank, world, local, dist, want_cpu):
     spec, cfg = wl.spec(world, device=local)
     eng = mci.CudaEngine(spec)
     if world > 1:
-        # the library owns its communicator: rank 0 creates the id, torch.distributed carries the 128 bytes
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        eng.comm_init(job_nccl_id(), rank, world)
     npb = wl.npb
     units_per_step = world * BLOCKS_PER_GPU * npb
 

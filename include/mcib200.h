@@ -311,7 +311,13 @@ int mci_reweight(mci_handle_t *h, double gamma, const double *goal);
  * (main.jl:122,152-166).
  */
 int mci_comm_unique_id(void *id128);
+/* Communicators are kept per process, keyed by the unique id: a later handle that passes an id this process has
+ * already used (same rank, world, device) JOINS that communicator instead of creating one, so the successive
+ * integrate() calls of a job pay for NCCL's start-up once.  Handles that share a communicator must not run
+ * iterations concurrently.  mci_destroy leaves the communicator alone; mci_comm_finalize destroys them all. */
 int mci_comm_init(mci_handle_t *h, const void *id128, int32_t rank, int32_t world);
+/* collective: every rank calls it after destroying its last handle (optional — process exit also ends them) */
+int mci_comm_finalize(void);
 /* partition blocks without a communicator (the caller reduces, e.g. torch.distributed) */
 int mci_set_partition(mci_handle_t *h, int32_t rank, int32_t world);
 /* device pointer + length (doubles) of the packed statistics buffer, for external collectives */

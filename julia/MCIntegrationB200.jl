@@ -188,12 +188,19 @@ end
 
 _mpi() = Base.require(Base.PkgId(Base.UUID("da04e1cc-30fd-572f-bb4f-1f8673147195"), "MPI"))
 
+# one NCCL unique id per MPI communicator and process: the library keeps the communicator of an id alive, so every
+# integrate_b200 call after the first joins it instead of paying NCCL's start-up again
+const NCCL_IDS = Dict{Any,Vector{UInt8}}()
+
 "Attach an NCCL communicator: rank 0 creates the id, MPI carries the 128 bytes (replaces src/utility/parallel.jl)."
 function comm_init!(handle, comm)
     MPI = _mpi()
-    id = zeros(UInt8, 128)
-    MPI.Comm_rank(comm) == 0 && ccall((:mci_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
-    MPI.Bcast!(id, 0, comm)
+    id = get!(NCCL_IDS, comm) do
+        fresh = zeros(UInt8, 128)
+        MPI.Comm_rank(comm) == 0 && ccall((:mci_comm_unique_id, LIB), Cint, (Ptr{UInt8},), fresh)
+        MPI.Bcast!(fresh, 0, comm)
+        fresh
+    end
     check(handle, ccall((:mci_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), handle, id, MPI.Comm_rank(comm), MPI.Comm_size(comm)))
 end
 

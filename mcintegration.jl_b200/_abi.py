@@ -129,6 +129,7 @@ EXPORTS = [
     "mci_reweight",
     "mci_comm_unique_id",
     "mci_comm_init",
+    "mci_comm_finalize",
     "mci_set_partition",
     "mci_stats_device_ptr",
     "mci_trace_samples",
@@ -192,6 +193,7 @@ def declare(lib, prefix="mci_"):
         f("launch_iteration", C.c_int, [H, C.c_uint64])
         f("comm_unique_id", C.c_int, [C.c_void_p])
         f("comm_init", C.c_int, [H, C.c_void_p, C.c_int32, C.c_int32])
+        f("comm_finalize", C.c_int, [])
         f("stats_device_ptr", C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)])
         f("launch_count", C.c_int, [H, C.POINTER(C.c_uint64)])
         f("last_timing", C.c_int, [H, C.POINTER(C.c_float), C.POINTER(C.c_float)])

@@ -152,8 +152,15 @@ class CudaEngine(HandleEngine):
         self._check(self.lib.mci_launch_iteration(self.h, int(it)))
 
     def comm_init(self, id_bytes: bytes, rank: int, world: int):
+        """attach the NCCL communicator named by the 128-byte id; an id this process has used before is JOINED, not
+        re-created, so successive engines (successive integrate(comm=...) calls) share one warm communicator"""
         buf = C.create_string_buffer(id_bytes, 128)
         self._check(self.lib.mci_comm_init(self.h, buf, int(rank), int(world)))
+
+    @staticmethod
+    def comm_finalize():
+        """destroy every NCCL communicator of this process (collective; after the last engine is closed)"""
+        _abi.load_library().mci_comm_finalize()
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -207,3 +207,9 @@ def test_missing_library_fails_loudly():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 3, r.stdout + r.stderr
     assert "LibraryMissing" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_comm_finalize_without_communicators():
+    """mci_comm_finalize is safe to call with nothing to end (no GPU, NCCL never loaded)"""
+    lib = _abi.load_library()
+    assert lib.mci_comm_finalize() == 0

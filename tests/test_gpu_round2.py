@@ -488,3 +488,33 @@ def test_fixed_point_scale_is_forgotten_when_maps_are_replaced():
         np.testing.assert_allclose(a.block_obs, b.block_obs, rtol=1e-11, atol=1e-300)
     finally:
         gpu.close(); cpu.close()
+
+
+def test_handles_share_the_communicator_of_an_id():
+    """mci_comm_init with an id this process has used before joins that communicator (one-rank world here): both handles
+    all-reduce through it and give what a handle without a communicator gives; the same id under another rank is refused;
+    mci_comm_finalize ends the communicators and a fresh id starts a new one."""
+    spec, _ = make_spec("gauss10", "vegas", n_block=16, neval_per_block=4096)
+    uid = mci.CudaEngine.comm_unique_id()
+    plain, a, b = mci.CudaEngine(spec), mci.CudaEngine(spec), mci.CudaEngine(spec)
+    try:
+        a.comm_init(uid, 0, 1)
+        b.comm_init(uid, 0, 1)  # joins
+        ref = plain.run_iteration(0)
+        for e in (a, b):
+            got = e.run_iteration(0)
+            np.testing.assert_allclose(got.block_obs, ref.block_obs, rtol=1e-12)
+            np.testing.assert_allclose(got.hist, ref.hist, rtol=1e-10)
+        with pytest.raises(Exception, match="already names a communicator"):
+            plain.comm_init(uid, 1, 2)
+    finally:
+        for e in (plain, a, b):
+            e.close()
+    mci.CudaEngine.comm_finalize()
+    c = mci.CudaEngine(spec)
+    try:
+        c.comm_init(mci.CudaEngine.comm_unique_id(), 0, 1)  # (an NCCL id bootstraps one communicator only)
+        np.testing.assert_allclose(c.run_iteration(0).block_obs, ref.block_obs, rtol=1e-12)
+    finally:
+        c.close()
+        mci.CudaEngine.comm_finalize()

@@ -27,7 +27,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 
 
 def fresh_comm():
-    """(rank, world, NCCL unique id) for one integrate() call: an id serves one communicator"""
+    """(rank, world, NCCL unique id): the library keeps one communicator per id for the life of the process"""
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
@@ -36,18 +36,24 @@ def fresh_comm():
 
 
 block = 16 * world
-if which == "c5":
-    kw = dict(solver="mcmc", neval=1e9, niter=10, block=block, var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4)
-    f, exact, tag = I.product4(), [[1.0]] * 4, "C5 20-D 4-component product, mcmc, neval=1e9/iter"
-else:
+def problem():
+    """fresh variables for every call: like the reference's, a Configuration resizes the pool of the variable it is
+    given (configuration.jl:156-160) and refuses to do that twice"""
+    if which == "c5":
+        kw = dict(solver="mcmc", neval=1e9, niter=10, block=block, var=mci.Continuous(0.0, 1.0), dof=[[20]] * 4)
+        return kw, I.product4(), [[1.0]] * 4, "C5 20-D 4-component product, mcmc, neval=1e9/iter"
     b = case("bubble")
     para = b["para"]
     kw = dict(solver="vegasmc", neval=1e8, niter=10, block=block, measure="bin_by_discrete", **b["cfg"]())
-    f, exact, tag = b["f"], [[I.lindhard_finite_temperature(para, q) for q in para.extQ]], "C4 example/bubble.jl, vegasmc, neval=1e8/iter"
+    return kw, b["f"], [[I.lindhard_finite_temperature(para, q) for q in para.extQ]], "C4 example/bubble.jl, vegasmc, neval=1e8/iter"
+
+
 # the first call of a process pays for the CUDA context, the NVRTC build of the problem's kernel and NCCL's topology
-# discovery: run the same problem once at a small size, then time the real one (which still creates its communicator)
-mci.integrate(f, seed=1, device=local, comm=fresh_comm(), **dict(kw, neval=block * 65536, niter=2))
+# discovery: run the same problem once at a small size, then time the real one (which joins the same communicator)
+kw, f, exact, tag = problem()
 comm = fresh_comm()
+mci.integrate(f, seed=1, device=local, comm=comm, **dict(kw, neval=block * 65536, niter=2))
+kw, f, exact, tag = problem()
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
 res = mci.integrate(f, seed=1234, device=local, comm=comm, **kw)
@@ -59,7 +65,7 @@ if rank == 0:
     dev = [[(m - e) / s for m, s, e in zip(mm, ss, ee)] for mm, ss, ee in zip(mean, std, exact)]
     print(json.dumps(dict(config=tag, n_gpus=world, block=block, mean=mean, sigma=std, dev_sigma=dev, wall_s=dt,
                           timing=res.timing, steps_per_s=kw["neval"] * kw["niter"] / res.timing["iterations_s"],
-                          note="steps_per_s over the iterations only; wall_s also holds the handle and the NCCL communicator of this call")),
+                          note="steps_per_s over the iterations only; wall_s also holds the creation of the handle")),
           flush=True)
 dist.barrier()
 dist.destroy_process_group()
