@@ -135,7 +135,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
     `comm` = (rank, world, unique_id_bytes) attaches an NCCL communicator (one process per GPU);
     `idx` = the integrand every :mcmc chain starts in (the kwarg of MCMC.montecarlo, mcmc/montecarlo.jl:76);
     `debug=True` warns, like the reference's loops, when the kernels met non-finite integrand values;
-    `fused` = run all iterations device-side in one library call (default: on one GPU when debug is off).
+    `fused` = run all iterations device-side in one library call (the default when debug is off).
     Everything else keeps the reference's meaning; `neval` is per iteration.  Like the reference (main.jl:136) every
     call draws the seed of its sample streams from config.rng, so repeated calls on one Configuration — a warm restart
     with config=result.config — use fresh, independent samples.
@@ -178,7 +178,7 @@ def integrate(integrand, *, solver="vegasmc", config=None, neval=1e4, niter=10, 
             engine.comm_init(comm[2], comm[0], comm[1])
         t2 = time.perf_counter()
         if fused is None:
-            fused = comm is None
+            fused = True  # also with a communicator: its all-reduce is stream-ordered like the kernels around it
         res = drive(engine, config, solver=solver, niter=niter, block=block, gamma=gamma, adapt=adapt,
                     reweight_goal=reweight_goal, ignore=ignore, print_level=print_level, debug=bool(debug), fused=fused)
         # where the wall time of this call went: building the handle (incl. an NVRTC build on the first use of a problem),

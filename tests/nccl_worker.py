@@ -31,13 +31,24 @@ def main():
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(mci.CudaEngine.comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    uid = bytes(idt.cpu().numpy().tobytes())
+    eng.comm_init(uid, rank, world)
     res = drive(eng, cfg, solver=solver, niter=4, block=spec.n_block)
     maps = eng.get_maps()
+    eng.close()
+    # a second handle joins the communicator of the same id and runs the same job as ONE fused library call
+    # (mci_run_iterations: the all-reduce is stream-ordered like everything else, no host round trip per iteration)
+    spec2, cfg2 = make_spec(name, solver, **kw)
+    spec2.device = local
+    eng2 = mci.CudaEngine(spec2)
+    eng2.comm_init(uid, rank, world)
+    res2 = drive(eng2, cfg2, solver=solver, niter=4, block=spec2.n_block, fused=True)
+    maps2 = eng2.get_maps()
+    eng2.close()
     with open(f"{out}.{rank}", "wb") as f:
         pickle.dump(dict(mean=[np.asarray(m) for m in res.mean], std=[np.asarray(s) for s in res.stdev], maps=maps,
-                         neval=res.neval), f)
-    eng.close()
+                         neval=res.neval, fused_mean=[np.asarray(m) for m in res2.mean],
+                         fused_std=[np.asarray(s) for s in res2.stdev], fused_maps=maps2, fused_neval=res2.neval), f)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -39,6 +39,17 @@ def test_nccl_ranks_match_single_gpu(tmp_path, name, solver):
             assert np.array_equal(a, b)
         for a, b in zip(ranks[0]["mean"], ranks[k]["mean"]):
             assert np.array_equal(a, b)
+    # the fused multi-iteration call over the shared communicator = the iteration-by-iteration driver
+    for k in range(world):
+        for a, b in zip(ranks[k]["maps"], ranks[k]["fused_maps"]):
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-12)
+        for a, b in zip(ranks[k]["mean"], ranks[k]["fused_mean"]):
+            np.testing.assert_allclose(a, b, rtol=1e-8)
+        for a, b in zip(ranks[k]["std"], ranks[k]["fused_std"]):
+            np.testing.assert_allclose(a, b, rtol=1e-5)
+        assert ranks[k]["neval"] == ranks[k]["fused_neval"]
+        for a, b in zip(ranks[0]["fused_maps"], ranks[k]["fused_maps"]):
+            assert np.array_equal(a, b)
     kw = dict(n_block=8, neval_per_block=20000) if solver == "vegas" else dict(n_block=8, neval_per_block=64 * 300, walkers=64)
     spec, cfg = make_spec(name, solver, **kw)
     eng = mci.CudaEngine(spec)
