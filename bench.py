@@ -499,6 +499,9 @@ def run_ours(args):
         sub = bench_workload(other, sub_args, rank, world, local, dist, want_cpu=(world == 1 and not args.no_cpu))
     if dist is not None:
         dist.barrier()
+        import mcintegration_jl_b200 as mci
+
+        mci.CudaEngine.comm_finalize()  # the job's NCCL communicator (every engine joined it: job_nccl_id)
         dist.destroy_process_group()
     sys.stdout.flush()
     os.dup2(stdout_fd, 1)

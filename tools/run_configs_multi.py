@@ -68,4 +68,5 @@ if rank == 0:
                           note="steps_per_s over the iterations only; wall_s also holds the creation of the handle")),
           flush=True)
 dist.barrier()
+mci.CudaEngine.comm_finalize()
 dist.destroy_process_group()
