@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -94,6 +95,62 @@ struct Compiled {
 /* program text + name expressions -> cubin: the same problem created again (every rank of a job, every test) compiles once */
 std::map<std::string, Compiled> g_cache;
 
+}  // namespace
+
+namespace {
+/* Opt-in disk cache (MCIB200_JIT_CACHE=<directory>): the first use of a problem in a process costs an NVRTC build
+ * (0.6 s for the BASELINE C5 kernel, measured); with the cache a later process loads the cubin instead.  A file is named by
+ * the FNV-1a hash of everything the cubin depends on — the embedded device headers of this library build, the generated
+ * problem header, the program text, the kernel names — and holds the lowered names and the cubin. */
+uint64_t fnv1a(uint64_t h, const char *p, size_t n) {
+  for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+  return h;
+}
+std::string disk_cache_path(const std::string &key) {
+  const char *dir = getenv("MCIB200_JIT_CACHE");
+  if (!dir || !*dir) return "";
+  uint64_t h = 1469598103934665603ull;
+  for (int i = 0; i < MCI_JIT_NUM_HEADERS; ++i) h = fnv1a(h, MCI_JIT_HEADER_SOURCES[i], strlen(MCI_JIT_HEADER_SOURCES[i]));
+  h = fnv1a(h, key.data(), key.size());
+  char name[64];
+  snprintf(name, sizeof name, "/mcib200_sm100a_%016llx.cubin", (unsigned long long)h);
+  return std::string(dir) + name;
+}
+bool disk_cache_load(const std::string &path, size_t n_names, Compiled &C) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  bool ok = false;
+  uint64_t magic = 0, nn = 0, nc = 0;
+  if (fread(&magic, 8, 1, f) == 1 && magic == 0x4d43494a49543031ull && fread(&nn, 8, 1, f) == 1 && nn == n_names) {
+    ok = true;
+    for (uint64_t i = 0; ok && i < nn; ++i) {
+      uint64_t len = 0;
+      ok = fread(&len, 8, 1, f) == 1 && len < (1u << 16);
+      std::string low(ok ? len : 0, '\0');
+      ok = ok && (len == 0 || fread(&low[0], 1, len, f) == len);
+      C.lowered.push_back(low);
+    }
+    ok = ok && fread(&nc, 8, 1, f) == 1 && nc > 0 && nc < (1ull << 30);
+    if (ok) { C.cubin.resize(nc); ok = fread(C.cubin.data(), 1, nc, f) == nc; }
+  }
+  fclose(f);
+  if (!ok) { C.lowered.clear(); C.cubin.clear(); }
+  return ok;
+}
+void disk_cache_store(const std::string &path, const Compiled &C) {
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return; /* a cache that cannot be written is not an error */
+  const uint64_t magic = 0x4d43494a49543031ull, nn = C.lowered.size(), nc = C.cubin.size();
+  bool ok = fwrite(&magic, 8, 1, f) == 1 && fwrite(&nn, 8, 1, f) == 1;
+  for (const auto &low : C.lowered) {
+    const uint64_t len = low.size();
+    ok = ok && fwrite(&len, 8, 1, f) == 1 && (len == 0 || fwrite(low.data(), 1, len, f) == len);
+  }
+  ok = ok && fwrite(&nc, 8, 1, f) == 1 && fwrite(C.cubin.data(), 1, nc, f) == nc;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str()); /* rename: readers never see a partial file */
+}
 }  // namespace
 
 /* "mci_jit_problem.h": every layout field of DevProblem as a compile-time constant / table */
@@ -171,6 +228,11 @@ int jit_compile(const DevProblem &P, const char *user_source, const std::vector<
   std::string key = prob + "\x01" + top;
   for (const auto &n : name_exprs) key += "\x01" + n;
   auto it = g_cache.find(key);
+  const std::string disk = it == g_cache.end() ? disk_cache_path(key) : std::string();
+  if (it == g_cache.end() && !disk.empty()) {
+    Compiled C;
+    if (disk_cache_load(disk, name_exprs.size(), C)) it = g_cache.emplace(key, std::move(C)).first;
+  }
   if (it == g_cache.end()) {
     std::vector<const char *> hsrc, hname;
     for (int i = 0; i < MCI_JIT_NUM_HEADERS; ++i) { hsrc.push_back(MCI_JIT_HEADER_SOURCES[i]); hname.push_back(MCI_JIT_HEADER_NAMES[i]); }
@@ -201,10 +263,11 @@ int jit_compile(const DevProblem &P, const char *user_source, const std::vector<
       C.lowered.push_back(low);
     }
     g_rtc.DestroyProgram(&prog);
-    if (const char *dump = getenv("MCIB200_JIT_DUMP")) { /* keep the cubin for cuobjdump -sass / -res-usage */
-      if (FILE *f = fopen(dump, "wb")) { fwrite(C.cubin.data(), 1, C.cubin.size(), f); fclose(f); }
-    }
+    if (!disk.empty()) disk_cache_store(disk, C);
     it = g_cache.emplace(key, std::move(C)).first;
+  }
+  if (const char *dump = getenv("MCIB200_JIT_DUMP")) { /* keep the cubin for cuobjdump -sass / -res-usage (tools/jit_sass.py) */
+    if (FILE *f = fopen(dump, "wb")) { fwrite(it->second.cubin.data(), 1, it->second.cubin.size(), f); fclose(f); }
   }
   if (compile_only) { kernels.clear(); return 0; } /* mci_jit_check: compile, do not load (no device needed) */
   /* one cudaLibrary per handle (context-bound); the cubin itself is cached */

@@ -5,6 +5,7 @@ GPU part: a user-source Gaussian reproduces the built-in one; jit=1 kernels pass
 as the ahead-of-time kernels."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -252,3 +253,36 @@ def test_fermik_user_integrand_end_to_end():
                         neval=2e6, niter=10, block=16, seed=5)
     assert abs(res.mean[0] - exact) < 6.0 * res.stdev[0], (res.mean[0], res.stdev[0], exact)
     assert res.stdev[0] < 0.02 * exact
+
+
+def test_disk_cache_round_trip(tmp_path):
+    """MCIB200_JIT_CACHE=<dir>: the first process builds with NVRTC and leaves <dir>/mcib200_sm100a_<hash>.cubin, the
+    second loads it (same lowered names, same cubin), a truncated file is ignored and rebuilt.  (CPU: compile only.)"""
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    prog = ("import sys, ctypes as C; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from mcintegration_jl_b200 import _abi\nfrom cases import make_spec\n"
+            "spec, _ = make_spec('product4', 'mcmc', walkers=64); spec.jit = 1\n"
+            "p, keep = spec.to_ctypes(); log = C.create_string_buffer(4096)\n"
+            "rc = _abi.load_library().mci_jit_check(C.byref(p), log, 4096); print(rc, log.value.decode()); sys.exit(rc != 0)\n"
+            % (os.path.dirname(here), here))
+    env = dict(os.environ, MCIB200_JIT_CACHE=str(tmp_path), MCIB200_JIT_DUMP=str(tmp_path / "dump.bin"))
+
+    def run():
+        r = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return open(tmp_path / "dump.bin", "rb").read()
+
+    first = run()
+    files = [f for f in os.listdir(tmp_path) if f.startswith("mcib200_sm100a_") and f.endswith(".cubin")]
+    assert len(files) == 1
+    path = tmp_path / files[0]
+    stored = open(path, "rb").read()
+    assert stored.endswith(first) and len(stored) > len(first)  # header (names) + the very cubin NVRTC produced
+    assert run() == first                                        # served from the file
+    assert open(path, "rb").read() == stored
+    open(path, "wb").write(stored[: len(stored) // 2])           # a torn file must not be trusted
+    assert len(run()) == len(first)
+    assert len(open(path, "rb").read()) == len(stored)           # ... and is replaced by a fresh build
