@@ -2,7 +2,10 @@
 """Time to solution of integrate() against neval (BASELINE C2, niter = 10, block = 16): the whole call — engine creation,
 10 x (fill, statistics to the host, train!) and the final average — on the GPU, next to the CPU port of the reference
 loop (oracle, all host cores) on the same problem.  Shows where the crossover lies for small jobs: the reference's
-default is neval = 1e4 (src/main.jl:74).  One JSON line per size."""
+default is neval = 1e4 (src/main.jl:74).  One JSON line per size.
+Lives under tests/ (not collected by pytest) because it runs the oracle as the CPU yardstick and checks the two means
+against each other: only tests/, smoke() and bench.py's CPU legs execute anything from oracle/.
+    python tests/perf_latency_sweep.py"""
 import json
 import os
 import sys
@@ -10,7 +13,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import mcintegration_jl_b200 as mci
 from mcintegration_jl_b200 import integrands
 from oracle_lib import oracle_integrate

@@ -193,6 +193,14 @@ def test_product_never_references_the_oracle():
                     assert bad not in txt, (fn, bad)
     needed = subprocess.run(["ldd", _abi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in needed
+    # the tuning and evidence scripts under tools/ run the product only: whatever needs the oracle as a yardstick lives in
+    # tests/ (tests/perf_latency_sweep.py) or is a CPU leg of bench.py
+    tools = os.path.join(ROOT, "tools")
+    for fn in os.listdir(tools):
+        if fn.endswith((".py", ".sh")):
+            txt = open(os.path.join(tools, fn)).read()
+            for bad in ("mci_oracle", "libmcioracle", "oracle_lib", "orc_create", "oracle_integrate", "OracleEngine"):
+                assert bad not in txt, (fn, bad)
 
 
 def test_missing_library_fails_loudly():

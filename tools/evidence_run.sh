@@ -32,7 +32,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # (4) BASELINE configs end to end, the reference's own timing workload, small-job latency, the kernel table
 python tools/run_configs.py > profiles/r2_baseline_configs.jsonl 2> $O/r2_baseline_configs.err
 python tools/cuba_benchmark.py > profiles/r2_cuba.jsonl 2> $O/r2_cuba.err
-python tools/latency_sweep.py > profiles/r2_time_to_solution.jsonl 2> $O/r2_latency.err
+python tests/perf_latency_sweep.py > profiles/r2_time_to_solution.jsonl 2> $O/r2_latency.err
 F=profiles/r2_fill_kernels_final.jsonl
 rm -f $F
 for c in "gauss10 vegas 26" "genz16_pool vegas 24" "product4 vegas 24"; do python tools/sweep_fill.py $c 8192 0,4,5,n 8 >> $F 2>> $O/r2_fill_final.err; done
