@@ -518,3 +518,11 @@ def test_handles_share_the_communicator_of_an_id():
     finally:
         c.close()
         mci.CudaEngine.comm_finalize()
+
+
+def test_integrate_reports_where_the_time_went():
+    """Result.timing (not in the reference): seconds spent creating the handle, attaching the communicator, and in the
+    iterations — what tools/run_configs_multi.py quotes its throughput over"""
+    res = mci.integrate(integrands.gauss_nd, var=mci.Continuous(-5.0, 5.0), dof=[[10]], solver="vegas", neval=1e4, niter=3, seed=7)
+    assert set(res.timing) == {"create_s", "comm_init_s", "iterations_s"}
+    assert all(0.0 <= v < 60.0 for v in res.timing.values()) and res.timing["iterations_s"] > 0.0
