@@ -33,6 +33,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/run_configs.py > profiles/r2_baseline_configs.jsonl 2> $O/r2_baseline_configs.err
 python tools/cuba_benchmark.py > profiles/r2_cuba.jsonl 2> $O/r2_cuba.err
 python tests/perf_latency_sweep.py > profiles/r2_time_to_solution.jsonl 2> $O/r2_latency.err
+python tools/vegas_benchmarks.py > profiles/r2_vegas_benchmarks.jsonl 2> $O/r2_vegas_benchmarks.err
 F=profiles/r2_fill_kernels_final.jsonl
 rm -f $F
 for c in "gauss10 vegas 26" "genz16_pool vegas 24" "product4 vegas 24"; do python tools/sweep_fill.py $c 8192 0,4,5,n 8 >> $F 2>> $O/r2_fill_final.err; done
@@ -41,5 +42,5 @@ for c in "product4 mcmc 22" "bubble vegasmc 22" "bubble mcmc 22" "bubble_fermik 
 # (5) compute-sanitizer over one small problem per kernel family
 (compute-sanitizer --tool memcheck python tools/sanitize_smoke.py; compute-sanitizer --tool racecheck python tools/sanitize_smoke.py) > profiles/r2_compute_sanitizer.txt 2>&1
 cp profiles/r2_*ncu.json profiles/r2_ncu_*.txt profiles/r2_bench_n1.json profiles/r2_bench_reference_arm.json profiles/r2_launches_bench_steps2.csv \
-   profiles/r2_baseline_configs.jsonl profiles/r2_cuba.jsonl profiles/r2_time_to_solution.jsonl $F profiles/r2_compute_sanitizer.txt $O/profiles/
+   profiles/r2_baseline_configs.jsonl profiles/r2_cuba.jsonl profiles/r2_time_to_solution.jsonl profiles/r2_vegas_benchmarks.jsonl $F profiles/r2_compute_sanitizer.txt $O/profiles/
 tail -c 300 profiles/r2_bench_n1.json; echo; tail -3 profiles/r2_compute_sanitizer.txt; cat $O/r2_make_ncu.err | tail -5
